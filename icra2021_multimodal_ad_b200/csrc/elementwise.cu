@@ -1,0 +1,241 @@
+// Small HBM-bound helpers around the GEMM chain: operand packing, score finalisation,
+// NAP statistics.  All are grid-stride / coalesced; none is on the critical path.
+#include "mmad_internal.cuh"
+
+namespace mmad {
+
+namespace {
+
+__device__ __forceinline__ void split_half(float v, __half& h, __half& l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn(v - __half2float(h));
+}
+
+// x [n, D] (row stride ldx) -> zero-padded fp32 [n, ldp] and/or fp16 hi/lo [n, ldh]
+__global__ void pad_split_kernel(const float* __restrict__ x, int ldx, int n, int D, float* __restrict__ xp, int ldp,
+                                 __half* __restrict__ xh, __half* __restrict__ xl, int ldh) {
+    const int cols = xp ? ldp : ldh;
+    const size_t total = (size_t)n * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / cols), c = (int)(i % cols);
+        float v = c < D ? x[(size_t)r * ldx + c] : 0.f;
+        if (xp && c < ldp) xp[(size_t)r * ldp + c] = v;
+        if (xh && c < ldh) {
+            __half h, l;
+            split_half(v, h, l);
+            xh[(size_t)r * ldh + c] = h;
+            if (xl) xl[(size_t)r * ldh + c] = l;
+        }
+    }
+}
+
+// W [N, K] fp32 -> (W * scale) split into fp16 hi/lo [N, Kp], zero padded
+__global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, int Kp, float scale,
+                                     __half* __restrict__ Wh, __half* __restrict__ Wl) {
+    const size_t total = (size_t)N * Kp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / Kp), c = (int)(i % Kp);
+        float v = c < K ? W[(size_t)r * K + c] * scale : 0.f;
+        __half h, l;
+        split_half(v, h, l);
+        Wh[i] = h;
+        Wl[i] = l;
+    }
+}
+
+__global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               int N, int Np, float* scale, float* shift) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    if (i < N) {
+        // eval BatchNorm1d: (a - mean) / sqrt(var + eps) * gamma + beta  ==  a * s + t
+        float s = gamma[i] / sqrtf(var[i] + eps);
+        scale[i] = s;
+        shift[i] = beta[i] - mean[i] * s;
+    } else {
+        scale[i] = 0.f;
+        shift[i] = 0.f;
+    }
+}
+
+__global__ void copy_pad_kernel(const float* src, int N, int Np, float* dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Np) dst[i] = i < N ? src[i] : 0.f;
+}
+
+// base[r] = inv_base * sum_{slots in [b_lo,b_hi)} part[slot][r];  sap likewise.
+// Fixed summation order -> deterministic scores.
+__global__ void finalize_scores_kernel(const float* __restrict__ part, int stride, int n, int b_lo, int b_hi,
+                                       int s_lo, int s_hi, float inv_base, float inv_sap, float* __restrict__ base,
+                                       float* __restrict__ sap) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (base) {
+        float a = 0.f;
+        for (int s = b_lo; s < b_hi; ++s) a += part[(size_t)s * stride + r];
+        base[r] = a * inv_base;
+    }
+    if (sap) {
+        float a = 0.f;
+        for (int s = s_lo; s < s_hi; ++s) a += part[(size_t)s * stride + r];
+        sap[r] = a * inv_sap;
+    }
+}
+
+__global__ void reduce_sum_all_kernel(const float* __restrict__ part, int stride, int n, int s_lo, int s_hi,
+                                      float* __restrict__ acc) {
+    // double accumulation inside the block, one atomic per block
+    double a = 0.0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+        for (int s = s_lo; s < s_hi; ++s) a += (double)part[(size_t)s * stride + r];
+    __shared__ double sm[256];
+    sm[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(acc, (float)sm[0]);
+}
+
+// sum[c] += sum_r d[r, c]  (fp64 accumulation; grid: x over columns, y over row slabs)
+__global__ void colsum_f64_kernel(const float* __restrict__ d, int ld, int n, int cols, double* __restrict__ sum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int rows_per = (n + gridDim.y - 1) / gridDim.y;
+    int r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    double a = 0.0;
+    for (int r = r0; r < r1; ++r) a += (double)d[(size_t)r * ld + c];
+    atomicAdd(&sum[c], a);
+}
+
+__global__ void gram_f64_accumulate_kernel(const float* __restrict__ g32, int ld32, int D, double* __restrict__ g64) {
+    const size_t total = (size_t)D * D;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / D), c = (int)(i % D);
+        g64[i] += (double)g32[(size_t)r * ld32 + c];
+    }
+}
+
+// NAP fit packing: B[j,:] = v_j (zero padded), colscale[j] = var_j^-1/2,
+// bias[j] = -(mu . v_j + mu2_j) * var_j^-1/2   (utils/normalize.py:36-45,72-103 folded)
+__global__ void nap_pack_kernel(const float* __restrict__ mu, const float* __restrict__ vt, const float* __restrict__ var,
+                                const float* __restrict__ mu2, int K, int D, int Dp, float* __restrict__ B,
+                                float* __restrict__ colscale, float* __restrict__ bias) {
+    const int j = blockIdx.x;
+    double dot = 0.0;
+    for (int c = threadIdx.x; c < Dp; c += blockDim.x) {
+        float v = c < D ? vt[(size_t)j * D + c] : 0.f;
+        B[(size_t)j * Dp + c] = v;
+        if (c < D) dot += (double)v * (double)mu[c];
+    }
+    __shared__ double sm[256];
+    sm[threadIdx.x] = dot;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float inv = 1.0f / sqrtf(var[j]);
+        colscale[j] = inv;
+        bias[j] = -((float)sm[0] + mu2[j]) * inv;
+    }
+}
+
+__global__ void center_rows_kernel(float* __restrict__ d, int ld, int n, int cols, const float* __restrict__ mu) {
+    const size_t total = (size_t)n * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / cols), c = (int)(i % cols);
+        d[(size_t)r * ld + c] -= mu[c];
+    }
+}
+
+inline int grid_for(size_t total, int block = 256) {
+    size_t g = (total + block - 1) / block;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g == 0 ? 1 : g));
+}
+
+}  // namespace
+
+int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,
+              cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    size_t total = (size_t)n * (xp ? ldp : ldh);
+    pad_split_kernel<<<grid_for(total), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s) {
+    split_weights_kernel<<<grid_for((size_t)N * Kp), 256, 0, s>>>(W, N, K, Kp, scale, Wh, Wl);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int N, int Np,
+            float* scale, float* shift, cudaStream_t s) {
+    fold_bn_kernel<<<(Np + 255) / 256, 256, 0, s>>>(gamma, beta, mean, var, eps, N, Np, scale, shift);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s) {
+    copy_pad_kernel<<<(Np + 255) / 256, 256, 0, s>>>(src, N, Np, dst);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int finalize_scores(const float* rowpart, int stride, int n, int b_lo, int b_hi, int s_lo, int s_hi, float inv_base,
+                    float inv_sap, float* base, float* sap, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    finalize_scores_kernel<<<(n + 255) / 256, 256, 0, s>>>(rowpart, stride, n, b_lo, b_hi, s_lo, s_hi, inv_base,
+                                                           inv_sap, base, sap);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int finalize_sum(const float* rowpart, int stride, int n, int slot_lo, int slot_hi, float scale, float* out,
+                 cudaStream_t s) {
+    return finalize_scores(rowpart, stride, n, slot_lo, slot_hi, 0, 0, scale, 0.f, out, nullptr, s);
+}
+
+int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slot_hi, float* acc, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    int g = (n + 255) / 256;
+    if (g > 64) g = 64;
+    reduce_sum_all_kernel<<<g, 256, 0, s>>>(rowpart, stride, n, slot_lo, slot_hi, acc);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    dim3 grid((cols + 127) / 128, n >= 4096 ? 32 : (n >= 256 ? 8 : 1));
+    colsum_f64_kernel<<<grid, 128, 0, s>>>(d, ld, n, cols, sum);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp, float* B,
+             float* colscale, float* bias, cudaStream_t s) {
+    nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, B, colscale, bias);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStream_t s) {
+    size_t total = (size_t)D * D;
+    gram_f64_accumulate_kernel<<<grid_for(total), 256, 0, s>>>(g32, ld32, D, g64);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int center_rows(float* d, int ld, int n, int cols, const float* mu, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    center_rows_kernel<<<grid_for((size_t)n * cols), 256, 0, s>>>(d, ld, n, cols, mu);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+}  // namespace mmad

@@ -1,0 +1,752 @@
+// libmmad.so -- C ABI (include/mmad.h): handle, weight packing, workspace planning and
+// the orchestration of the fused layer chain
+//     enc(x) -> dec -> [d_0 = xhat - x] -> enc(xhat) with per-layer diff epilogues
+// (reference: reconstruction_aggregation.py:6-37, utils/metric.py:132-222).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "mmad_internal.cuh"
+
+namespace mmad {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct Layer {
+    int K = 0, N = 0, Kp = 0, Np = 0;
+    bool has_bn = false, loaded = false;
+    float* W = nullptr;       // [N, Kp] fp32, zero padded
+    float* bias = nullptr;    // [Np]
+    float* scale = nullptr;   // [Np] eval-BN scale  gamma / sqrt(var+eps)
+    float* shift = nullptr;   // [Np] eval-BN shift  beta - mean*scale
+    __half* Wh = nullptr;     // [N, Kp] fp16 hi of W * wscale
+    __half* Wl = nullptr;     // [N, Kp] fp16 lo
+    float wscale = 1.f;
+    TcOperand tcB;
+    bool tc_ready = false;
+};
+
+struct NapFit {
+    bool ready = false;
+    int lo = 0, hi = 0, K = 0, D = 0, Dp = 0;
+    float* B = nullptr;         // [K, Dp] rows v_j
+    float* colscale = nullptr;  // [K] var_j^-1/2
+    float* bias = nullptr;      // [K] -(mu.v_j + mu2_j) var_j^-1/2
+    float wscale = 256.f;
+    __half* Bh = nullptr;
+    __half* Bl = nullptr;
+    TcOperand tcB;
+    bool tc_ready = false;
+};
+
+}  // namespace mmad
+
+using namespace mmad;
+
+struct mmad_handle {
+    mmad_desc_t desc;
+    int device = 0;
+    std::vector<Layer> enc, dec;
+    NapFit nap;
+    // mmad_score_host staging (allocated on first use, kept)
+    void* host_ws = nullptr;
+    size_t host_ws_bytes = 0;
+    float* host_x[2] = {nullptr, nullptr};
+    float* host_out[2] = {nullptr, nullptr};
+    int host_chunk = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+namespace mmad {
+
+constexpr int kMaxChunk = 16384;
+constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
+
+static int D_of(mmad_t h) { return h->desc.enc_widths[0]; }
+static int width_of_diff(mmad_t h, int l) { return h->desc.enc_widths[l]; }   // d_0 has width D, d_l width w_l
+
+static int concat_width(mmad_t h, int lo, int hi) {
+    int s = 0;
+    for (int l = lo; l < hi; ++l) s += width_of_diff(h, l);
+    return s;
+}
+
+static void free_layer(Layer& L) {
+    cudaFree(L.W); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); cudaFree(L.Wh); cudaFree(L.Wl);
+    L = Layer();
+}
+
+// ------------------------------------------------------------------------------------
+// workspace plan
+// ------------------------------------------------------------------------------------
+struct Plan {
+    size_t total = 0;
+    int R = 0;
+    // fp32 buffers
+    size_t xp = 0;
+    size_t H[MMAD_MAX_LAYERS + 1] = {0};   // enc(x) outputs, index 1..L
+    size_t G[MMAD_MAX_LAYERS + 1] = {0};   // decoder outputs, index 1..Ld
+    size_t E[MMAD_MAX_LAYERS + 1] = {0};   // enc(xhat) outputs, index 1..L
+    size_t rowpart = 0;
+    size_t diffs = 0;
+    size_t gram32 = 0;
+    // fp16 hi/lo twins (tensor-core modes)
+    size_t xh = 0, xl = 0;
+    size_t Hh[MMAD_MAX_LAYERS + 1] = {0}, Hl[MMAD_MAX_LAYERS + 1] = {0};
+    size_t Gh[MMAD_MAX_LAYERS + 1] = {0}, Gl[MMAD_MAX_LAYERS + 1] = {0};
+    size_t Eh[MMAD_MAX_LAYERS + 1] = {0}, El[MMAD_MAX_LAYERS + 1] = {0};
+    size_t dh = 0, dl = 0;
+    int slot_off[MMAD_MAX_LAYERS + 3] = {0};   // rowpart slot ranges per diff index, then NAP slots
+    int n_slots = 0;
+    int Dselp = 0;
+};
+
+struct PlanOpts {
+    int lo = 0, hi = 0;
+    bool diffs_ws = false;   // concatenated diffs materialised in the workspace
+    bool gram = false;
+    bool tc = false;
+};
+
+static int tile_n_for(mmad_t h) {
+    return h->desc.precision == MMAD_PREC_FP32 ? gemm_simt_tile_n() : gemm_tc_tile_n();
+}
+
+static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
+    Plan p;
+    p.R = R;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += round_up_sz(bytes, 256);
+        return at;
+    };
+    const int L = h->desc.n_enc, Ld = h->desc.n_dec;
+    const int Dp = round_up(D_of(h), kPad);
+    const size_t RR = (size_t)R;
+    p.xp = take(RR * Dp * 4);
+    for (int l = 1; l <= L; ++l) p.H[l] = take(RR * h->enc[l - 1].Np * 4);
+    for (int l = 1; l <= Ld; ++l) p.G[l] = take(RR * h->dec[l - 1].Np * 4);
+    for (int l = 1; l <= L; ++l) p.E[l] = take(RR * h->enc[l - 1].Np * 4);
+    const int tn = tile_n_for(h);
+    int slots = 0;
+    for (int l = 0; l <= L; ++l) {
+        p.slot_off[l] = slots;
+        slots += (width_of_diff(h, l) + tn - 1) / tn;
+    }
+    p.slot_off[L + 1] = slots;
+    int nap_k = h->nap.ready ? h->nap.K : concat_width(h, 0, L + 1);
+    slots += (nap_k + tn - 1) / tn;
+    p.slot_off[L + 2] = slots;
+    p.n_slots = slots;
+    p.rowpart = take((size_t)slots * RR * 4);
+    p.Dselp = round_up(std::max(1, concat_width(h, o.lo, o.hi)), kPad);
+    if (o.diffs_ws) p.diffs = take(RR * p.Dselp * 4);
+    if (o.gram) p.gram32 = take((size_t)concat_width(h, o.lo, o.hi) * p.Dselp * 4);
+    if (o.tc) {
+        p.xh = take(RR * Dp * 2);
+        p.xl = take(RR * Dp * 2);
+        for (int l = 1; l <= L; ++l) { p.Hh[l] = take(RR * h->enc[l - 1].Np * 2); p.Hl[l] = take(RR * h->enc[l - 1].Np * 2); }
+        for (int l = 1; l <= Ld; ++l) { p.Gh[l] = take(RR * h->dec[l - 1].Np * 2); p.Gl[l] = take(RR * h->dec[l - 1].Np * 2); }
+        for (int l = 1; l <= L; ++l) { p.Eh[l] = take(RR * h->enc[l - 1].Np * 2); p.El[l] = take(RR * h->enc[l - 1].Np * 2); }
+        if (o.diffs_ws) { p.dh = take(RR * p.Dselp * 2); p.dl = take(RR * p.Dselp * 2); }
+    }
+    p.total = off;
+    return p;
+}
+
+static int pick_chunk(mmad_t h, int n, size_t ws_bytes, const PlanOpts& o, Plan* out) {
+    int R = std::min(std::max(n, 1), kMaxChunk);
+    R = round_up(R, 128);
+    while (true) {
+        Plan p = make_plan(h, R, o);
+        if (p.total <= ws_bytes) { *out = p; return MMAD_OK; }
+        if (R <= 128) {
+            set_error("workspace too small: %zu bytes given, %zu needed for a 128-row chunk", ws_bytes, p.total);
+            return MMAD_E_WORKSPACE;
+        }
+        R = round_up(R / 2, 128);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// one fused layer:  out = epi(in . W^T)
+// ------------------------------------------------------------------------------------
+struct Act {            // an activation matrix in the workspace (or the caller's x)
+    const float* f = nullptr; int ld = 0;
+    const __half* h = nullptr; const __half* l = nullptr; int ldh = 0;
+};
+
+static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogue e, cudaStream_t s) {
+    e.bias = Lr.bias;
+    if (Lr.has_bn) { e.bn_scale = Lr.scale; e.bn_shift = Lr.shift; }
+    e.slope = h->desc.lrelu_slope;
+    if (h->desc.precision == MMAD_PREC_FP32) {
+        GemmShape g;
+        g.M = rows; g.N = Lr.N; g.K = Lr.K;
+        g.A = in.f; g.lda = in.ld;
+        g.B = Lr.W; g.ldb = Lr.Kp;
+        e.acc_scale = 1.f;
+        return gemm_simt(g, e, s);
+    }
+    // tensor-core path: TMA descriptors over the fp16 hi/lo twins
+    TcOperand A;
+    int rc = tc_make_operand_map(&A.hi, in.h, rows, Lr.K, in.ldh, 128);
+    if (rc) return rc;
+    rc = tc_make_operand_map(&A.lo, in.l ? in.l : in.h, rows, Lr.K, in.ldh, 128);
+    if (rc) return rc;
+    A.rows = rows; A.k = Lr.K;
+    e.acc_scale = 1.f / Lr.wscale;
+    return gemm_tc(A, Lr.tcB, rows, Lr.N, Lr.K, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
+}
+
+// What a chain invocation should produce for one chunk.
+struct ChainOut {
+    float* xhat = nullptr; int ldxhat = 0;      // caller buffer for the reconstruction
+    float* z = nullptr; int ldz = 0;            // caller buffer for the code
+    bool need_d0 = false;                       // row sums of d_0^2 into rowpart slots of l=0
+    int lo = 0, hi = 0;                         // diffs [lo,hi) wanted (row sums and/or values)
+    bool need_rowsums = false;
+    float* dout = nullptr; int lddout = 0;      // concatenated diffs destination (caller or workspace)
+    __half* dh = nullptr; __half* dl = nullptr; int lddh = 0;
+};
+
+static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, const Plan& p, const ChainOut& co,
+                     cudaStream_t s) {
+    const int L = h->desc.n_enc, Ld = h->desc.n_dec, D = D_of(h);
+    const int Dp = round_up(D, kPad);
+    const bool tc = h->desc.precision != MMAD_PREC_FP32;
+    const bool x_direct = !tc && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    Act a0;
+    if (x_direct) {
+        a0.f = x; a0.ld = ldx;
+    } else {
+        int rc = pad_split(x, ldx, rows, D, (float*)(ws + p.xp), Dp, tc ? (__half*)(ws + p.xh) : nullptr,
+                           tc ? (__half*)(ws + p.xl) : nullptr, Dp, s);
+        if (rc) return rc;
+        a0.f = (const float*)(ws + p.xp); a0.ld = Dp;
+        a0.h = (const __half*)(ws + p.xh); a0.l = (const __half*)(ws + p.xl); a0.ldh = Dp;
+    }
+    const bool want_enc2 = co.hi > 1 && co.hi > co.lo;   // any d_l with l>=1 requested
+    // ---- encoder on x ----
+    Act cur = a0;
+    for (int l = 1; l <= L; ++l) {
+        const Layer& Lr = h->enc[l - 1];
+        Epilogue e;
+        e.Y = (float*)(ws + p.H[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
+        if (tc) { e.Yh = (__half*)(ws + p.Hh[l]); e.Yl = (__half*)(ws + p.Hl[l]); e.ldh = Lr.Np; }
+        int rc = run_layer(h, Lr, cur, rows, e, s);
+        if (rc) return rc;
+        cur = Act{e.Y, Lr.Np, e.Yh, e.Yl, Lr.Np};
+    }
+    if (co.z) {
+        MMAD_CUDA_OK(cudaMemcpy2DAsync(co.z, (size_t)co.ldz * 4, ws + p.H[L], (size_t)h->enc[L - 1].Np * 4,
+                                       (size_t)h->enc[L - 1].N * 4, rows, cudaMemcpyDeviceToDevice, s));
+    }
+    // ---- decoder ----
+    int col_off = 0;
+    for (int l = 1; l <= Ld; ++l) {
+        const Layer& Lr = h->dec[l - 1];
+        Epilogue e;
+        e.Y = (float*)(ws + p.G[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
+        if (tc) { e.Yh = (__half*)(ws + p.Gh[l]); e.Yl = (__half*)(ws + p.Gl[l]); e.ldh = Lr.Np; }
+        if (l == Ld && (co.need_d0 || (co.lo == 0 && co.hi > 0))) {
+            e.ref = a0.f; e.ldref = a0.ld;
+            e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[0] * p.R; e.rowpart_stride = p.R;
+            if (co.lo == 0 && co.hi > 0) {
+                if (co.dout) { e.dout = co.dout; e.lddout = co.lddout; }
+                if (co.dh) { e.Dh = co.dh; e.Dl = co.dl; e.lddh = co.lddh; e.d_scale = kDiffScale; }
+            }
+        }
+        int rc = run_layer(h, Lr, cur, rows, e, s);
+        if (rc) return rc;
+        cur = Act{e.Y, Lr.Np, e.Yh, e.Yl, Lr.Np};
+    }
+    if (co.lo == 0 && co.hi > 0) col_off = D;
+    if (co.xhat) {
+        MMAD_CUDA_OK(cudaMemcpy2DAsync(co.xhat, (size_t)co.ldxhat * 4, ws + p.G[Ld], (size_t)h->dec[Ld - 1].Np * 4,
+                                       (size_t)D * 4, rows, cudaMemcpyDeviceToDevice, s));
+    }
+    if (!want_enc2) return MMAD_OK;
+    // ---- encoder on xhat, diff epilogues against the stashed enc(x) activations ----
+    const int last = std::min(L, co.hi - 1);
+    for (int l = 1; l <= last; ++l) {
+        const Layer& Lr = h->enc[l - 1];
+        Epilogue e;
+        e.Y = (float*)(ws + p.E[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
+        if (tc) { e.Yh = (__half*)(ws + p.Eh[l]); e.Yl = (__half*)(ws + p.El[l]); e.ldh = Lr.Np; }
+        if (l == last) { e.Y = nullptr; e.Yh = nullptr; e.Yl = nullptr; }   // nothing consumes it
+        if (l >= co.lo) {
+            e.ref = (const float*)(ws + p.H[l]); e.ldref = Lr.Np;
+            e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[l] * p.R; e.rowpart_stride = p.R;
+            if (co.dout) { e.dout = co.dout + col_off; e.lddout = co.lddout; }
+            if (co.dh) { e.Dh = co.dh + col_off; e.Dl = co.dl + col_off; e.lddh = co.lddh; e.d_scale = kDiffScale; }
+            col_off += Lr.N;
+        }
+        int rc = run_layer(h, Lr, cur, rows, e, s);
+        if (rc) return rc;
+        cur = Act{(const float*)(ws + p.E[l]), Lr.Np, (const __half*)(ws + p.Eh[l]), (const __half*)(ws + p.El[l]), Lr.Np};
+    }
+    return MMAD_OK;
+}
+
+static int check_ready(mmad_t h) {
+    if (!h) { set_error("null handle"); return MMAD_E_ARG; }
+    for (auto& L : h->enc) if (!L.loaded) { set_error("encoder layer weights not loaded (mmad_set_layer)"); return MMAD_E_STATE; }
+    for (auto& L : h->dec) if (!L.loaded) { set_error("decoder layer weights not loaded (mmad_set_layer)"); return MMAD_E_STATE; }
+    return MMAD_OK;
+}
+
+static int check_range(mmad_t h, int lo, int hi) {
+    if (lo < 0 || hi <= lo || hi > h->desc.n_enc + 1) {
+        set_error("layer range [%d,%d) invalid for %d diffs (apply the reference clamp first)", lo, hi, h->desc.n_enc + 1);
+        return MMAD_E_ARG;
+    }
+    return MMAD_OK;
+}
+
+}  // namespace mmad
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char* mmad_last_error(void) { return g_err; }
+int mmad_version(void) { return 100; }
+
+int mmad_create(const mmad_desc_t* d, mmad_t* out) {
+    if (!d || !out) { set_error("null argument"); return MMAD_E_ARG; }
+    if (d->n_enc < 1 || d->n_dec < 1 || d->n_enc > MMAD_MAX_LAYERS || d->n_dec > MMAD_MAX_LAYERS) {
+        set_error("layer counts out of range"); return MMAD_E_ARG;
+    }
+    if (d->enc_widths[0] != d->dec_widths[d->n_dec]) {
+        set_error("decoder output width %d != input width %d", d->dec_widths[d->n_dec], d->enc_widths[0]);
+        return MMAD_E_ARG;
+    }
+    for (int i = 0; i <= d->n_enc; ++i) if (d->enc_widths[i] < 1) { set_error("bad encoder width"); return MMAD_E_ARG; }
+    for (int i = 0; i <= d->n_dec; ++i) if (d->dec_widths[i] < 1) { set_error("bad decoder width"); return MMAD_E_ARG; }
+    if (d->precision < MMAD_PREC_FP32 || d->precision > MMAD_PREC_F16) { set_error("bad precision"); return MMAD_E_ARG; }
+    int dev = 0;
+    MMAD_CUDA_OK(cudaGetDevice(&dev));
+    if (d->precision != MMAD_PREC_FP32 && !tc_available()) {
+        set_error("tensor-core precision requested but the device is not sm_100"); return MMAD_E_UNSUPPORTED;
+    }
+    mmad_handle* h = new mmad_handle();
+    h->desc = *d;
+    h->device = dev;
+    h->enc.resize(d->n_enc);
+    h->dec.resize(d->n_dec);
+    auto init = [&](std::vector<Layer>& v, const int* w, int n) -> int {
+        for (int i = 0; i < n; ++i) {
+            Layer& L = v[i];
+            L.K = w[i]; L.N = w[i + 1];
+            L.Kp = round_up(L.K, kPad); L.Np = round_up(L.N, kPad);
+            L.has_bn = i < n - 1;
+            MMAD_CUDA_OK(cudaMalloc(&L.W, (size_t)L.N * L.Kp * 4));
+            MMAD_CUDA_OK(cudaMalloc(&L.bias, (size_t)L.Np * 4));
+            MMAD_CUDA_OK(cudaMalloc(&L.scale, (size_t)L.Np * 4));
+            MMAD_CUDA_OK(cudaMalloc(&L.shift, (size_t)L.Np * 4));
+            MMAD_CUDA_OK(cudaMalloc(&L.Wh, (size_t)L.N * L.Kp * 2));
+            MMAD_CUDA_OK(cudaMalloc(&L.Wl, (size_t)L.N * L.Kp * 2));
+        }
+        return MMAD_OK;
+    };
+    int rc = init(h->enc, d->enc_widths, d->n_enc);
+    if (!rc) rc = init(h->dec, d->dec_widths, d->n_dec);
+    if (rc) { mmad_destroy(h); return rc; }
+    *out = h;
+    return MMAD_OK;
+}
+
+int mmad_destroy(mmad_t h) {
+    if (!h) return MMAD_OK;
+    for (auto& L : h->enc) free_layer(L);
+    for (auto& L : h->dec) free_layer(L);
+    cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.Bh); cudaFree(h->nap.Bl);
+    cudaFree(h->host_ws);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->host_x[i]); cudaFree(h->host_out[i]);
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    delete h;
+    return MMAD_OK;
+}
+
+int mmad_set_precision(mmad_t h, int precision) {
+    if (!h) { set_error("null handle"); return MMAD_E_ARG; }
+    if (precision < MMAD_PREC_FP32 || precision > MMAD_PREC_F16) { set_error("bad precision"); return MMAD_E_ARG; }
+    if (precision != MMAD_PREC_FP32 && !tc_available()) {
+        set_error("tensor-core precision requested but the device is not sm_100"); return MMAD_E_UNSUPPORTED;
+    }
+    h->desc.precision = precision;
+    return MMAD_OK;
+}
+
+int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const float* d_b, const float* d_gamma,
+                   const float* d_beta, const float* d_mean, const float* d_var, void* stream) {
+    if (!h || !d_W || !d_b) { set_error("null argument"); return MMAD_E_ARG; }
+    auto& v = module == 0 ? h->enc : h->dec;
+    if (module < 0 || module > 1 || index < 0 || index >= (int)v.size()) { set_error("bad layer index"); return MMAD_E_ARG; }
+    Layer& L = v[index];
+    if (L.has_bn != (d_gamma != nullptr)) {
+        set_error("layer %d.%d: BatchNorm tensors %s", module, index, L.has_bn ? "missing" : "unexpected");
+        return MMAD_E_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    MMAD_CUDA_OK(cudaMemsetAsync(L.W, 0, (size_t)L.N * L.Kp * 4, s));
+    MMAD_CUDA_OK(cudaMemcpy2DAsync(L.W, (size_t)L.Kp * 4, d_W, (size_t)L.K * 4, (size_t)L.K * 4, L.N,
+                                   cudaMemcpyDeviceToDevice, s));
+    int rc = copy_pad_vec(d_b, L.N, L.Np, L.bias, s);
+    if (rc) return rc;
+    if (L.has_bn) {
+        if (!d_beta || !d_mean || !d_var) { set_error("incomplete BatchNorm tensors"); return MMAD_E_ARG; }
+        rc = fold_bn(d_gamma, d_beta, d_mean, d_var, h->desc.bn_eps, L.N, L.Np, L.scale, L.shift, s);
+        if (rc) return rc;
+    }
+    // fp16 hi/lo twins of the weights, pre-scaled by a power of two so that the lo parts stay
+    // in the fp16 normal range (|W| <= 1/sqrt(K); 2^8 puts max|W'| at a few tens)
+    L.wscale = 256.f;
+    rc = split_weights(d_W, L.N, L.K, L.Kp, L.wscale, L.Wh, L.Wl, s);
+    if (rc) return rc;
+    L.tc_ready = false;
+    if (tc_available()) {
+        rc = tc_make_operand_map(&L.tcB.hi, L.Wh, L.N, L.K, L.Kp, gemm_tc_tile_n());
+        if (!rc) rc = tc_make_operand_map(&L.tcB.lo, L.Wl, L.N, L.K, L.Kp, gemm_tc_tile_n());
+        if (rc) return rc;
+        L.tcB.rows = L.N; L.tcB.k = L.K;
+        L.tc_ready = true;
+    }
+    L.loaded = true;
+    return MMAD_OK;
+}
+
+int mmad_fc_layer_forward(const float* d_x, int ldx, int n, int K, int N, const float* d_W, const float* d_b,
+                          const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var,
+                          float slope, float eps, float* d_y, int ldy, void* stream) {
+    if (!d_x || !d_W || !d_y || n < 0 || K < 1 || N < 1 || ldx < K || ldy < N) { set_error("bad argument"); return MMAD_E_ARG; }
+    if (d_gamma && (!d_beta || !d_mean || !d_var)) { set_error("incomplete BatchNorm tensors"); return MMAD_E_ARG; }
+    GemmShape g;
+    g.M = n; g.N = N; g.K = K; g.A = d_x; g.lda = ldx; g.B = d_W; g.ldb = K;
+    Epilogue e;
+    e.bias = d_b;
+    if (d_gamma) { e.bn_scale = d_gamma; e.bn_shift = d_beta; e.bn_mean = d_mean; e.bn_var = d_var; e.bn_eps = eps; }
+    e.slope = slope;
+    e.Y = d_y; e.ldy = ldy; e.y_cols = N;
+    return gemm_simt(g, e, (cudaStream_t)stream);
+}
+
+size_t mmad_workspace_bytes(mmad_t h, int max_rows) {
+    if (!h || max_rows < 1) return 0;
+    PlanOpts o;
+    o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.gram = false; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
+    int R = round_up(std::min(max_rows, kMaxChunk), 128);
+    return make_plan(h, R, o).total;
+}
+
+int mmad_concat_width(mmad_t h, int lo, int hi) {
+    if (!h || check_range(h, lo, hi)) return MMAD_E_ARG;
+    return concat_width(h, lo, hi);
+}
+
+int mmad_ae_forward(mmad_t h, const float* d_x, int ldx, int n, float* d_xhat, float* d_z, void* d_ws,
+                    size_t ws_bytes, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (n < 0 || !d_x || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    PlanOpts o; o.tc = h->desc.precision != MMAD_PREC_FP32;
+    o.lo = 0; o.hi = 1;
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        ChainOut co;
+        co.lo = 0; co.hi = 0;
+        if (d_xhat) { co.xhat = d_xhat + (size_t)r0 * D_of(h); co.ldxhat = D_of(h); }
+        if (d_z) { co.z = d_z + (size_t)r0 * h->desc.enc_widths[h->desc.n_enc]; co.ldz = h->desc.enc_widths[h->desc.n_enc]; }
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, (char*)d_ws, p, co, (cudaStream_t)stream);
+        if (rc) return rc;
+        r0 += rows;
+    }
+    return MMAD_OK;
+}
+
+int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss, void* d_ws, size_t ws_bytes,
+                    void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (n < 0 || !d_x || !d_loss || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
+    PlanOpts o; o.tc = h->desc.precision != MMAD_PREC_FP32;
+    o.lo = 0; o.hi = 1;
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        ChainOut co;
+        co.need_d0 = true; co.lo = 0; co.hi = 0;
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, (char*)d_ws, p, co, s);
+        if (rc) return rc;
+        rc = reduce_sum_all((const float*)((char*)d_ws + p.rowpart), p.R, rows, p.slot_off[0], p.slot_off[1], d_loss, s);
+        if (rc) return rc;
+        r0 += rows;
+    }
+    return MMAD_OK;
+}
+
+static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, cudaStream_t s) {
+    const NapFit& f = h->nap;
+    const int L = h->desc.n_enc;
+    Epilogue e;
+    e.bias = f.bias;
+    e.col_scale = f.colscale;
+    e.sq_self = 1;
+    e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[L + 1] * p.R;
+    e.rowpart_stride = p.R;
+    int rc;
+    if (h->desc.precision == MMAD_PREC_FP32) {
+        GemmShape g;
+        g.M = rows; g.N = f.K; g.K = f.D;
+        g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp;
+        g.B = f.B; g.ldb = f.Dp;
+        rc = gemm_simt(g, e, s);
+    } else {
+        TcOperand A;
+        rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.D, p.Dselp, 128);
+        if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.D, p.Dselp, 128);
+        if (rc) return rc;
+        A.rows = rows; A.k = f.D;
+        e.acc_scale = 1.f / (f.wscale * kDiffScale);
+        rc = gemm_tc(A, f.tcB, rows, f.K, f.D, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
+    }
+    if (rc) return rc;
+    return finalize_sum((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[L + 1], p.slot_off[L + 2], 1.f / f.K,
+                        d_nap, s);
+}
+
+int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float* d_nap,
+               float* d_diffs, void* d_ws, size_t ws_bytes, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (n < 0 || !d_x || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    if (d_nap && !(h->nap.ready && h->nap.lo == lo && h->nap.hi == hi)) {
+        set_error("NAP requested but no fit installed for layers [%d,%d)", lo, hi);
+        return MMAD_E_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tc = h->desc.precision != MMAD_PREC_FP32;
+    PlanOpts o;
+    o.lo = lo; o.hi = hi; o.tc = tc; o.diffs_ws = d_nap != nullptr;
+    const int Dsel = concat_width(h, lo, hi);
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        char* ws = (char*)d_ws;
+        ChainOut co;
+        co.lo = (d_sap || d_nap || d_diffs) ? lo : 0;
+        co.hi = (d_sap || d_nap || d_diffs) ? hi : 0;
+        co.need_d0 = d_base != nullptr;
+        co.need_rowsums = d_sap != nullptr;
+        if (d_nap) {
+            co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
+            if (tc) { co.dh = (__half*)(ws + p.dh); co.dl = (__half*)(ws + p.dl); co.lddh = p.Dselp; }
+        } else if (d_diffs) {
+            co.dout = d_diffs + (size_t)r0 * Dsel; co.lddout = Dsel;
+        }
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
+        if (rc) return rc;
+        if (d_base || d_sap) {
+            rc = finalize_scores((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[0], p.slot_off[1],
+                                 p.slot_off[lo], p.slot_off[hi], 1.f / D_of(h), 1.f / Dsel,
+                                 d_base ? d_base + r0 : nullptr, d_sap ? d_sap + r0 : nullptr, s);
+            if (rc) return rc;
+        }
+        if (d_nap) {
+            if (d_diffs)
+                MMAD_CUDA_OK(cudaMemcpy2DAsync(d_diffs + (size_t)r0 * Dsel, (size_t)Dsel * 4, ws + p.diffs,
+                                               (size_t)p.Dselp * 4, (size_t)Dsel * 4, rows, cudaMemcpyDeviceToDevice, s));
+            rc = nap_gemm(h, p, ws, rows, d_nap + r0, s);
+            if (rc) return rc;
+        }
+        r0 += rows;
+    }
+    return MMAD_OK;
+}
+
+int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, double* d_sum, void* d_ws,
+                            size_t ws_bytes, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (!d_x || !d_sum || n < 0) { set_error("bad input"); return MMAD_E_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    PlanOpts o; o.lo = lo; o.hi = hi; o.tc = h->desc.precision != MMAD_PREC_FP32; o.diffs_ws = true;
+    const int Dsel = concat_width(h, lo, hi);
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        char* ws = (char*)d_ws;
+        ChainOut co; co.lo = lo; co.hi = hi;
+        co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
+        if (rc) return rc;
+        rc = colsum_f64((const float*)(ws + p.diffs), p.Dselp, rows, Dsel, d_sum, s);
+        if (rc) return rc;
+        r0 += rows;
+    }
+    return MMAD_OK;
+}
+
+int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, const float* d_mu,
+                             double* d_gram, void* d_ws, size_t ws_bytes, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (!d_x || !d_mu || !d_gram || n < 0) { set_error("bad input"); return MMAD_E_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    PlanOpts o; o.lo = lo; o.hi = hi; o.tc = h->desc.precision != MMAD_PREC_FP32; o.diffs_ws = true; o.gram = true;
+    const int Dsel = concat_width(h, lo, hi);
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        char* ws = (char*)d_ws;
+        ChainOut co; co.lo = lo; co.hi = hi;
+        co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
+        if (rc) return rc;
+        rc = center_rows((float*)(ws + p.diffs), p.Dselp, rows, Dsel, d_mu, s);
+        if (rc) return rc;
+        // G32 = Dc^T Dc : both operands are the [rows, Dsel] diff matrix read "transposed"
+        GemmShape g;
+        g.M = Dsel; g.N = Dsel; g.K = rows;
+        g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp; g.transA = true;
+        g.B = (const float*)(ws + p.diffs); g.ldb = p.Dselp; g.transB = true;
+        Epilogue e;
+        e.Y = (float*)(ws + p.gram32); e.ldy = p.Dselp; e.y_cols = Dsel;
+        rc = gemm_simt(g, e, s);
+        if (rc) return rc;
+        rc = gram_f64_accumulate((const float*)(ws + p.gram32), p.Dselp, Dsel, d_gram, s);
+        if (rc) return rc;
+        r0 += rows;
+    }
+    return MMAD_OK;
+}
+
+int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const float* d_vt, const float* d_var,
+                     const float* d_mu2, void* stream) {
+    if (!h || !d_mu || !d_vt || !d_var || !d_mu2) { set_error("null argument"); return MMAD_E_ARG; }
+    int rc = check_range(h, lo, hi);
+    if (rc) return rc;
+    const int D = concat_width(h, lo, hi);
+    if (K < 1 || K > D) { set_error("NAP fit: K=%d must be in [1,%d]", K, D); return MMAD_E_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NapFit& f = h->nap;
+    MMAD_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.Bh); cudaFree(f.Bl);
+    f = NapFit();
+    f.lo = lo; f.hi = hi; f.K = K; f.D = D; f.Dp = round_up(D, kPad);
+    MMAD_CUDA_OK(cudaMalloc(&f.B, (size_t)K * f.Dp * 4));
+    MMAD_CUDA_OK(cudaMalloc(&f.colscale, (size_t)round_up(K, kPad) * 4));
+    MMAD_CUDA_OK(cudaMalloc(&f.bias, (size_t)round_up(K, kPad) * 4));
+    MMAD_CUDA_OK(cudaMalloc(&f.Bh, (size_t)K * f.Dp * 2));
+    MMAD_CUDA_OK(cudaMalloc(&f.Bl, (size_t)K * f.Dp * 2));
+    rc = nap_pack(d_mu, d_vt, d_var, d_mu2, K, D, f.Dp, f.B, f.colscale, f.bias, s);
+    if (rc) return rc;
+    rc = split_weights(d_vt, K, D, f.Dp, f.wscale, f.Bh, f.Bl, s);
+    if (rc) return rc;
+    if (tc_available()) {
+        rc = tc_make_operand_map(&f.tcB.hi, f.Bh, K, D, f.Dp, gemm_tc_tile_n());
+        if (!rc) rc = tc_make_operand_map(&f.tcB.lo, f.Bl, K, D, f.Dp, gemm_tc_tile_n());
+        if (rc) return rc;
+        f.tcB.rows = K; f.tcB.k = D;
+        f.tc_ready = true;
+    }
+    f.ready = true;
+    return MMAD_OK;
+}
+
+// Host-buffer scoring: double-buffered H2D / compute / D2H over two internal streams.
+int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, int hi, float* h_base, float* h_sap,
+                    float* h_nap) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (!h_x || n < 0 || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    if (h_nap && !(h->nap.ready && h->nap.lo == lo && h->nap.hi == hi)) {
+        set_error("NAP requested but no fit installed for layers [%d,%d)", lo, hi);
+        return MMAD_E_STATE;
+    }
+    const int D = D_of(h);
+    const int chunk = (int)std::min<long long>(kMaxChunk, std::max<long long>(128, (n + 127) / 128 * 128));
+    if (!h->s_copy) {
+        MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MMAD_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            MMAD_CUDA_OK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+            MMAD_CUDA_OK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    size_t need_ws = mmad_workspace_bytes(h, chunk);
+    if (h->host_chunk < chunk || h->host_ws_bytes < need_ws) {
+        MMAD_CUDA_OK(cudaDeviceSynchronize());
+        cudaFree(h->host_ws); h->host_ws = nullptr;
+        for (int i = 0; i < 2; ++i) { cudaFree(h->host_x[i]); cudaFree(h->host_out[i]); h->host_x[i] = h->host_out[i] = nullptr; }
+        MMAD_CUDA_OK(cudaMalloc(&h->host_ws, need_ws));
+        for (int i = 0; i < 2; ++i) {
+            MMAD_CUDA_OK(cudaMalloc(&h->host_x[i], (size_t)chunk * D * 4));
+            MMAD_CUDA_OK(cudaMalloc(&h->host_out[i], (size_t)chunk * 3 * 4));
+        }
+        h->host_ws_bytes = need_ws;
+        h->host_chunk = chunk;
+    }
+    long long r0 = 0;
+    int it = 0;
+    for (; r0 < n; ++it) {
+        const int b = it & 1;
+        const int rows = (int)std::min<long long>(h->host_chunk, n - r0);
+        // input buffer b is free once the compute that read it two iterations ago is done
+        if (it >= 2) MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        MMAD_CUDA_OK(cudaMemcpy2DAsync(h->host_x[b], (size_t)D * 4, h_x + (size_t)r0 * ldx, (size_t)ldx * 4,
+                                       (size_t)D * 4, rows, cudaMemcpyHostToDevice, h->s_copy));
+        MMAD_CUDA_OK(cudaEventRecord(h->ev_in[b], h->s_copy));
+        MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_comp, h->ev_in[b], 0));
+        float* o = h->host_out[b];
+        rc = mmad_score(h, h->host_x[b], D, rows, lo, hi, h_base ? o : nullptr, h_sap ? o + h->host_chunk : nullptr,
+                        h_nap ? o + 2 * (size_t)h->host_chunk : nullptr, nullptr, h->host_ws, h->host_ws_bytes, h->s_comp);
+        if (rc) return rc;
+        MMAD_CUDA_OK(cudaEventRecord(h->ev_free[b], h->s_comp));
+        if (h_base) MMAD_CUDA_OK(cudaMemcpyAsync(h_base + r0, o, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        if (h_sap) MMAD_CUDA_OK(cudaMemcpyAsync(h_sap + r0, o + h->host_chunk, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        if (h_nap) MMAD_CUDA_OK(cudaMemcpyAsync(h_nap + r0, o + 2 * (size_t)h->host_chunk, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        r0 += rows;
+    }
+    MMAD_CUDA_OK(cudaStreamSynchronize(h->s_comp));
+    MMAD_CUDA_OK(cudaStreamSynchronize(h->s_copy));
+    return MMAD_OK;
+}
+
+}  // extern "C"

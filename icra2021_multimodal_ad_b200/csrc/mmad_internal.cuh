@@ -1,0 +1,102 @@
+// Internal declarations shared by the libmmad.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mmad.h"
+
+namespace mmad {
+
+void set_error(const char* fmt, ...);
+
+#define MMAD_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            mmad::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return MMAD_E_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+constexpr int kPad = 64;   // every activation / weight row is padded to a multiple of 64 elements
+
+// ---------------------------------------------------------------------------------------
+// Fused GEMM epilogue description (shared by the CUDA-core and the tcgen05 kernels).
+//   acc = sum_k A[m,k] * B[n,k]                 (B rows are output features: Y = X W^T)
+//   v   = acc * acc_scale * col_scale[n] + bias[n]
+//   if (act) v = leaky_relu(v) * bn_scale[n] + bn_shift[n]
+//   Y[m,n] = v (and fp16 hi/lo split copies for the tensor-core path)
+//   if (ref)  d = v - ref[m,n];  dout[m,n] = d;  rowpart[tile_n][m] = sum_n d^2
+//   if (sq_self) rowpart[tile_n][m] = sum_n v^2             (NAP rotation epilogue)
+// ---------------------------------------------------------------------------------------
+struct Epilogue {
+    const float* bias = nullptr;
+    const float* bn_scale = nullptr;   // non-null => LeakyReLU + BatchNorm affine
+    const float* bn_shift = nullptr;
+    const float* bn_mean = nullptr;    // non-null => bn_scale/bn_shift hold raw gamma/beta, folded in the epilogue
+    const float* bn_var = nullptr;
+    float bn_eps = 1e-5f;
+    float slope = 0.2f;
+    float acc_scale = 1.0f;
+    const float* col_scale = nullptr;  // optional per-column multiplier applied with acc_scale
+    float* Y = nullptr;  int ldy = 0;  int y_cols = 0;   // writes cols [0,y_cols); cols >= N are zero-filled
+    __half* Yh = nullptr; __half* Yl = nullptr; int ldh = 0;
+    const float* ref = nullptr; int ldref = 0;
+    float* dout = nullptr; int lddout = 0;
+    __half* Dh = nullptr; __half* Dl = nullptr; int lddh = 0;   // fp16 split of d * d_scale (NAP operand)
+    float d_scale = 1.0f;
+    float* rowpart = nullptr; int rowpart_stride = 0;   // [tiles_n][rowpart_stride]
+    int sq_self = 0;
+    float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
+};
+
+struct GemmShape {
+    int M, N, K;
+    const float* A; int lda;     // [M, K] (or [K, M] when transA)
+    const float* B; int ldb;     // [N, K] (or [K, N] when transB)
+    bool transA = false, transB = false;
+};
+
+// CUDA-core fp32 GEMM with the fused epilogue (gemm_simt.cu)
+int gemm_simt(const GemmShape& g, const Epilogue& e, cudaStream_t s);
+int gemm_simt_tile_n();   // columns covered by one rowpart slot
+
+// tcgen05 GEMM (gemm_tc.cu): operands are fp16 hi/lo pairs described by TMA maps.
+struct TcOperand {
+    CUtensorMap hi, lo;      // 2-D maps, box = [64 (K) x rows], 128B swizzle
+    int rows = 0, k = 0;
+};
+int tc_available();
+int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, int ld, int box_rows);
+int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
+            const Epilogue& e, cudaStream_t s);
+int gemm_tc_tile_n();
+
+// elementwise helpers (elementwise.cu)
+int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,
+              cudaStream_t s);
+int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s);
+int finalize_scores(const float* rowpart, int stride, int n, int slot_lo_base, int slot_hi_base,
+                    int sap_slot_lo, int sap_slot_hi, float inv_base, float inv_sap,
+                    float* base, float* sap, cudaStream_t s);
+int finalize_sum(const float* rowpart, int stride, int n, int slot_lo, int slot_hi, float scale, float* out,
+                 cudaStream_t s);
+int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slot_hi, float* acc, cudaStream_t s);
+int fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int N, int Np,
+            float* scale, float* shift, cudaStream_t s);
+int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s);
+int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_t s);
+int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStream_t s);
+int center_rows(float* d, int ld, int n, int cols, const float* mu, cudaStream_t s);
+int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp,
+             float* B, float* colscale, float* bias, cudaStream_t s);
+
+}  // namespace mmad

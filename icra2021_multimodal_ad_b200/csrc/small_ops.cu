@@ -1,0 +1,90 @@
+// Stand-alone HBM-bound ops of the path exposed through the C ABI: summed squared error,
+// per-row mean of squares, VIB reparameterisation.
+#include "mmad_internal.cuh"
+
+using namespace mmad;
+
+namespace {
+
+__global__ void sq_diff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                   float* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d = a[i] - b[i];
+        acc += (double)(d * d);
+    }
+    __shared__ double sm[256];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, (float)sm[0]);
+}
+
+// one warp per row, coalesced over columns
+__global__ void row_mean_sq_kernel(const float* __restrict__ d, int ld, int n, int cols, float* __restrict__ out) {
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= n) return;
+    const float* p = d + (size_t)row * ld;
+    float acc = 0.f;
+    for (int c = lane; c < cols; c += 32) acc = fmaf(p[c], p[c], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc / (float)cols;
+}
+
+__global__ void vib_kernel(const float* __restrict__ o, int ld, int B, int h, int k, const float* __restrict__ eps,
+                           float* __restrict__ z, float* __restrict__ mu, float* __restrict__ logvar) {
+    const long long total = (long long)B * h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(i / h), j = (int)(i % h);
+        float m = o[(size_t)b * ld + j];
+        float lv = o[(size_t)b * ld + h + j];
+        mu[i] = m;
+        logvar[i] = lv;
+        float sigma = expf(lv * 0.5f);
+        for (int kk = 0; kk < k; ++kk) {
+            size_t zi = (size_t)kk * total + i;
+            z[zi] = eps ? fmaf(eps[zi], sigma, m) : m;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_out, void* stream) {
+    if (!d_a || !d_b || !d_out || n < 0) { set_error("bad argument"); return MMAD_E_ARG; }
+    if (n == 0) return MMAD_OK;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 4) g = 148 * 4;
+    sq_diff_sum_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, d_out);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int mmad_row_mean_sq(const float* d_d, int ld, int n, int cols, float* d_out, void* stream) {
+    if (!d_d || !d_out || n < 0 || cols < 1 || ld < cols) { set_error("bad argument"); return MMAD_E_ARG; }
+    if (n == 0) return MMAD_OK;
+    row_mean_sq_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_d, ld, n, cols, d_out);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int mmad_vib_reparam(const float* d_out, int ld, int B, int h, int k, const float* d_eps, float* d_z, float* d_mu,
+                     float* d_logvar, void* stream) {
+    if (!d_out || !d_z || !d_mu || !d_logvar || B < 0 || h < 1 || ld < 2 * h) { set_error("bad argument"); return MMAD_E_ARG; }
+    if (k < 1) { set_error("k should be >= 1"); return MMAD_E_ARG; }
+    if (B == 0) return MMAD_OK;
+    long long total = (long long)B * h;
+    long long g = (total + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    vib_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_out, ld, B, h, k, d_eps, d_z, d_mu, d_logvar);
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Device engine: one ``mmad_t`` handle (packed weights + NAP fit) bound to a CUDA device.
+
+Thin host-side plumbing over the C ABI: torch owns device memory and streams, libmmad
+does the arithmetic.  Nothing here computes on the CPU or through torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Desc, PREC, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def clamp_layer_range(n_diffs: int, start: int, end: Optional[int]):
+    """utils/metric.py:155-162 followed by python slice semantics ``diffs[start:end]``."""
+    if end is None:
+        end = n_diffs + 1
+    if start > n_diffs - 1:
+        start = n_diffs - 1
+    if end - start < 1:
+        end = start + 1
+    lo, hi, _ = slice(start, end).indices(n_diffs)
+    return lo, hi
+
+
+class Engine:
+    def __init__(self, enc_widths: Sequence[int], dec_widths: Sequence[int], precision: str = "fp32",
+                 device: Optional[torch.device] = None, lrelu_slope: float = 0.2, bn_eps: float = 1e-5):
+        if not torch.cuda.is_available():
+            raise _lib.MmadError("icra2021_multimodal_ad_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.enc_widths, self.dec_widths = list(enc_widths), list(dec_widths)
+        d = Desc()
+        d.n_enc, d.n_dec = len(enc_widths) - 1, len(dec_widths) - 1
+        for i, w in enumerate(enc_widths):
+            d.enc_widths[i] = w
+        for i, w in enumerate(dec_widths):
+            d.dec_widths[i] = w
+        d.lrelu_slope, d.bn_eps, d.precision = lrelu_slope, bn_eps, PREC[precision]
+        self.precision = precision
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().mmad_create(C.byref(d), C.byref(self._h)))
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_rows = 0
+        self.nap_range = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().mmad_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------------
+    @property
+    def D(self) -> int:
+        return self.enc_widths[0]
+
+    @property
+    def n_diffs(self) -> int:
+        return len(self.enc_widths)
+
+    def set_precision(self, precision: str):
+        check(lib().mmad_set_precision(self._h, PREC[precision]))
+        self.precision = precision
+        self._ws = None
+        self._ws_rows = 0
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Pack a reference-format state dict (keys ``encoder.net.{i}.layer.weight`` ...)."""
+        with torch.cuda.device(self.device):
+            for m, prefix, widths in ((0, "encoder", self.enc_widths), (1, "decoder", self.dec_widths)):
+                for i in range(len(widths) - 1):
+                    def g(name):
+                        t = sd.get(f"{prefix}.net.{i}.{name}")
+                        if t is None:
+                            return None
+                        return t.detach().to(self.device, torch.float32).contiguous()
+                    W, b = g("layer.weight"), g("layer.bias")
+                    if W is None or tuple(W.shape) != (widths[i + 1], widths[i]):
+                        raise ValueError(f"{prefix}.net.{i}.layer.weight missing or wrong shape")
+                    bn = [g("bn.weight"), g("bn.bias"), g("bn.running_mean"), g("bn.running_var")]
+                    check(lib().mmad_set_layer(self._h, m, i, _ptr(W), _ptr(b), *[_ptr(t) for t in bn], _stream()))
+            torch.cuda.current_stream().synchronize()   # the temporaries above may be freed now
+
+    # ---- workspace ---------------------------------------------------------------------
+    def workspace(self, rows: int) -> torch.Tensor:
+        rows = max(128, min(int(rows), 16384))
+        if self._ws is None or rows > self._ws_rows:
+            nbytes = lib().mmad_workspace_bytes(self._h, rows)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_rows = rows
+        return self._ws
+
+    def _check_x(self, x: torch.Tensor) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise _lib.MmadError("input must be a CUDA tensor (no CPU path)")
+        if x.dim() != 2 or x.shape[1] != self.D:
+            raise ValueError(f"expected [n, {self.D}] input, got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < self.D):
+            x = x.contiguous()
+        return x
+
+    # ---- forward / loss ------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, want_code: bool = False):
+        x = self._check_x(x)
+        n = x.shape[0]
+        xhat = torch.empty(n, self.D, dtype=torch.float32, device=x.device)
+        z = torch.empty(n, self.enc_widths[-1], dtype=torch.float32, device=x.device) if want_code else None
+        ws = self.workspace(n)
+        with torch.cuda.device(self.device):
+            check(lib().mmad_ae_forward(self._h, x.data_ptr(), x.stride(0) if n > 1 else self.D, n, xhat.data_ptr(),
+                                        _ptr(z), ws.data_ptr(), ws.numel(), _stream()))
+        return (xhat, z) if want_code else xhat
+
+    def recon_loss(self, x: torch.Tensor) -> torch.Tensor:
+        x = self._check_x(x)
+        n = x.shape[0]
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        ws = self.workspace(n)
+        with torch.cuda.device(self.device):
+            check(lib().mmad_recon_loss(self._h, x.data_ptr(), x.stride(0) if n > 1 else self.D, n, out.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream()))
+        return out[0]
+
+    # ---- scoring ------------------------------------------------------------------------
+    def concat_width(self, lo: int, hi: int) -> int:
+        r = lib().mmad_concat_width(self._h, lo, hi)
+        if r < 0:
+            check(r)
+        return r
+
+    def score(self, x: torch.Tensor, lo: int = 0, hi: Optional[int] = None, base: bool = True, sap: bool = True,
+              nap: bool = False, diffs: bool = False) -> Dict[str, torch.Tensor]:
+        """Fused get_diffs + base/SAP/NAP scores for rows of ``x`` (device tensor)."""
+        x = self._check_x(x)
+        n = x.shape[0]
+        hi = self.n_diffs if hi is None else hi
+        out: Dict[str, torch.Tensor] = {}
+        mk = lambda: torch.empty(n, dtype=torch.float32, device=x.device)  # noqa: E731
+        if base:
+            out["base"] = mk()
+        if sap:
+            out["sap"] = mk()
+        if nap:
+            out["nap"] = mk()
+        if diffs:
+            out["diffs"] = torch.empty(n, self.concat_width(lo, hi), dtype=torch.float32, device=x.device)
+        ws = self.workspace(n)
+        with torch.cuda.device(self.device):
+            check(lib().mmad_score(self._h, x.data_ptr(), x.stride(0) if n > 1 else self.D, n, lo, hi,
+                                   _ptr(out.get("base")), _ptr(out.get("sap")), _ptr(out.get("nap")),
+                                   _ptr(out.get("diffs")), ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    def score_host(self, x: np.ndarray, lo: int = 0, hi: Optional[int] = None, base: bool = True, sap: bool = True,
+                   nap: bool = False) -> Dict[str, np.ndarray]:
+        """Host-buffer entry point (``mmad_score_host``): x is a C-contiguous fp32 ndarray (ideally in
+        pinned memory); returns host arrays.  H2D/compute/D2H are pipelined inside the library."""
+        if isinstance(x, torch.Tensor):
+            x = x.numpy()
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        hi = self.n_diffs if hi is None else hi
+        out = {k: np.empty(n, dtype=np.float32) for k, on in (("base", base), ("sap", sap), ("nap", nap)) if on}
+        p = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        with torch.cuda.device(self.device):
+            check(lib().mmad_score_host(self._h, x.ctypes.data, x.shape[1], n, lo, hi, p("base"), p("sap"), p("nap")))
+        return out
+
+    # ---- NAP fit ------------------------------------------------------------------------
+    def nap_accumulate_sum(self, x: torch.Tensor, lo: int, hi: int, acc: torch.Tensor):
+        x = self._check_x(x)
+        ws = self.workspace(x.shape[0])
+        with torch.cuda.device(self.device):
+            check(lib().mmad_nap_accumulate_sum(self._h, x.data_ptr(), x.stride(0) if x.shape[0] > 1 else self.D,
+                                                x.shape[0], lo, hi, acc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+
+    def nap_accumulate_gram(self, x: torch.Tensor, lo: int, hi: int, mu: torch.Tensor, gram: torch.Tensor):
+        x = self._check_x(x)
+        # the gram pass needs an extra [Dsel, Dsel] fp32 tile in the workspace
+        dsel = self.concat_width(lo, hi)
+        need = lib().mmad_workspace_bytes(self._h, min(max(x.shape[0], 128), 16384)) + dsel * (dsel + 64) * 4 + 4096
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_rows = 16384
+        ws = self._ws
+        with torch.cuda.device(self.device):
+            check(lib().mmad_nap_accumulate_gram(self._h, x.data_ptr(), x.stride(0) if x.shape[0] > 1 else self.D,
+                                                 x.shape[0], lo, hi, mu.data_ptr(), gram.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), _stream()))
+
+    def nap_set_fit(self, lo: int, hi: int, mu: torch.Tensor, vt: torch.Tensor, var: torch.Tensor, mu2: torch.Tensor):
+        f = lambda t: t.detach().to(self.device, torch.float32).contiguous()  # noqa: E731
+        mu, vt, var, mu2 = f(mu), f(vt), f(var), f(mu2)
+        with torch.cuda.device(self.device):
+            check(lib().mmad_nap_set_fit(self._h, lo, hi, vt.shape[0], mu.data_ptr(), vt.data_ptr(), var.data_ptr(),
+                                         mu2.data_ptr(), _stream()))
+            torch.cuda.current_stream().synchronize()
+        self.nap_range = (lo, hi)
+        self._ws = None      # NAP slot count may have changed
+        self._ws_rows = 0
+
+    def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
+                batch_rows: int = 16384) -> Dict[str, torch.Tensor]:
+        """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
+        N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
+        var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
+        ``group``: torch.distributed process group -- the row shards' sum and Gram are all-reduced
+        (one exchange per pass).  mu2 (the Standardizer mean of the rotated
+        train data) is identically zero in exact arithmetic and is installed as zero."""
+        import torch.distributed as dist
+        hi = self.n_diffs if hi is None else hi
+        dsel = self.concat_width(lo, hi)
+        dev = self.device
+        n_local = x_train.shape[0]
+        s = torch.zeros(dsel, dtype=torch.float64, device=dev)
+        for r0 in range(0, n_local, batch_rows):
+            self.nap_accumulate_sum(x_train[r0:r0 + batch_rows], lo, hi, s)
+        n_total = torch.tensor([n_local], dtype=torch.float64, device=dev)
+        if group is not None or (dist.is_available() and dist.is_initialized() and group is not False):
+            dist.all_reduce(s, group=group if group not in (None, True) else None)
+            dist.all_reduce(n_total, group=group if group not in (None, True) else None)
+        N = int(n_total.item())
+        mu = (s / N).float()
+        gram = torch.zeros(dsel, dsel, dtype=torch.float64, device=dev)
+        for r0 in range(0, n_local, batch_rows):
+            self.nap_accumulate_gram(x_train[r0:r0 + batch_rows], lo, hi, mu, gram)
+        if group is not None or (dist.is_available() and dist.is_initialized() and group is not False):
+            dist.all_reduce(gram, group=group if group not in (None, True) else None)
+        fit = nap_fit_from_stats(mu, gram, N)
+        self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
+        return fit
+
+
+def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int) -> Dict[str, torch.Tensor]:
+    """Eigendecomposition of the centred Gram matrix (fp64, cuSOLVER syevd through
+    torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2)."""
+    lam, V = torch.linalg.eigh(gram)            # ascending
+    lam = lam.flip(0)
+    V = V.flip(1)
+    K = min(n_total, gram.shape[0])
+    var = (lam[:K] / (n_total - 1)).float()
+    vt = V[:, :K].t().contiguous().float()
+    return {"mu": mu.float(), "vt": vt, "var": var, "mu2": torch.zeros(K, dtype=torch.float32, device=mu.device),
+            "n": n_total}

@@ -1,0 +1,194 @@
+/*
+ * mmad.h -- C ABI of libmmad.so, the B200 (sm_100a) implementation of the
+ * autoencoder + RaPP reconstruction-aggregation hot path of
+ * Yoo-Youngjae/ICRA2021_multimodal_ad.
+ *
+ * The reference is pure Python and has no FFI of its own; each
+ * entry point below names the reference function (file:line) whose arithmetic it
+ * replaces.  The Python package ``icra2021_multimodal_ad_b200`` binds these with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative MMAD_E_* code on error;
+ *    mmad_last_error() returns a thread-local message.  No C++ exception crosses.
+ *  - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  The caller owns
+ *    every buffer; the library allocates device memory only in mmad_create /
+ *    mmad_set_layer / mmad_nap_set_fit (packed weights) -- never on the scoring path.
+ *  - scratch comes from a caller-provided workspace sized by the *_workspace_bytes
+ *    queries; work is enqueued on the caller's cudaStream_t (passed as void*),
+ *    asynchronously, with no implicit synchronisation unless stated.
+ *  - a handle is bound to the device current at mmad_create and is not thread-safe.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with
+ *    MMAD_E_CUDA.
+ */
+#ifndef MMAD_H_
+#define MMAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMAD_MAX_LAYERS 16
+
+#define MMAD_OK 0
+#define MMAD_E_ARG (-1)
+#define MMAD_E_CUDA (-2)
+#define MMAD_E_STATE (-3)
+#define MMAD_E_WORKSPACE (-4)
+#define MMAD_E_UNSUPPORTED (-5)
+
+/* GEMM arithmetic.  FP32: CUDA-core fp32 FMA (bit-for-bit fp32 products, the parity
+ * reference mode).  F16X3: tcgen05 tensor cores, every fp32 operand split into an fp16
+ * pair (hi + lo), three MMAs per product, fp32 accumulation in TMEM -- meets the 1e-4
+ * score tolerance.  F16: one tcgen05 pass on the hi parts only (separately stated
+ * tolerance). */
+#define MMAD_PREC_FP32 0
+#define MMAD_PREC_F16X3 1
+#define MMAD_PREC_F16 2
+
+typedef struct mmad_handle* mmad_t;
+
+typedef struct {
+    int n_enc;                              /* encoder layers (reference: config.n_layers) */
+    int n_dec;                              /* decoder layers */
+    int enc_widths[MMAD_MAX_LAYERS + 1];    /* [D, h1.., btl]   model_builder.py:21-28 */
+    int dec_widths[MMAD_MAX_LAYERS + 1];    /* [btl, .., D]     model_builder.py:30-37 */
+    float lrelu_slope;                      /* 0.2              modules/activation.py:37-38 */
+    float bn_eps;                           /* 1e-5             layers/fc_layer.py:30 */
+    int precision;                          /* MMAD_PREC_* */
+} mmad_desc_t;
+
+const char* mmad_last_error(void);
+int mmad_version(void);
+
+/* model_builder.py:6-53 (ae_wrapper/get_model): build the packed device model. */
+int mmad_create(const mmad_desc_t* desc, mmad_t* out);
+int mmad_destroy(mmad_t h);
+int mmad_set_precision(mmad_t h, int precision);
+
+/* Load one FCLayer (layers/fc_layer.py:23-35) from state_dict tensors.  module 0 =
+ * encoder, 1 = decoder.  d_W [N,K] row-major fp32, d_b [N].  BatchNorm pointers are
+ * NULL for the bare last layer (modules/fc_module.py:49-54).  Repacks (pads K to the
+ * tile multiple, splits fp16 hi/lo, folds eval BatchNorm into scale/shift). */
+int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const float* d_b,
+                   const float* d_gamma, const float* d_beta, const float* d_mean,
+                   const float* d_var, void* stream);
+
+/* layers/fc_layer.py:37-48 FCLayer.forward (eval mode) as a stand-alone fused op on raw
+ * state_dict tensors: y = BN(lrelu(x W^T + b)) or y = x W^T + b when d_gamma == NULL.
+ * This is what ``for layer in model.encoder.layer_list: x = layer(x)``
+ * (reconstruction_aggregation.py:25-27) executes per layer. */
+int mmad_fc_layer_forward(const float* d_x, int ldx, int n, int K, int N, const float* d_W, const float* d_b,
+                          const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var,
+                          float slope, float eps, float* d_y, int ldy, void* stream);
+
+/* Bytes of workspace needed to process up to max_rows rows per call (scoring, forward
+ * and NAP calls chunk internally to what the workspace allows). */
+size_t mmad_workspace_bytes(mmad_t h, int max_rows);
+
+/* models/auto_encoder.py:36-50 AutoEncoder.forward in eval mode: d_xhat[n,D] = dec(enc(x)).
+ * d_z (optional, [n,btl]) receives AutoEncoder.encode (36-39). ldx = row stride of d_x in floats. */
+int mmad_ae_forward(mmad_t h, const float* d_x, int ldx, int n, float* d_xhat, float* d_z,
+                    void* d_ws, size_t ws_bytes, void* stream);
+
+/* models/auto_encoder.py:79-91 validate / 52-55 get_loss_value in eval mode:
+ * *d_loss (one float) = sum (xhat - x)^2. */
+int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss,
+                    void* d_ws, size_t ws_bytes, void* stream);
+
+/* reconstruction_aggregation.py:6-37 get_diffs fused with utils/metric.py:132-133
+ * (base score) and 145-171 (SAP):
+ *   d_base[n] = mean_j d_0^2              (NULL to skip)
+ *   d_sap[n]  = mean over concat(d_lo..d_hi-1) of d^2   (NULL to skip)
+ *   d_diffs   = the concatenated diffs [n, sum_{l=lo}^{hi-1} w_l] row-major (NULL to skip)
+ *   d_nap[n]  = NAP score (utils/metric.py:183-222) from the fit installed with
+ *               mmad_nap_set_fit (NULL to skip; the fit's layer range must equal lo..hi)
+ * layer_lo / layer_hi follow the python slice diffs[lo:hi] AFTER the reference's
+ * clamping (utils/metric.py:155-162); 0 <= lo < hi <= n_enc+1.
+ * encoder(x) is evaluated once, not twice as in the reference. */
+int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int layer_hi,
+               float* d_base, float* d_sap, float* d_nap, float* d_diffs,
+               void* d_ws, size_t ws_bytes, void* stream);
+
+/* Same as mmad_score with HOST buffers: rows are staged through pinned memory in
+ * chunks, host->device copies overlap compute on internal streams, results are copied
+ * back, and the call returns after everything has landed (synchronous).  This is the
+ * call the e2e benchmark times. */
+int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int layer_lo, int layer_hi,
+                    float* h_base, float* h_sap, float* h_nap);
+
+/* modules/loss.py:31-32 nn.MSELoss(reduction='sum'): *d_out += sum_i (a_i - b_i)^2 (zero it first). */
+int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_out, void* stream);
+/* utils/metric.py:133,171 (d**2).mean(axis=1) over a [n, cols] matrix with row stride ld. */
+int mmad_row_mean_sq(const float* d_d, int ld, int n, int cols, float* d_out, void* stream);
+/* decorators/variational_info_bottleneck.py:19-42 ('normal'): d_out [B, 2h] -> mu, logvar [B,h],
+ * z[k,B,h] = eps * exp(logvar/2) + mu (d_eps [k,B,h]); d_eps == NULL => z = mu broadcast. */
+int mmad_vib_reparam(const float* d_out, int ld, int B, int h, int k, const float* d_eps, float* d_z,
+                     float* d_mu, float* d_logvar, void* stream);
+
+/* ---- NAP fit: utils/normalize.py:47-70 (Rotater.fit) + 20-34 (Standardizer.fit) ----
+ * Pass 1: d_sum[Dsel] (fp64) += column sums of the concatenated diffs of these rows.
+ * Pass 2: d_gram[Dsel*Dsel] (fp64, row-major, full symmetric) += (d-mu)^T (d-mu),
+ *         d_mu[Dsel] fp32 being sum/N after the caller has combined all shards
+ *         (multi-GPU: all-reduce d_sum, then d_gram, between the calls).
+ * Dsel = mmad_concat_width(h, lo, hi). */
+int mmad_concat_width(mmad_t h, int layer_lo, int layer_hi);
+int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int layer_hi,
+                            double* d_sum, void* d_ws, size_t ws_bytes, void* stream);
+int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int layer_hi,
+                             const float* d_mu, double* d_gram, void* d_ws, size_t ws_bytes, void* stream);
+/* Install a fit: d_mu[Dsel]; d_vt [K, Dsel] row-major = rows are right singular vectors
+ * v_j (utils/normalize.py:67); d_var[K] (Standardizer.var), d_mu2[K] (Standardizer.mu).
+ * Packs V*diag(var^-1/2) for the scoring GEMM. */
+int mmad_nap_set_fit(mmad_t h, int layer_lo, int layer_hi, int K, const float* d_mu,
+                     const float* d_vt, const float* d_var, const float* d_mu2, void* stream);
+
+/* ---- metrics: utils/metric.py:29-130 (sklearn roc_curve/auc, precision_recall_curve,
+ * np.quantile, F1, confusion) on device.  d_score fp32, d_label uint8 (0/1).
+ * h_out receives doubles; results are bit-identical to the reference given identical
+ * scores.  These calls synchronise the stream (they return host scalars). */
+size_t mmad_metric_workspace_bytes(long long n);
+int mmad_auc_roc(const float* d_score, const uint8_t* d_label, long long n, double* h_out,
+                 void* d_ws, size_t ws_bytes, void* stream);
+int mmad_auc_prc(const float* d_score, const uint8_t* d_label, long long n, double* h_out,
+                 void* d_ws, size_t ws_bytes, void* stream);
+/* threshold = np.quantile(valid, q) in fp32 (NumPy 2 semantics). */
+int mmad_quantile(const float* d_valid, long long n, float q, float* h_out,
+                  void* d_ws, size_t ws_bytes, void* stream);
+/* h_counts[4] = {tp, fp, fn, tn} with pred = score > thr (strict=1, get_f1_score) or
+ * score >= thr (strict=0, get_confusion_matrix). */
+int mmad_confusion(const float* d_score, const uint8_t* d_label, long long n, float thr, int strict,
+                   long long* h_counts, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- training: models/auto_encoder.py:57-77 AutoEncoder.step ----
+ * Train-mode forward (BatchNorm batch statistics), loss = sum (xhat-x)^2, backward.
+ * Parameters, gradients, BN running stats live in caller-owned fp32 tensors, passed
+ * as arrays of device pointers in state_dict order per layer.  If d_eps != NULL the
+ * encoder output is treated as (mu, logvar) and reparameterised with the given noise
+ * (decorators/variational_info_bottleneck.py:19-42) and beta_kl * KL is added. */
+typedef struct {
+    float* W; float* b; float* gamma; float* beta; float* run_mean; float* run_var;   /* params/buffers */
+    float* gW; float* gb; float* ggamma; float* gbeta;                               /* gradients */
+} mmad_train_layer_t;
+
+size_t mmad_train_workspace_bytes(mmad_t h, int batch);
+/* allreduce hook: called (if non-NULL) on BN statistic buffers so that N-GPU data
+ * parallel equals 1 GPU on the concatenated batch; count floats at d_buf on stream. */
+typedef int (*mmad_allreduce_fn)(void* ctx, float* d_buf, long long count, void* stream);
+int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long global_batch,
+                       const mmad_train_layer_t* enc, const mmad_train_layer_t* dec,
+                       const float* d_eps, float beta_kl, float bn_momentum,
+                       float* d_loss, void* d_ws, size_t ws_bytes,
+                       mmad_allreduce_fn allreduce, void* allreduce_ctx, void* stream);
+/* torch.optim.Adam (novelty_detection.py:90) over a flat list of tensors, one launch. */
+int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads, float* const* h_m,
+                   float* const* h_v, const long long* h_numel, int step, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMAD_H_ */

@@ -1,0 +1,90 @@
+"""CPU checks of the boundary: the library loads, exports every symbol include/mmad.h declares,
+and the host layer mirrors the reference's API surface (no compute calls here)."""
+import argparse
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from icra2021_multimodal_ad_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "mmad.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"\b(mmad_[a-z0-9_]+)\s*\(", txt))
+    names -= {"mmad_allreduce_fn"}
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mmad.h but not exported"
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    assert _lib.lib().mmad_version() >= 100
+
+
+def test_create_rejects_bad_descriptors_without_gpu():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    d = _lib.Desc()
+    d.n_enc, d.n_dec = 0, 1
+    assert L.mmad_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"layer" in L.mmad_last_error()
+    d.n_enc, d.n_dec = 1, 1
+    d.enc_widths[0], d.enc_widths[1] = 8, 4
+    d.dec_widths[0], d.dec_widths[1] = 4, 9
+    assert L.mmad_create(ctypes.byref(d), ctypes.byref(h)) == -1
+
+
+def test_model_surface_matches_reference():
+    from icra2021_multimodal_ad_b200.model_builder import ae_wrapper, get_model
+    cfg = argparse.Namespace(input_size=1728, btl_size=100, n_layers=5, gpu_id=-1)
+    m = get_model(cfg)
+    keys = list(m.state_dict().keys())
+    assert keys[:7] == ["encoder.net.0.layer.weight", "encoder.net.0.layer.bias", "encoder.net.0.bn.weight",
+                        "encoder.net.0.bn.bias", "encoder.net.0.bn.running_mean", "encoder.net.0.bn.running_var",
+                        "encoder.net.0.bn.num_batches_tracked"]
+    assert "encoder.net.4.layer.bias" in keys and "encoder.net.4.bn.weight" not in keys
+    assert sum(p.numel() for p in m.parameters()) == 10225670
+    assert [l.layer.out_features for l in m.encoder.layer_list] == [1402, 1076, 751, 425, 100]
+    assert [l.layer.out_features for l in m.decoder.layer_list] == [425, 751, 1076, 1402, 1728]
+    assert isinstance(m.encoder.layer_list, list) and len(list(m.parameters())) == 36
+    for name in ("encode", "decode", "forward", "get_loss_value", "step", "validate", "attach",
+                 "get_all_optimizers_state_dicts"):
+        assert hasattr(m, name)
+    assert m.optimizer_list == []
+    m2 = ae_wrapper(argparse.Namespace(input_size=(3, 8, 8), btl_size=10, n_layers=3, gpu_id=-1))
+    assert m2.encoder.widths == [192, 131, 70, 10]
+
+
+def test_no_cpu_fallback():
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    m = get_model(argparse.Namespace(input_size=64, btl_size=100, n_layers=5, gpu_id=-1)).eval()
+    with pytest.raises(_lib.MmadError):
+        m(torch.rand(4, 64))
+
+
+def test_reference_error_behaviour():
+    from icra2021_multimodal_ad_b200.modules import FCModule
+    with pytest.raises(Exception, match="Either batch_norm or dropout"):
+        FCModule(8, 4, [6], use_batch_norm=True, dropout_p=0.5)
+
+
+def test_layer_range_clamp_matches_reference():
+    from icra2021_multimodal_ad_b200.engine import clamp_layer_range
+    from oracle.rapp_oracle import clamp_layer_range as ref
+    for n in (4, 6):
+        for lo in range(0, 10):
+            for hi in list(range(-2, 10)) + [None]:
+                a, b = ref(n, lo, hi)
+                exp = list(range(n))[a:b]
+                l2, h2 = clamp_layer_range(n, lo, hi)
+                assert list(range(l2, h2)) == exp or (exp == [] and h2 <= l2)

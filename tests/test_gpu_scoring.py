@@ -1,0 +1,123 @@
+"""GPU parity of the fused scoring path against the oracle and the golden fixtures.
+Tolerances: activations/diffs 1e-5 relative to the matrix max, base/SAP
+scores 1e-4 relative per sample, NAP 1e-4 on well-conditioned (single-layer) selections."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32"]
+
+
+def _rel_max(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _model(D, btl, nl, seed, precision="fp32"):
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=precision))
+    m.load_state_dict(synth_state_dict(D, btl, nl, seed))
+    return m.eval()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["score_D64.pt", "score_D128_l3.pt", "score_D1728.pt"])
+def test_scores_match_reference_golden(name, precision):
+    from icra2021_multimodal_ad_b200.reconstruction_aggregation import get_diffs, get_scores
+    g = load_golden(name)
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    m = _model(D, btl, nl, seed, precision)
+    xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    r = g["xhat"].shape[0]
+    with torch.no_grad():
+        xhat = m(xte.cuda()).cpu()
+        diffs = get_diffs(xte.numpy(), m, batch_size=g["bs"])
+        loss = float(m.get_loss_value(xte.cuda(), xte.cuda()))
+    assert _rel_max(xhat[:r], g["xhat"]) < 1e-5
+    assert len(diffs) == nl + 1
+    for d, dg in zip(diffs, g["diffs_te"]):
+        assert d.dtype == np.float32 and d.shape[0] == g["n_te"]
+        assert _rel_max(d[:r], dg) < 2e-5
+    assert abs(loss - g["loss_sum_te"]) / g["loss_sum_te"] < 1e-5
+    for sel, ent in g["sap"].items():
+        lo, hi = sel.split(":")
+        lo, hi = int(lo), (None if hi == "None" else int(hi))
+        sc = get_scores(xte, m, lo, hi)
+        np.testing.assert_allclose(sc["sap"].cpu().numpy(), ent["score"].numpy(), rtol=1e-4)
+        np.testing.assert_allclose(sc["base"].cpu().numpy(), g["base"]["score"].numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_against_oracle_ragged_and_edges(precision):
+    from oracle import rapp_oracle as RO
+    D, btl, nl, seed = 128, 100, 5, 77
+    sd = synth_state_dict(D, btl, nl, seed)
+    m = _model(D, btl, nl, seed, precision)
+    eng = m.engine()
+    for n in (1, 2, 127, 129, 300):
+        x, _ = synth_windows(n, D, 500 + n)
+        ref = RO.get_diffs(x, sd, batch_size=64)
+        out = eng.score(x.cuda(), 0, nl + 1, diffs=True)
+        cat = np.concatenate(ref, axis=1)
+        assert _rel_max(out["diffs"].cpu().numpy(), cat) < 2e-5
+        np.testing.assert_allclose(out["sap"].cpu().numpy(), RO.sap_score(ref), rtol=1e-4)
+        np.testing.assert_allclose(out["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=1e-4)
+        for lo, hi in ((1, 3), (2, 6), (5, 6), (0, 1)):
+            o2 = eng.score(x.cuda(), lo, hi, base=False)
+            np.testing.assert_allclose(o2["sap"].cpu().numpy(), RO.sap_score(ref, lo, hi), rtol=1e-4)
+    # empty input
+    out = eng.score(torch.empty(0, D, device="cuda"), 0, nl + 1)
+    assert out["sap"].numel() == 0
+    # strided rows (a column slice of a wider matrix)
+    wide = torch.rand(50, D + 7, device="cuda")
+    o1 = eng.score(wide[:, :D], 0, nl + 1)["sap"]
+    o2 = eng.score(wide[:, :D].contiguous(), 0, nl + 1)["sap"]
+    assert torch.equal(o1, o2)
+    # determinism
+    x, _ = synth_windows(300, D, 9)
+    a = eng.score(x.cuda())["sap"]
+    b = eng.score(x.cuda())["sap"]
+    assert torch.equal(a, b)
+
+
+def test_layer_by_layer_api_matches_fused_chain():
+    """reconstruction_aggregation.py:25-27 iterates model.encoder.layer_list; the stand-alone
+    FCLayer op must agree with the fused chain."""
+    from oracle import rapp_oracle as RO
+    D, btl, nl, seed = 64, 100, 5, 3
+    m = _model(D, btl, nl, seed)
+    sd = synth_state_dict(D, btl, nl, seed)
+    x, _ = synth_windows(70, D, 1)
+    h = x.cuda()
+    ref = x
+    for layer, L in zip(m.encoder.layer_list, RO.module_layers(sd, "encoder")):
+        h = layer(h)
+        ref = RO.fc_layer_eval(ref, L)
+        assert _rel_max(h.cpu(), ref) < 1e-5
+    z = m.encode(x.cuda())
+    assert _rel_max(z.cpu(), ref) < 1e-5
+    xh = m.decode(z)
+    assert _rel_max(xh.cpu(), RO.ae_forward_eval(x, sd)) < 1e-5
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_nap_single_layers_match_reference(precision):
+    g = load_golden("score_D64.pt")
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    m = _model(D, btl, nl, seed, precision)
+    eng = m.engine()
+    xtr, _ = synth_windows(g["n_tr"], D, seed + 1, anomaly_rate=0.0)
+    xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    for sel in ("0:1", "1:2"):
+        lo, hi = map(int, sel.split(":"))
+        eng.nap_fit(xtr.cuda(), lo, hi, group=False)
+        s = eng.score(xte.cuda(), lo, hi, base=False, sap=False, nap=True)["nap"].cpu().numpy()
+        np.testing.assert_allclose(s, g["nap"][sel]["score"].numpy(), rtol=1e-3)
