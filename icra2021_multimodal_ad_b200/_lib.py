@@ -58,6 +58,9 @@ SIGNATURES = {
     "mmad_auc_prc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "mmad_quantile": (_i, [_vp, _ll, _f, C.POINTER(C.c_float), _vp, _sz, _vp]),
     "mmad_confusion": (_i, [_vp, _vp, _ll, _f, _i, C.POINTER(C.c_longlong), _vp, _sz, _vp]),
+    "mmad_profile_begin": (_i, [_vp]),
+    "mmad_profile_end": (_i, [_vp, C.POINTER(C.c_double)]),
+    "mmad_launch_count": (C.c_ulonglong, []),
     "mmad_train_workspace_bytes": (_sz, [_vp, _i]),
     "mmad_train_fwd_bwd": (_i, [_vp, _vp, _i, _i, _ll, C.POINTER(TrainLayer), C.POINTER(TrainLayer), _vp, _f, _f,
                                 _vp, _vp, _sz, ALLREDUCE_FN, _vp, _vp]),

@@ -163,12 +163,14 @@ int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half*
     if (n <= 0) return MMAD_OK;
     size_t total = (size_t)n * (xp ? ldp : ldh);
     pad_split_kernel<<<grid_for(total), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
 
 int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s) {
     split_weights_kernel<<<grid_for((size_t)N * Kp), 256, 0, s>>>(W, N, K, Kp, scale, Wh, Wl);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -176,12 +178,14 @@ int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh,
 int fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int N, int Np,
             float* scale, float* shift, cudaStream_t s) {
     fold_bn_kernel<<<(Np + 255) / 256, 256, 0, s>>>(gamma, beta, mean, var, eps, N, Np, scale, shift);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
 
 int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s) {
     copy_pad_kernel<<<(Np + 255) / 256, 256, 0, s>>>(src, N, Np, dst);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -191,6 +195,7 @@ int finalize_scores(const float* rowpart, int stride, int n, int b_lo, int b_hi,
     if (n <= 0) return MMAD_OK;
     finalize_scores_kernel<<<(n + 255) / 256, 256, 0, s>>>(rowpart, stride, n, b_lo, b_hi, s_lo, s_hi, inv_base,
                                                            inv_sap, base, sap);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -205,6 +210,7 @@ int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slo
     int g = (n + 255) / 256;
     if (g > 64) g = 64;
     reduce_sum_all_kernel<<<g, 256, 0, s>>>(rowpart, stride, n, slot_lo, slot_hi, acc);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -213,6 +219,7 @@ int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_
     if (n <= 0) return MMAD_OK;
     dim3 grid((cols + 127) / 128, n >= 4096 ? 32 : (n >= 256 ? 8 : 1));
     colsum_f64_kernel<<<grid, 128, 0, s>>>(d, ld, n, cols, sum);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -220,6 +227,7 @@ int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_
 int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp, float* B,
              float* colscale, float* bias, cudaStream_t s) {
     nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, B, colscale, bias);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -227,6 +235,7 @@ int nap_pack(const float* mu, const float* vt, const float* var, const float* mu
 int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStream_t s) {
     size_t total = (size_t)D * D;
     gram_f64_accumulate_kernel<<<grid_for(total), 256, 0, s>>>(g32, ld32, D, g64);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -234,6 +243,7 @@ int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStre
 int center_rows(float* d, int ld, int n, int cols, const float* mu, cudaStream_t s) {
     if (n <= 0) return MMAD_OK;
     center_rows_kernel<<<grid_for((size_t)n * cols), 256, 0, s>>>(d, ld, n, cols, mu);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }

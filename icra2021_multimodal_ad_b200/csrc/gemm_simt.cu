@@ -232,6 +232,7 @@ int launch(const GemmShape& g, const Epilogue& e, cudaStream_t s) {
         gemm_simt_kernel<BM, true, false><<<grid, NTHREADS, 0, s>>>(g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, vecA, vecB, e);
     else
         gemm_simt_kernel<BM, true, true><<<grid, NTHREADS, 0, s>>>(g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, vecA, vecB, e);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }

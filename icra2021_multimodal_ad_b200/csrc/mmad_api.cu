@@ -12,6 +12,7 @@
 namespace mmad {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -64,6 +65,10 @@ struct mmad_handle {
     int host_chunk = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // optional per-launch CUDA-event profile of the GEMM kernel (mmad_profile_begin/end)
+    bool prof = false;
+    struct ProfRec { cudaEvent_t a, b; double flops; };
+    std::vector<ProfRec> prof_recs;
 };
 
 namespace mmad {
@@ -186,7 +191,20 @@ struct Act {            // an activation matrix in the workspace (or the caller'
     const __half* h = nullptr; const __half* l = nullptr; int ldh = 0;
 };
 
+struct ProfScope {   // records a CUDA-event pair around one GEMM launch when profiling is on
+    mmad_t h; cudaStream_t s; cudaEvent_t b = nullptr;
+    ProfScope(mmad_t h_, cudaStream_t s_, double flops) : h(h_), s(s_) {
+        if (!h->prof) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        h->prof_recs.push_back({a, b, flops});
+    }
+    ~ProfScope() { if (b) cudaEventRecord(b, s); }
+};
+
 static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogue e, cudaStream_t s) {
+    ProfScope prof(h, s, 2.0 * rows * (double)Lr.N * (double)Lr.K);
     e.bias = Lr.bias;
     if (Lr.has_bn) { e.bn_scale = Lr.scale; e.bn_shift = Lr.shift; }
     e.slope = h->desc.lrelu_slope;
@@ -466,6 +484,7 @@ int mmad_ae_forward(mmad_t h, const float* d_x, int ldx, int n, float* d_xhat, f
                     size_t ws_bytes, void* stream) {
     int rc = check_ready(h);
     if (rc) return rc;
+    if (n == 0) return MMAD_OK;
     if (n < 0 || !d_x || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
     PlanOpts o; o.tc = h->desc.precision != MMAD_PREC_FP32;
     o.lo = 0; o.hi = 1;
@@ -489,7 +508,7 @@ int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss, v
                     void* stream) {
     int rc = check_ready(h);
     if (rc) return rc;
-    if (n < 0 || !d_x || !d_loss || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    if (n < 0 || (n > 0 && !d_x) || !d_loss || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
     PlanOpts o; o.tc = h->desc.precision != MMAD_PREC_FP32;
@@ -513,6 +532,7 @@ int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss, v
 static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, cudaStream_t s) {
     const NapFit& f = h->nap;
     const int L = h->desc.n_enc;
+    ProfScope prof(h, s, 2.0 * rows * (double)f.K * (double)f.D);
     Epilogue e;
     e.bias = f.bias;
     e.col_scale = f.colscale;
@@ -545,6 +565,7 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
+    if (n == 0) return MMAD_OK;
     if (n < 0 || !d_x || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
     if (d_nap && !(h->nap.ready && h->nap.lo == lo && h->nap.hi == hi)) {
         set_error("NAP requested but no fit installed for layers [%d,%d)", lo, hi);
@@ -597,6 +618,7 @@ int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int lo, 
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
+    if (n == 0) return MMAD_OK;
     if (!d_x || !d_sum || n < 0) { set_error("bad input"); return MMAD_E_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     PlanOpts o; o.lo = lo; o.hi = hi; o.tc = h->desc.precision != MMAD_PREC_FP32; o.diffs_ws = true;
@@ -623,6 +645,7 @@ int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lo,
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
+    if (n == 0) return MMAD_OK;
     if (!d_x || !d_mu || !d_gram || n < 0) { set_error("bad input"); return MMAD_E_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     PlanOpts o; o.lo = lo; o.hi = hi; o.tc = h->desc.precision != MMAD_PREC_FP32; o.diffs_ws = true; o.gram = true;
@@ -694,6 +717,7 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
+    if (n == 0) return MMAD_OK;
     if (!h_x || n < 0 || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
     if (h_nap && !(h->nap.ready && h->nap.lo == lo && h->nap.hi == hi)) {
         set_error("NAP requested but no fit installed for layers [%d,%d)", lo, hi);
@@ -748,5 +772,31 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
     MMAD_CUDA_OK(cudaStreamSynchronize(h->s_copy));
     return MMAD_OK;
 }
+
+int mmad_profile_begin(mmad_t h) {
+    if (!h) { set_error("null handle"); return MMAD_E_ARG; }
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->prof_recs.clear();
+    h->prof = true;
+    return MMAD_OK;
+}
+
+int mmad_profile_end(mmad_t h, double* h_out) {
+    if (!h || !h_out) { set_error("null argument"); return MMAD_E_ARG; }
+    h->prof = false;
+    MMAD_CUDA_OK(cudaDeviceSynchronize());
+    double ms = 0.0, flops = 0.0;
+    for (auto& r : h->prof_recs) {
+        float t = 0.f;
+        MMAD_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; flops += r.flops;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    h_out[0] = ms; h_out[1] = flops; h_out[2] = (double)h->prof_recs.size();
+    h->prof_recs.clear();
+    return MMAD_OK;
+}
+
+unsigned long long mmad_launch_count(void) { return mmad::g_launches; }
 
 }  // extern "C"

@@ -13,7 +13,9 @@
 namespace mmad {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
+#define MMAD_LAUNCHED() (++mmad::g_launches)
 #define MMAD_CUDA_OK(expr)                                                              \
     do {                                                                                \
         cudaError_t _e = (expr);                                                        \

@@ -62,6 +62,7 @@ int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_o
     long long g = (n + 255) / 256;
     if (g > 148 * 4) g = 148 * 4;
     sq_diff_sum_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, d_out);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -70,6 +71,7 @@ int mmad_row_mean_sq(const float* d_d, int ld, int n, int cols, float* d_out, vo
     if (!d_d || !d_out || n < 0 || cols < 1 || ld < cols) { set_error("bad argument"); return MMAD_E_ARG; }
     if (n == 0) return MMAD_OK;
     row_mean_sq_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_d, ld, n, cols, d_out);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
@@ -83,6 +85,7 @@ int mmad_vib_reparam(const float* d_out, int ld, int B, int h, int k, const floa
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     vib_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(d_out, ld, B, h, k, d_eps, d_z, d_mu, d_logvar);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }

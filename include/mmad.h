@@ -188,6 +188,15 @@ int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads,
                    float* const* h_v, const long long* h_numel, int step, float lr, float beta1,
                    float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- measurement hooks (bench.py) ----
+ * mmad_profile_begin: record a CUDA-event pair around every fused-GEMM launch of this handle.
+ * mmad_profile_end: synchronise; h_out[0] = sum of GEMM kernel durations (ms), h_out[1] = their
+ * algorithmic FLOPs (2*M*N*K per launch), h_out[2] = number of GEMM launches.
+ * mmad_launch_count: kernels launched by the library since load (all handles). */
+int mmad_profile_begin(mmad_t h);
+int mmad_profile_end(mmad_t h, double* h_out);
+unsigned long long mmad_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif
