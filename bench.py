@@ -203,7 +203,7 @@ def main():
         xtr, _ = synth_windows(per, D, 1234 + rank, anomaly_rate=0.0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fit = eng.nap_fit(xtr.to(dev), 0, NL + 1, group=None if world > 1 else False)
+        fit = eng.nap_fit(xtr.to(dev), 0, NL + 1, distributed=world > 1)
         torch.cuda.synchronize()
         fit_s = time.perf_counter() - t0
 

@@ -1,8 +1,429 @@
-// tcgen05 GEMM -- placeholder until the tensor-core engine lands (next commit).
+// tcgen05 / TMEM / TMA fused layer GEMM for sm_100a  (MMAD_PREC_F16X3, MMAD_PREC_F16)
+//
+//   acc[m,n] = sum_k A[m,k] * B[n,k]         A = activations [M,K], B = weights [N,K]  (Y = X W^T)
+//
+// Every fp32 operand is carried as an fp16 pair (hi + lo, x ~= hi + lo to ~2^-22).  PASSES == 3
+// issues  hi*hi + hi*lo + lo*hi  into one fp32 TMEM accumulator (fp32-equivalent products at the
+// fp16 tensor-core rate / 3); PASSES == 1 issues hi*hi only.
+//
+// Persistent, warp-specialised, one CTA per SM (grid = min(tiles, #SM)):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2-D boxes [rows x 64 halfs], 128-byte swizzle,
+//              into a ring of smem stages, completion on mbarriers (expect_tx)
+//   warp 1     MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256,
+//              K=16 per instruction, smem descriptors advanced by 32 B inside the swizzle atom;
+//              tcgen05.commit releases smem stages and publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) from one of two
+//              256-column TMEM accumulator buffers while the next tile's MMAs fill the other;
+//              fused bias / LeakyReLU / BatchNorm affine / diff against the stashed activation /
+//              per-row sum of squares / fp16 hi-lo re-split for the next layer.
+// CTA tile 128 x 256 x 64.  Tiles are ordered n-fastest so CTAs running together share the
+// activation tile in L2.  All mbarrier waits are bounded and trap instead of hanging the GPU.
+#include <dlfcn.h>
+
 #include "mmad_internal.cuh"
+
 namespace mmad {
-int tc_available() { return 0; }
-int gemm_tc_tile_n() { return 128; }
-int tc_make_operand_map(CUtensorMap*, const __half*, int, int, int, int) { set_error("tcgen05 path not built"); return MMAD_E_UNSUPPORTED; }
-int gemm_tc(const TcOperand&, const TcOperand&, int, int, int, int, const Epilogue&, cudaStream_t) { set_error("tcgen05 path not built"); return MMAD_E_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;                 // halfs per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int TMEM_COLS = 512;              // two 256-column fp32 accumulators
+
+template <int PASSES> struct Cfg {
+    static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
+    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_TILE_BYTES);
+    static constexpr int kStages = PASSES == 3 ? 2 : 4;
+    static constexpr int kSmemTiles = kStages * kStageBytes;   // 192 KB
+    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < 4000000000LL)     // ~2 s at 2 GHz
+        if (mbar_try_wait(bar, parity)) return;
+    printf("mmad gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// smem matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (SM100 version 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+    int M, N, K;
+    int tiles_m, tiles_n;
+};
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int PASSES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+               TcParams p, Epilogue e) {
+    using C = Cfg<PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_mul = reinterpret_cast<float*>(smem + C::kSmemTiles);
+    float* s_bias = s_mul + BN;
+    float* s_sc = s_bias + BN;
+    float* s_sh = s_sc + BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sh + BN);
+    uint64_t* full = bars;                       // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> TMA
+    uint64_t* acc_full = empty + C::kStages;     // [2]        MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;          // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
+        if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
+    }
+    if (warp == 1) {   // TMEM allocation is a warp-wide operation; the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    mbar_expect_tx(fb, C::kStageBytes);
+                    uint8_t* st = smem + stage * C::kStageBytes;
+                    tma_load_2d(smem_u32(st), &mapAh, fb, kb * BK, m0);
+                    tma_load_2d(smem_u32(st + A_TILE_BYTES), &mapBh, fb, kb * BK, n0);
+                    if (PASSES == 3) {
+                        tma_load_2d(smem_u32(st + A_TILE_BYTES + B_TILE_BYTES), &mapAl, fb, kb * BK, m0);
+                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &mapBl, fb, kb * BK, n0);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n0 = (t % p.tiles_n) * BN;
+                int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
+                n_eff = (n_eff + 15) & ~15;
+                const uint32_t idesc = make_idesc(n_eff);
+                mbar_wait(smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t dAh = make_smem_desc(st);
+                    const uint64_t dBh = make_smem_desc(st + A_TILE_BYTES);
+                    const uint64_t dAl = make_smem_desc(st + A_TILE_BYTES + B_TILE_BYTES);
+                    const uint64_t dBl = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, 16-byte units
+                        if (PASSES == 3) {
+                            umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
+                            umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1);
+                            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                        } else {
+                            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | k) != 0);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty[stage]));                        // frees the smem stage when the MMAs retire
+                    if (kb == num_kb - 1) umma_commit(smem_u32(&acc_full[acc])); // accumulator complete
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int et = threadIdx.x - 64;        // 0..127
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool y_vec = e.Y && (e.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.Y) & 15) == 0);
+        const bool h_vec = e.Yh && (e.ldh % 8 == 0) && ((reinterpret_cast<uintptr_t>(e.Yh) & 15) == 0) &&
+                           (!e.Yl || (reinterpret_cast<uintptr_t>(e.Yl) & 15) == 0);
+        const bool ref_vec = e.ref && (e.ldref % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.ref) & 15) == 0);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
+            // stage the per-column epilogue vectors of this tile
+            asm volatile("bar.sync 1, 128;");
+            for (int c = et; c < BN; c += 128) {
+                const int gc = n0 + c;
+                const bool ok = gc < p.N;
+                s_mul[c] = e.acc_scale * ((e.col_scale && ok) ? e.col_scale[gc] : 1.f);
+                s_bias[c] = (e.bias && ok) ? e.bias[gc] : 0.f;
+                s_sc[c] = (e.bn_scale && ok) ? e.bn_scale[gc] : 1.f;
+                s_sh[c] = (e.bn_scale && ok) ? e.bn_shift[gc] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;");
+            mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
+            tc_fence_after();
+            const int r = m0 + q * 32 + lane;
+            const bool rok = r < p.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            float sq = 0.f;
+            int n_cols = p.N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
+            int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // columns to write (zero padded)
+            const int c_end = (max(n_cols, w_cols) + 31) & ~31;
+            for (int c0 = 0; c0 < c_end && c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    float x = fmaf(__uint_as_float(v[j]), s_mul[c], s_bias[c]);
+                    if (e.pre && rok && c < n_cols) e.pre[(size_t)r * e.ldpre + n0 + c] = x;
+                    if (e.bn_scale) {
+                        x = x > 0.f ? x : x * e.slope;
+                        x = fmaf(x, s_sc[c], s_sh[c]);
+                    }
+                    o[j] = c < n_cols ? x : 0.f;
+                }
+                if (rok) {
+                    if (e.Y) {
+                        float* yp = e.Y + (size_t)r * e.ldy + n0 + c0;
+                        if (y_vec && c0 + 32 <= w_cols) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (c0 + j < w_cols) yp[j] = o[j];
+                        }
+                    }
+                    if (e.Yh) {
+                        __half hh[32], ll[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            hh[j] = __float2half_rn(o[j]);
+                            ll[j] = __float2half_rn(o[j] - __half2float(hh[j]));
+                        }
+                        __half* hp = e.Yh + (size_t)r * e.ldh + n0 + c0;
+                        __half* lp = e.Yl ? e.Yl + (size_t)r * e.ldh + n0 + c0 : nullptr;
+                        if (h_vec && c0 + 32 <= w_cols) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j]);
+                                if (lp) *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j]);
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (c0 + j < w_cols) { hp[j] = hh[j]; if (lp) lp[j] = ll[j]; }
+                        }
+                    }
+                    if (e.ref) {
+                        const float* rp = e.ref + (size_t)r * e.ldref + n0 + c0;
+                        float d[32];
+                        if (ref_vec && c0 + 32 <= n_cols) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 f = *reinterpret_cast<const float4*>(rp + j);
+                                d[j] = o[j] - f.x; d[j + 1] = o[j + 1] - f.y; d[j + 2] = o[j + 2] - f.z; d[j + 3] = o[j + 3] - f.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) d[j] = (c0 + j < n_cols) ? o[j] - rp[j] : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sq = fmaf(d[j], d[j], sq);
+                        if (e.dout) {
+                            float* dp = e.dout + (size_t)r * e.lddout + n0 + c0;
+                            for (int j = 0; j < 32; ++j) if (c0 + j < n_cols) dp[j] = d[j];
+                        }
+                        if (e.Dh) {
+                            __half* hp = e.Dh + (size_t)r * e.lddh + n0 + c0;
+                            __half* lp = e.Dl + (size_t)r * e.lddh + n0 + c0;
+                            for (int j = 0; j < 32; ++j) if (c0 + j < n_cols) {
+                                const float ds = d[j] * e.d_scale;
+                                const __half h = __float2half_rn(ds);
+                                hp[j] = h;
+                                lp[j] = __float2half_rn(ds - __half2float(h));
+                            }
+                        }
+                    } else if (e.sq_self) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sq = fmaf(o[j], o[j], sq);
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc]));
+            if (e.rowpart && rok) e.rowpart[(size_t)tn * e.rowpart_stride + r] = sq;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_tc_state = -1;   // -1 unknown, 0 unavailable, 1 ok
+int g_num_sms = 148;
+
+int init_tc() {
+    if (g_tc_state >= 0) return g_tc_state;
+    g_tc_state = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (prop.major != 10) return 0;
+    g_num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        cudaGetLastError();
+        return 0;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    g_tc_state = 1;
+    return 1;
+}
+
+}  // namespace
+
+int tc_available() { return init_tc(); }
+int gemm_tc_tile_n() { return BN; }
+
+// 2-D map over a row-major fp16 matrix [rows, k] with row stride ld (elements): box = [64 x box_rows],
+// 128-byte swizzle, zero fill outside [rows, k].
+int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int k, int ld, int box_rows) {
+    if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8)) { set_error("TMA operand must be 16-byte aligned (ld=%d)", ld); return MMAD_E_ARG; }
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d k=%d ld=%d", (int)r, rows, k, ld); return MMAD_E_CUDA; }
+    return MMAD_OK;
+}
+
+int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s) {
+    if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
+    if (M <= 0 || N <= 0) return MMAD_OK;
+    TcParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (passes == 3)
+        gemm_tc_kernel<3><<<grid, NTHREADS, Cfg<3>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.lo, p, e);
+    else
+        gemm_tc_kernel<1><<<grid, NTHREADS, Cfg<1>::kSmemBytes, s>>>(A.hi, A.hi, B.hi, B.hi, p, e);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+}  // namespace mmad

@@ -219,14 +219,15 @@ class Engine:
         self._ws_rows = 0
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
-                batch_rows: int = 16384) -> Dict[str, torch.Tensor]:
+                batch_rows: int = 16384, distributed: Optional[bool] = None) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
-        ``group``: torch.distributed process group -- the row shards' sum and Gram are all-reduced
-        (one exchange per pass).  mu2 (the Standardizer mean of the rotated
+        ``distributed`` (default: whether torch.distributed is initialised) / ``group``: the row
+        shards' sum and Gram are all-reduced (one exchange per pass).  mu2 (the Standardizer mean of the rotated
         train data) is identically zero in exact arithmetic and is installed as zero."""
         import torch.distributed as dist
+        use_dist = (dist.is_available() and dist.is_initialized()) if distributed is None else bool(distributed)
         hi = self.n_diffs if hi is None else hi
         dsel = self.concat_width(lo, hi)
         dev = self.device
@@ -235,16 +236,16 @@ class Engine:
         for r0 in range(0, n_local, batch_rows):
             self.nap_accumulate_sum(x_train[r0:r0 + batch_rows], lo, hi, s)
         n_total = torch.tensor([n_local], dtype=torch.float64, device=dev)
-        if group is not None or (dist.is_available() and dist.is_initialized() and group is not False):
-            dist.all_reduce(s, group=group if group not in (None, True) else None)
-            dist.all_reduce(n_total, group=group if group not in (None, True) else None)
+        if use_dist:
+            dist.all_reduce(s, group=group)
+            dist.all_reduce(n_total, group=group)
         N = int(n_total.item())
         mu = (s / N).float()
         gram = torch.zeros(dsel, dsel, dtype=torch.float64, device=dev)
         for r0 in range(0, n_local, batch_rows):
             self.nap_accumulate_gram(x_train[r0:r0 + batch_rows], lo, hi, mu, gram)
-        if group is not None or (dist.is_available() and dist.is_initialized() and group is not False):
-            dist.all_reduce(gram, group=group if group not in (None, True) else None)
+        if use_dist:
+            dist.all_reduce(gram, group=group)
         fit = nap_fit_from_stats(mu, gram, N)
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
         return fit

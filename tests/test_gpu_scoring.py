@@ -12,7 +12,7 @@ from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_wind
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ["fp32"]
+PRECISIONS = ["fp32", "f16x3"]
 
 
 def _rel_max(a, b):
@@ -118,6 +118,40 @@ def test_nap_single_layers_match_reference(precision):
     xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
     for sel in ("0:1", "1:2"):
         lo, hi = map(int, sel.split(":"))
-        eng.nap_fit(xtr.cuda(), lo, hi, group=False)
+        eng.nap_fit(xtr.cuda(), lo, hi, distributed=False)
         s = eng.score(xte.cuda(), lo, hi, base=False, sap=False, nap=True)["nap"].cpu().numpy()
         np.testing.assert_allclose(s, g["nap"][sel]["score"].numpy(), rtol=1e-3)
+
+
+def test_f16_single_pass_stated_tolerance():
+    """MMAD_PREC_F16 (one tensor-core pass on the fp16 hi parts): separately stated tolerance --
+    per-sample SAP/base within 2e-2 relative, median within 3e-3 (precision modes)."""
+    from icra2021_multimodal_ad_b200.reconstruction_aggregation import get_scores
+    g = load_golden("score_D1728.pt")
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    m = _model(D, btl, nl, seed, "f16")
+    xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    sc = get_scores(xte, m, 0, 7)
+    ref = g["sap"]["0:7"]["score"].numpy()
+    rel = np.abs(sc["sap"].cpu().numpy() - ref) / ref
+    assert rel.max() < 2e-2 and np.median(rel) < 3e-3, (rel.max(), np.median(rel))
+
+
+def test_tensor_core_gemm_tile_edges():
+    """Shapes that exercise partial M/N/K tiles of the 128x256x64 tcgen05 kernel against the fp32 kernel."""
+    for D, btl, nl in ((1728, 100, 5), (300, 17, 2), (2048, 100, 5), (93, 10, 3)):
+        sd = synth_state_dict(D, btl, nl, 123)
+        from icra2021_multimodal_ad_b200.model_builder import get_model
+        outs = {}
+        for prec in ("fp32", "f16x3"):
+            m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=prec)).eval()
+            m.load_state_dict(sd)
+            for n in (1, 130, 700):
+                x, _ = synth_windows(n, D, 40 + n)
+                o = m.engine().score(x.cuda(), 0, nl + 1, diffs=True)
+                outs[(prec, n)] = {k: v.cpu().numpy() for k, v in o.items()}
+        for n in (1, 130, 700):
+            a, b = outs[("fp32", n)], outs[("f16x3", n)]
+            assert _rel_max(b["diffs"], a["diffs"]) < 2e-5, (D, n)
+            np.testing.assert_allclose(b["sap"], a["sap"], rtol=5e-5)
+            np.testing.assert_allclose(b["base"], a["base"], rtol=5e-5)
