@@ -189,7 +189,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("MMAD_DEFAULT_PRECISION", "fp32")
+        precision = os.environ.get("MMAD_DEFAULT_PRECISION", "f16x3")
     sd = synth_state_dict(D, BTL, NL, 0)
     cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
     model = get_model(cfg).eval()

@@ -99,35 +99,40 @@ __global__ void reduce_sum_all_kernel(const float* __restrict__ part, int stride
 }
 
 // sum[c] += sum_r d[r, c]  (fp64 accumulation; grid: x over columns, y over row slabs)
-__global__ void colsum_f64_kernel(const float* __restrict__ d, int ld, int n, int cols, double* __restrict__ sum) {
+__global__ void colsum_f64_kernel(const float* __restrict__ d, int ld, int n, int cols, SegMap sm,
+                                  double* __restrict__ sum) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
+    const int pc = seg_pad_col(sm, c);
     int rows_per = (n + gridDim.y - 1) / gridDim.y;
     int r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
     double a = 0.0;
-    for (int r = r0; r < r1; ++r) a += (double)d[(size_t)r * ld + c];
+    for (int r = r0; r < r1; ++r) a += (double)d[(size_t)r * ld + pc];
     atomicAdd(&sum[c], a);
 }
 
-__global__ void gram_f64_accumulate_kernel(const float* __restrict__ g32, int ld32, int D, double* __restrict__ g64) {
+__global__ void gram_f64_accumulate_kernel(const float* __restrict__ g32, int ld32, int D, SegMap sm,
+                                           double* __restrict__ g64) {
     const size_t total = (size_t)D * D;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(i / D), c = (int)(i % D);
-        g64[i] += (double)g32[(size_t)r * ld32 + c];
+        g64[i] += (double)g32[(size_t)seg_pad_col(sm, r) * ld32 + seg_pad_col(sm, c)];
     }
 }
 
 // NAP fit packing: B[j,:] = v_j (zero padded), colscale[j] = var_j^-1/2,
 // bias[j] = -(mu . v_j + mu2_j) * var_j^-1/2   (utils/normalize.py:36-45,72-103 folded)
 __global__ void nap_pack_kernel(const float* __restrict__ mu, const float* __restrict__ vt, const float* __restrict__ var,
-                                const float* __restrict__ mu2, int K, int D, int Dp, float* __restrict__ B,
-                                float* __restrict__ colscale, float* __restrict__ bias) {
+                                const float* __restrict__ mu2, int K, int D, int Dp, SegMap seg,
+                                float* __restrict__ B, float* __restrict__ colscale, float* __restrict__ bias) {
     const int j = blockIdx.x;
     double dot = 0.0;
-    for (int c = threadIdx.x; c < Dp; c += blockDim.x) {
-        float v = c < D ? vt[(size_t)j * D + c] : 0.f;
-        B[(size_t)j * Dp + c] = v;
-        if (c < D) dot += (double)v * (double)mu[c];
+    for (int c = threadIdx.x; c < Dp; c += blockDim.x) B[(size_t)j * Dp + c] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float v = vt[(size_t)j * D + c];
+        B[(size_t)j * Dp + seg_pad_col(seg, c)] = v;
+        dot += (double)v * (double)mu[c];
     }
     __shared__ double sm[256];
     sm[threadIdx.x] = dot;
@@ -143,11 +148,12 @@ __global__ void nap_pack_kernel(const float* __restrict__ mu, const float* __res
     }
 }
 
-__global__ void center_rows_kernel(float* __restrict__ d, int ld, int n, int cols, const float* __restrict__ mu) {
+__global__ void center_rows_kernel(float* __restrict__ d, int ld, int n, int cols, SegMap sm,
+                                   const float* __restrict__ mu) {
     const size_t total = (size_t)n * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(i / cols), c = (int)(i % cols);
-        d[(size_t)r * ld + c] -= mu[c];
+        d[(size_t)r * ld + seg_pad_col(sm, c)] -= mu[c];
     }
 }
 
@@ -215,34 +221,34 @@ int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slo
     return MMAD_OK;
 }
 
-int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_t s) {
+int colsum_f64(const float* d, int ld, int n, int cols, const SegMap& sm, double* sum, cudaStream_t s) {
     if (n <= 0) return MMAD_OK;
     dim3 grid((cols + 127) / 128, n >= 4096 ? 32 : (n >= 256 ? 8 : 1));
-    colsum_f64_kernel<<<grid, 128, 0, s>>>(d, ld, n, cols, sum);
+    colsum_f64_kernel<<<grid, 128, 0, s>>>(d, ld, n, cols, sm, sum);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
 
-int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp, float* B,
-             float* colscale, float* bias, cudaStream_t s) {
-    nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, B, colscale, bias);
+int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp,
+             const SegMap& sm, float* B, float* colscale, float* bias, cudaStream_t s) {
+    nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, sm, B, colscale, bias);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
 
-int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStream_t s) {
+int gram_f64_accumulate(const float* g32, int ld32, int D, const SegMap& sm, double* g64, cudaStream_t s) {
     size_t total = (size_t)D * D;
-    gram_f64_accumulate_kernel<<<grid_for(total), 256, 0, s>>>(g32, ld32, D, g64);
+    gram_f64_accumulate_kernel<<<grid_for(total), 256, 0, s>>>(g32, ld32, D, sm, g64);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }
 
-int center_rows(float* d, int ld, int n, int cols, const float* mu, cudaStream_t s) {
+int center_rows(float* d, int ld, int n, int cols, const SegMap& sm, const float* mu, cudaStream_t s) {
     if (n <= 0) return MMAD_OK;
-    center_rows_kernel<<<grid_for((size_t)n * cols), 256, 0, s>>>(d, ld, n, cols, mu);
+    center_rows_kernel<<<grid_for((size_t)n * cols), 256, 0, s>>>(d, ld, n, cols, sm, mu);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

@@ -198,8 +198,8 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
                 if (e.ref) {
                     float d = 0.f;
                     if (c < N) d = v - e.ref[(size_t)r * e.ldref + c];
-                    if (e.dout && c < N) e.dout[(size_t)r * e.lddout + c] = d;
-                    if (e.Dh && c < N) {
+                    if (e.dout && c < e.d_cols) e.dout[(size_t)r * e.lddout + c] = d;
+                    if (e.Dh && c < e.d_cols) {
                         const float ds = d * e.d_scale;
                         __half h = __float2half_rn(ds);
                         e.Dh[(size_t)r * e.lddh + c] = h;

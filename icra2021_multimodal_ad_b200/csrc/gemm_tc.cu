@@ -34,13 +34,15 @@ constexpr int NTHREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int TMEM_COLS = 512;              // two 256-column fp32 accumulators
+constexpr int STG_LD = 36;                  // floats per row of an epilogue transpose tile (conflict-free float4)
 
 template <int PASSES> struct Cfg {
     static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
     static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int kStages = PASSES == 3 ? 2 : 4;
     static constexpr int kSmemTiles = kStages * kStageBytes;   // 192 KB
-    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 4 * 32 * STG_LD * 4 /*transpose tiles*/ +
+                                      256 /*barriers*/ + 1024 /*align*/;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -140,7 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     float* s_bias = s_mul + BN;
     float* s_sc = s_bias + BN;
     float* s_sh = s_sc + BN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sh + BN);
+    float* s_stage = s_sh + BN;                  // 4 warps x [32][STG_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * STG_LD);
     uint64_t* full = bars;                       // [kStages]  TMA -> MMA
     uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> TMA
     uint64_t* acc_full = empty + C::kStages;     // [2]        MMA -> epilogue
@@ -229,13 +232,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         }
     } else {
         // ================= epilogue (warps 2..5) =================
+        // TMEM hands each thread one accumulator ROW (32 columns per tcgen05.ld).  Row-per-thread
+        // global accesses would touch 32 different rows per instruction, so every 32x32 chunk is
+        // transposed through a warp-private smem tile and re-read as (4 rows x 8 float4 columns)
+        // per instruction: every global load/store of a warp then covers whole 128-byte row segments.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int et = threadIdx.x - 64;        // 0..127
+        float* stg = s_stage + q * (32 * STG_LD);
+        const int rsub = lane >> 3;             // 0..3  row inside a group of 4
+        const int c4 = (lane & 7) * 4;          // first of this lane's 4 columns inside the 32-column chunk
         int acc = 0; uint32_t acc_phase = 0;
-        const bool y_vec = e.Y && (e.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.Y) & 15) == 0);
-        const bool h_vec = e.Yh && (e.ldh % 8 == 0) && ((reinterpret_cast<uintptr_t>(e.Yh) & 15) == 0) &&
-                           (!e.Yl || (reinterpret_cast<uintptr_t>(e.Yl) & 15) == 0);
-        const bool ref_vec = e.ref && (e.ldref % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.ref) & 15) == 0);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
             // stage the per-column epilogue vectors of this tile
@@ -251,97 +257,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             asm volatile("bar.sync 1, 128;");
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
-            const int r = m0 + q * 32 + lane;
-            const bool rok = r < p.M;
+            const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            float sq = 0.f;
+            float sq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sq[i] = 0.f;
             int n_cols = p.N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
-            int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // columns to write (zero padded)
-            const int c_end = (max(n_cols, w_cols) + 31) & ~31;
+            int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
+            int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
+            const int c_end = (max(max(n_cols, w_cols), dw_cols) + 31) & ~31;
             for (int c0 = 0; c0 < c_end && c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                float o[32];
+                // issue this chunk's reference loads first: 8 independent 16-byte loads per lane in
+                // flight while the accumulator chunk is fetched from TMEM and transposed
+                float4 rf[8];
+                if (e.ref) {
+                    const int ccp = c0 + c4;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = c0 + j;
-                    float x = fmaf(__uint_as_float(v[j]), s_mul[c], s_bias[c]);
-                    if (e.pre && rok && c < n_cols) e.pre[(size_t)r * e.ldpre + n0 + c] = x;
-                    if (e.bn_scale) {
-                        x = x > 0.f ? x : x * e.slope;
-                        x = fmaf(x, s_sc[c], s_sh[c]);
-                    }
-                    o[j] = c < n_cols ? x : 0.f;
-                }
-                if (rok) {
-                    if (e.Y) {
-                        float* yp = e.Y + (size_t)r * e.ldy + n0 + c0;
-                        if (y_vec && c0 + 32 <= w_cols) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (c0 + j < w_cols) yp[j] = o[j];
-                        }
-                    }
-                    if (e.Yh) {
-                        __half hh[32], ll[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            hh[j] = __float2half_rn(o[j]);
-                            ll[j] = __float2half_rn(o[j] - __half2float(hh[j]));
-                        }
-                        __half* hp = e.Yh + (size_t)r * e.ldh + n0 + c0;
-                        __half* lp = e.Yl ? e.Yl + (size_t)r * e.ldh + n0 + c0 : nullptr;
-                        if (h_vec && c0 + 32 <= w_cols) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j]);
-                                if (lp) *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j]);
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (c0 + j < w_cols) { hp[j] = hh[j]; if (lp) lp[j] = ll[j]; }
-                        }
-                    }
-                    if (e.ref) {
-                        const float* rp = e.ref + (size_t)r * e.ldref + n0 + c0;
-                        float d[32];
-                        if (ref_vec && c0 + 32 <= n_cols) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 f = *reinterpret_cast<const float4*>(rp + j);
-                                d[j] = o[j] - f.x; d[j + 1] = o[j + 1] - f.y; d[j + 2] = o[j + 2] - f.z; d[j + 3] = o[j + 3] - f.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) d[j] = (c0 + j < n_cols) ? o[j] - rp[j] : 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sq = fmaf(d[j], d[j], sq);
-                        if (e.dout) {
-                            float* dp = e.dout + (size_t)r * e.lddout + n0 + c0;
-                            for (int j = 0; j < 32; ++j) if (c0 + j < n_cols) dp[j] = d[j];
-                        }
-                        if (e.Dh) {
-                            __half* hp = e.Dh + (size_t)r * e.lddh + n0 + c0;
-                            __half* lp = e.Dl + (size_t)r * e.lddh + n0 + c0;
-                            for (int j = 0; j < 32; ++j) if (c0 + j < n_cols) {
-                                const float ds = d[j] * e.d_scale;
-                                const __half h = __float2half_rn(ds);
-                                hp[j] = h;
-                                lp[j] = __float2half_rn(ds - __half2float(h));
-                            }
-                        }
-                    } else if (e.sq_self) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sq = fmaf(o[j], o[j], sq);
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = row_base + it * 4 + rsub;
+                        rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < p.M && ccp + 3 < n_cols)
+                            rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + ccp));
                     }
                 }
+                {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    float4* wr = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        wr[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+                __syncwarp();
+                const int cc = c0 + c4;                 // tile-local column of this lane's float4
+                const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
+                const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc);
+                const float4 sh = *reinterpret_cast<const float4*>(s_sh + cc);
+                const bool k0 = cc < n_cols, k1 = cc + 1 < n_cols, k2 = cc + 2 < n_cols, k3 = cc + 3 < n_cols;
+                const bool wy = cc < w_cols, wd = cc < dw_cols;   // widths are multiples of 4 (padded to 64)
+                const size_t gcol = (size_t)n0 + cc;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rl = it * 4 + rsub;
+                    const int r = row_base + rl;
+                    const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
+                    float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
+                    float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
+                    if (r < p.M) {
+                        if (e.pre && k0) {     // train: pre-activation (scalar: caller-owned layout)
+                            float* pp = e.pre + (size_t)r * e.ldpre + gcol;
+                            pp[0] = x0; if (k1) pp[1] = x1; if (k2) pp[2] = x2; if (k3) pp[3] = x3;
+                        }
+                        if (e.bn_scale) {
+                            x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
+                            x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
+                            x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
+                            x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
+                        }
+                        x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
+                        if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
+                        if (e.Yh && wy) {
+                            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                            uint2 hv;
+                            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
+                            if (e.Yl) {
+                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
+                                const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                                uint2 lv;
+                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
+                            }
+                        }
+                        if (e.ref) {
+                            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                            if (k3) {
+                                const float4 f = rf[it];
+                                d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
+                            } else if (k0) {
+                                const float* rp = e.ref + (size_t)r * e.ldref + gcol;
+                                d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
+                            }
+                            sq[it] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq[it]))));
+                            if (e.dout && wd) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + gcol) = make_float4(d0, d1, d2, d3);
+                            if (e.Dh && wd) {
+                                const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
+                                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
+                                const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                                uint2 hv, lv;
+                                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + gcol) = hv;
+                                *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + gcol) = lv;
+                            }
+                        } else if (e.sq_self) {
+                            sq[it] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq[it]))));
+                        }
+                    }
+                }
+                __syncwarp();     // the staging tile is rewritten by the next chunk
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc]));
-            if (e.rowpart && rok) e.rowpart[(size_t)tn * e.rowpart_stride + r] = sq;
+            if (e.rowpart) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    float v = sq[it];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    const int r = row_base + it * 4 + rsub;
+                    if ((lane & 7) == 0 && r < p.M) e.rowpart[(size_t)tn * e.rowpart_stride + r] = v;
+                }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -411,6 +446,12 @@ int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int k, i
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s) {
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
+    auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
+    if (!al(e.Y, e.ldy, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) || !al(e.dout, e.lddout, 4) ||
+        !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (e.y_cols % 4) || (e.d_cols % 4)) {
+        set_error("gemm_tc: epilogue buffers must be 16-byte aligned with padded leading dimensions");
+        return MMAD_E_ARG;
+    }
     TcParams p;
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = (M + BM - 1) / BM;

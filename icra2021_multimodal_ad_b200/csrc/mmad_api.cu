@@ -85,6 +85,19 @@ static int concat_width(mmad_t h, int lo, int hi) {
     return s;
 }
 
+static SegMap make_segmap(mmad_t h, int lo, int hi) {
+    SegMap m;
+    int t = 0, p = 0, n = 0;
+    for (int l = lo; l < hi; ++l, ++n) {
+        m.tight_off[n] = t; m.pad_off[n] = p;
+        t += width_of_diff(h, l);
+        p += round_up(width_of_diff(h, l), kPad);
+    }
+    m.n = n;
+    m.tight_off[n] = t; m.pad_off[n] = p;
+    return m;
+}
+
 static void free_layer(Layer& L) {
     cudaFree(L.W); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); cudaFree(L.Wh); cudaFree(L.Wl);
     L = Layer();
@@ -112,7 +125,8 @@ struct Plan {
     size_t dh = 0, dl = 0;
     int slot_off[MMAD_MAX_LAYERS + 3] = {0};   // rowpart slot ranges per diff index, then NAP slots
     int n_slots = 0;
-    int Dselp = 0;
+    int Dselp = 0;          // padded width of the concatenated diffs in the workspace
+    SegMap seg;             // tight <-> padded column map of the selected layers
 };
 
 struct PlanOpts {
@@ -154,9 +168,10 @@ static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
     p.slot_off[L + 2] = slots;
     p.n_slots = slots;
     p.rowpart = take((size_t)slots * RR * 4);
-    p.Dselp = round_up(std::max(1, concat_width(h, o.lo, o.hi)), kPad);
+    p.seg = make_segmap(h, o.lo, o.hi);
+    p.Dselp = std::max(kPad, p.seg.pad_off[p.seg.n]);
     if (o.diffs_ws) p.diffs = take(RR * p.Dselp * 4);
-    if (o.gram) p.gram32 = take((size_t)concat_width(h, o.lo, o.hi) * p.Dselp * 4);
+    if (o.gram) p.gram32 = take((size_t)p.Dselp * p.Dselp * 4);
     if (o.tc) {
         p.xh = take(RR * Dp * 2);
         p.xl = take(RR * Dp * 2);
@@ -234,7 +249,7 @@ struct ChainOut {
     bool need_d0 = false;                       // row sums of d_0^2 into rowpart slots of l=0
     int lo = 0, hi = 0;                         // diffs [lo,hi) wanted (row sums and/or values)
     bool need_rowsums = false;
-    float* dout = nullptr; int lddout = 0;      // concatenated diffs destination (caller or workspace)
+    float* dout = nullptr; int lddout = 0;      // padded concatenated diffs in the workspace (Plan::seg layout)
     __half* dh = nullptr; __half* dl = nullptr; int lddh = 0;
 };
 
@@ -243,16 +258,18 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
     const int L = h->desc.n_enc, Ld = h->desc.n_dec, D = D_of(h);
     const int Dp = round_up(D, kPad);
     const bool tc = h->desc.precision != MMAD_PREC_FP32;
-    const bool x_direct = !tc && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool x_aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool x_direct = !tc && x_aligned;
     Act a0;
     if (x_direct) {
         a0.f = x; a0.ld = ldx;
     } else {
-        int rc = pad_split(x, ldx, rows, D, (float*)(ws + p.xp), Dp, tc ? (__half*)(ws + p.xh) : nullptr,
+        int rc = pad_split(x, ldx, rows, D, (tc && x_aligned) ? nullptr : (float*)(ws + p.xp), Dp, tc ? (__half*)(ws + p.xh) : nullptr,
                            tc ? (__half*)(ws + p.xl) : nullptr, Dp, s);
         if (rc) return rc;
         a0.f = (const float*)(ws + p.xp); a0.ld = Dp;
         a0.h = (const __half*)(ws + p.xh); a0.l = (const __half*)(ws + p.xl); a0.ldh = Dp;
+        if (x_aligned) { a0.f = x; a0.ld = ldx; }   // d_0 reads the caller's x directly
     }
     const bool want_enc2 = co.hi > 1 && co.hi > co.lo;   // any d_l with l>=1 requested
     // ---- encoder on x ----
@@ -276,11 +293,16 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         const Layer& Lr = h->dec[l - 1];
         Epilogue e;
         e.Y = (float*)(ws + p.G[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
-        if (tc) { e.Yh = (__half*)(ws + p.Gh[l]); e.Yl = (__half*)(ws + p.Gl[l]); e.ldh = Lr.Np; }
+        if (tc) {   // the next layer reads the fp16 pair; fp32 is only kept when the caller wants xhat
+            e.Yh = (__half*)(ws + p.Gh[l]); e.Yl = (__half*)(ws + p.Gl[l]); e.ldh = Lr.Np;
+            if (!(l == Ld && co.xhat)) e.Y = nullptr;
+            if (l == Ld && !want_enc2) { e.Yh = nullptr; e.Yl = nullptr; }
+        }
         if (l == Ld && (co.need_d0 || (co.lo == 0 && co.hi > 0))) {
             e.ref = a0.f; e.ldref = a0.ld;
             e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[0] * p.R; e.rowpart_stride = p.R;
             if (co.lo == 0 && co.hi > 0) {
+                e.d_cols = Lr.Np;
                 if (co.dout) { e.dout = co.dout; e.lddout = co.lddout; }
                 if (co.dh) { e.Dh = co.dh; e.Dl = co.dl; e.lddh = co.lddh; e.d_scale = kDiffScale; }
             }
@@ -289,7 +311,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         if (rc) return rc;
         cur = Act{e.Y, Lr.Np, e.Yh, e.Yl, Lr.Np};
     }
-    if (co.lo == 0 && co.hi > 0) col_off = D;
+    if (co.lo == 0 && co.hi > 0) col_off = Dp;
     if (co.xhat) {
         MMAD_CUDA_OK(cudaMemcpy2DAsync(co.xhat, (size_t)co.ldxhat * 4, ws + p.G[Ld], (size_t)h->dec[Ld - 1].Np * 4,
                                        (size_t)D * 4, rows, cudaMemcpyDeviceToDevice, s));
@@ -301,14 +323,15 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         const Layer& Lr = h->enc[l - 1];
         Epilogue e;
         e.Y = (float*)(ws + p.E[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
-        if (tc) { e.Yh = (__half*)(ws + p.Eh[l]); e.Yl = (__half*)(ws + p.El[l]); e.ldh = Lr.Np; }
+        if (tc) { e.Yh = (__half*)(ws + p.Eh[l]); e.Yl = (__half*)(ws + p.El[l]); e.ldh = Lr.Np; e.Y = nullptr; }
         if (l == last) { e.Y = nullptr; e.Yh = nullptr; e.Yl = nullptr; }   // nothing consumes it
         if (l >= co.lo) {
             e.ref = (const float*)(ws + p.H[l]); e.ldref = Lr.Np;
             e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[l] * p.R; e.rowpart_stride = p.R;
+            e.d_cols = Lr.Np;
             if (co.dout) { e.dout = co.dout + col_off; e.lddout = co.lddout; }
             if (co.dh) { e.Dh = co.dh + col_off; e.Dl = co.dl + col_off; e.lddh = co.lddh; e.d_scale = kDiffScale; }
-            col_off += Lr.N;
+            col_off += Lr.Np;
         }
         int rc = run_layer(h, Lr, cur, rows, e, s);
         if (rc) return rc;
@@ -470,7 +493,7 @@ int mmad_fc_layer_forward(const float* d_x, int ldx, int n, int K, int N, const 
 size_t mmad_workspace_bytes(mmad_t h, int max_rows) {
     if (!h || max_rows < 1) return 0;
     PlanOpts o;
-    o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.gram = false; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
+    o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.gram = true; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
     int R = round_up(std::min(max_rows, kMaxChunk), 128);
     return make_plan(h, R, o).total;
 }
@@ -532,7 +555,7 @@ int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss, v
 static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, cudaStream_t s) {
     const NapFit& f = h->nap;
     const int L = h->desc.n_enc;
-    ProfScope prof(h, s, 2.0 * rows * (double)f.K * (double)f.D);
+    ProfScope prof(h, s, 2.0 * rows * (double)f.K * (double)f.D);   // algorithmic: tight D'
     Epilogue e;
     e.bias = f.bias;
     e.col_scale = f.colscale;
@@ -542,18 +565,18 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
     int rc;
     if (h->desc.precision == MMAD_PREC_FP32) {
         GemmShape g;
-        g.M = rows; g.N = f.K; g.K = f.D;
+        g.M = rows; g.N = f.K; g.K = f.Dp;
         g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp;
         g.B = f.B; g.ldb = f.Dp;
         rc = gemm_simt(g, e, s);
     } else {
         TcOperand A;
-        rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.D, p.Dselp, 128);
-        if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.D, p.Dselp, 128);
+        rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.Dp, p.Dselp, 128);
+        if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.Dp, p.Dselp, 128);
         if (rc) return rc;
-        A.rows = rows; A.k = f.D;
+        A.rows = rows; A.k = f.Dp;
         e.acc_scale = 1.f / (f.wscale * kDiffScale);
-        rc = gemm_tc(A, f.tcB, rows, f.K, f.D, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
+        rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
     }
     if (rc) return rc;
     return finalize_sum((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[L + 1], p.slot_off[L + 2], 1.f / f.K,
@@ -574,7 +597,7 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = h->desc.precision != MMAD_PREC_FP32;
     PlanOpts o;
-    o.lo = lo; o.hi = hi; o.tc = tc; o.diffs_ws = d_nap != nullptr;
+    o.lo = lo; o.hi = hi; o.tc = tc; o.diffs_ws = d_nap != nullptr || d_diffs != nullptr;
     const int Dsel = concat_width(h, lo, hi);
     Plan p;
     for (int r0 = 0; r0 < n;) {
@@ -587,12 +610,8 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
         co.hi = (d_sap || d_nap || d_diffs) ? hi : 0;
         co.need_d0 = d_base != nullptr;
         co.need_rowsums = d_sap != nullptr;
-        if (d_nap) {
-            co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
-            if (tc) { co.dh = (__half*)(ws + p.dh); co.dl = (__half*)(ws + p.dl); co.lddh = p.Dselp; }
-        } else if (d_diffs) {
-            co.dout = d_diffs + (size_t)r0 * Dsel; co.lddout = Dsel;
-        }
+        if (d_diffs || (d_nap && !tc)) { co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp; }
+        if (d_nap && tc) { co.dh = (__half*)(ws + p.dh); co.dl = (__half*)(ws + p.dl); co.lddh = p.Dselp; }
         rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
         if (rc) return rc;
         if (d_base || d_sap) {
@@ -601,10 +620,14 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
                                  d_base ? d_base + r0 : nullptr, d_sap ? d_sap + r0 : nullptr, s);
             if (rc) return rc;
         }
+        if (d_diffs) {   // padded workspace segments -> the reference's tight concatenation
+            for (int i = 0; i < p.seg.n; ++i)
+                MMAD_CUDA_OK(cudaMemcpy2DAsync(d_diffs + (size_t)r0 * Dsel + p.seg.tight_off[i], (size_t)Dsel * 4,
+                                               ws + p.diffs + (size_t)p.seg.pad_off[i] * 4, (size_t)p.Dselp * 4,
+                                               (size_t)(p.seg.tight_off[i + 1] - p.seg.tight_off[i]) * 4, rows,
+                                               cudaMemcpyDeviceToDevice, s));
+        }
         if (d_nap) {
-            if (d_diffs)
-                MMAD_CUDA_OK(cudaMemcpy2DAsync(d_diffs + (size_t)r0 * Dsel, (size_t)Dsel * 4, ws + p.diffs,
-                                               (size_t)p.Dselp * 4, (size_t)Dsel * 4, rows, cudaMemcpyDeviceToDevice, s));
             rc = nap_gemm(h, p, ws, rows, d_nap + r0, s);
             if (rc) return rc;
         }
@@ -633,7 +656,7 @@ int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int lo, 
         co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
         rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
         if (rc) return rc;
-        rc = colsum_f64((const float*)(ws + p.diffs), p.Dselp, rows, Dsel, d_sum, s);
+        rc = colsum_f64((const float*)(ws + p.diffs), p.Dselp, rows, Dsel, p.seg, d_sum, s);
         if (rc) return rc;
         r0 += rows;
     }
@@ -660,18 +683,18 @@ int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lo,
         co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp;
         rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
         if (rc) return rc;
-        rc = center_rows((float*)(ws + p.diffs), p.Dselp, rows, Dsel, d_mu, s);
+        rc = center_rows((float*)(ws + p.diffs), p.Dselp, rows, Dsel, p.seg, d_mu, s);
         if (rc) return rc;
         // G32 = Dc^T Dc : both operands are the [rows, Dsel] diff matrix read "transposed"
         GemmShape g;
-        g.M = Dsel; g.N = Dsel; g.K = rows;
+        g.M = p.Dselp; g.N = p.Dselp; g.K = rows;    // padded columns are zero -> zero rows/cols of G32
         g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp; g.transA = true;
         g.B = (const float*)(ws + p.diffs); g.ldb = p.Dselp; g.transB = true;
         Epilogue e;
-        e.Y = (float*)(ws + p.gram32); e.ldy = p.Dselp; e.y_cols = Dsel;
+        e.Y = (float*)(ws + p.gram32); e.ldy = p.Dselp; e.y_cols = p.Dselp;
         rc = gemm_simt(g, e, s);
         if (rc) return rc;
-        rc = gram_f64_accumulate((const float*)(ws + p.gram32), p.Dselp, Dsel, d_gram, s);
+        rc = gram_f64_accumulate((const float*)(ws + p.gram32), p.Dselp, Dsel, p.seg, d_gram, s);
         if (rc) return rc;
         r0 += rows;
     }
@@ -690,21 +713,22 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
     MMAD_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.Bh); cudaFree(f.Bl);
     f = NapFit();
-    f.lo = lo; f.hi = hi; f.K = K; f.D = D; f.Dp = round_up(D, kPad);
+    const SegMap seg = make_segmap(h, lo, hi);
+    f.lo = lo; f.hi = hi; f.K = K; f.D = D; f.Dp = seg.pad_off[seg.n];
     MMAD_CUDA_OK(cudaMalloc(&f.B, (size_t)K * f.Dp * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.colscale, (size_t)round_up(K, kPad) * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.bias, (size_t)round_up(K, kPad) * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.Bh, (size_t)K * f.Dp * 2));
     MMAD_CUDA_OK(cudaMalloc(&f.Bl, (size_t)K * f.Dp * 2));
-    rc = nap_pack(d_mu, d_vt, d_var, d_mu2, K, D, f.Dp, f.B, f.colscale, f.bias, s);
+    rc = nap_pack(d_mu, d_vt, d_var, d_mu2, K, D, f.Dp, seg, f.B, f.colscale, f.bias, s);
     if (rc) return rc;
-    rc = split_weights(d_vt, K, D, f.Dp, f.wscale, f.Bh, f.Bl, s);
+    rc = split_weights(f.B, K, f.Dp, f.Dp, f.wscale, f.Bh, f.Bl, s);
     if (rc) return rc;
     if (tc_available()) {
-        rc = tc_make_operand_map(&f.tcB.hi, f.Bh, K, D, f.Dp, gemm_tc_tile_n());
-        if (!rc) rc = tc_make_operand_map(&f.tcB.lo, f.Bl, K, D, f.Dp, gemm_tc_tile_n());
+        rc = tc_make_operand_map(&f.tcB.hi, f.Bh, K, f.Dp, f.Dp, gemm_tc_tile_n());
+        if (!rc) rc = tc_make_operand_map(&f.tcB.lo, f.Bl, K, f.Dp, f.Dp, gemm_tc_tile_n());
         if (rc) return rc;
-        f.tcB.rows = K; f.tcB.k = D;
+        f.tcB.rows = K; f.tcB.k = f.Dp;
         f.tc_ready = true;
     }
     f.ready = true;
@@ -754,8 +778,12 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         const int rows = (int)std::min<long long>(h->host_chunk, n - r0);
         // input buffer b is free once the compute that read it two iterations ago is done
         if (it >= 2) MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
-        MMAD_CUDA_OK(cudaMemcpy2DAsync(h->host_x[b], (size_t)D * 4, h_x + (size_t)r0 * ldx, (size_t)ldx * 4,
-                                       (size_t)D * 4, rows, cudaMemcpyHostToDevice, h->s_copy));
+        if (ldx == D)
+            MMAD_CUDA_OK(cudaMemcpyAsync(h->host_x[b], h_x + (size_t)r0 * ldx, (size_t)rows * D * 4,
+                                         cudaMemcpyHostToDevice, h->s_copy));
+        else
+            MMAD_CUDA_OK(cudaMemcpy2DAsync(h->host_x[b], (size_t)D * 4, h_x + (size_t)r0 * ldx, (size_t)ldx * 4,
+                                           (size_t)D * 4, rows, cudaMemcpyHostToDevice, h->s_copy));
         MMAD_CUDA_OK(cudaEventRecord(h->ev_in[b], h->s_copy));
         MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_comp, h->ev_in[b], 0));
         float* o = h->host_out[b];

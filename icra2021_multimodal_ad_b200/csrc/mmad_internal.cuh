@@ -55,6 +55,7 @@ struct Epilogue {
     float* dout = nullptr; int lddout = 0;
     __half* Dh = nullptr; __half* Dl = nullptr; int lddh = 0;   // fp16 split of d * d_scale (NAP operand)
     float d_scale = 1.0f;
+    int d_cols = 0;                                      // dout/Dh/Dl columns written (>= N: zero filled)
     float* rowpart = nullptr; int rowpart_stride = 0;   // [tiles_n][rowpart_stride]
     int sq_self = 0;
     float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
@@ -66,6 +67,20 @@ struct GemmShape {
     const float* B; int ldb;     // [N, K] (or [K, N] when transB)
     bool transA = false, transB = false;
 };
+
+// Column map of the concatenated diffs: the workspace copy pads every layer segment to a
+// multiple of kPad columns (aligned vector stores, TMA-legal strides); 'tight' is the reference's
+// concatenation (utils/metric.py:166-167).
+struct SegMap {
+    int n = 0;
+    int tight_off[MMAD_MAX_LAYERS + 2] = {0};
+    int pad_off[MMAD_MAX_LAYERS + 2] = {0};
+};
+__host__ __device__ inline int seg_pad_col(const SegMap& m, int c) {
+    int i = 0;
+    while (i + 1 < m.n && c >= m.tight_off[i + 1]) ++i;
+    return m.pad_off[i] + (c - m.tight_off[i]);
+}
 
 // CUDA-core fp32 GEMM with the fused epilogue (gemm_simt.cu)
 int gemm_simt(const GemmShape& g, const Epilogue& e, cudaStream_t s);
@@ -95,10 +110,10 @@ int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slo
 int fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int N, int Np,
             float* scale, float* shift, cudaStream_t s);
 int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s);
-int colsum_f64(const float* d, int ld, int n, int cols, double* sum, cudaStream_t s);
-int gram_f64_accumulate(const float* g32, int ld32, int D, double* g64, cudaStream_t s);
-int center_rows(float* d, int ld, int n, int cols, const float* mu, cudaStream_t s);
+int colsum_f64(const float* d, int ld, int n, int cols, const SegMap& sm, double* sum, cudaStream_t s);
+int gram_f64_accumulate(const float* g32, int ld32, int D, const SegMap& sm, double* g64, cudaStream_t s);
+int center_rows(float* d, int ld, int n, int cols, const SegMap& sm, const float* mu, cudaStream_t s);
 int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp,
-             float* B, float* colscale, float* bias, cudaStream_t s);
+             const SegMap& sm, float* B, float* colscale, float* bias, cudaStream_t s);
 
 }  // namespace mmad

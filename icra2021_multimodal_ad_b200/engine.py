@@ -195,13 +195,7 @@ class Engine:
 
     def nap_accumulate_gram(self, x: torch.Tensor, lo: int, hi: int, mu: torch.Tensor, gram: torch.Tensor):
         x = self._check_x(x)
-        # the gram pass needs an extra [Dsel, Dsel] fp32 tile in the workspace
-        dsel = self.concat_width(lo, hi)
-        need = lib().mmad_workspace_bytes(self._h, min(max(x.shape[0], 128), 16384)) + dsel * (dsel + 64) * 4 + 4096
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws_rows = 16384
-        ws = self._ws
+        ws = self.workspace(x.shape[0])
         with torch.cuda.device(self.device):
             check(lib().mmad_nap_accumulate_gram(self._h, x.data_ptr(), x.stride(0) if x.shape[0] > 1 else self.D,
                                                  x.shape[0], lo, hi, mu.data_ptr(), gram.data_ptr(), ws.data_ptr(),
