@@ -53,6 +53,11 @@ SIGNATURES = {
     "mmad_sq_diff_sum": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "mmad_row_mean_sq": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mmad_vib_reparam": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mmad_normalizer_workspace_bytes": (_sz, [_i]),
+    "mmad_col_stats": (_i, [_vp, _i, _ll, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmad_gram_accumulate": (_i, [_vp, _i, _ll, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmad_rotate": (_i, [_vp, _i, _ll, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),
+    "mmad_standardize": (_i, [_vp, _i, _ll, _i, _vp, _vp, _vp, _i, _vp]),
     "mmad_metric_workspace_bytes": (_sz, [_ll]),
     "mmad_auc_roc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "mmad_auc_prc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),

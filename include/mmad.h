@@ -146,6 +146,25 @@ int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lay
 int mmad_nap_set_fit(mmad_t h, int layer_lo, int layer_hi, int K, const float* d_mu,
                      const float* d_vt, const float* d_var, const float* d_mu2, void* stream);
 
+/* ---- stand-alone normaliser ops (utils/normalize.py API compatibility: Rotater / Standardizer on
+ * arbitrary device matrices d[n, cols], row stride ld) ----
+ * mmad_col_stats: d_mean[cols] = column means (fp64 accumulation, utils/normalize.py:31,61);
+ *   d_var (optional) = diag(np.cov) with ddof=1 (normalize.py:34).
+ * mmad_gram_accumulate: d_gram[cols*cols] (fp64) += (d-mu)^T (d-mu)  (basis of Rotater.fit: the right
+ *   singular vectors of the centred matrix are the eigenvectors of this Gram matrix).
+ * mmad_rotate: d_out[n, K] = (d - mu) V with d_vt = V^T [K, cols] row-major (normalize.py:72-103).
+ * mmad_standardize: d_out = (d - mu) / sqrt(var) (normalize.py:36-45; no epsilon, like the reference).
+ * ws: mmad_normalizer_workspace_bytes(cols). */
+size_t mmad_normalizer_workspace_bytes(int cols);
+int mmad_col_stats(const float* d_d, int ld, long long n, int cols, float* d_mean, float* d_var, void* d_ws,
+                   size_t ws_bytes, void* stream);
+int mmad_gram_accumulate(const float* d_d, int ld, long long n, int cols, const float* d_mu, double* d_gram,
+                         void* d_ws, size_t ws_bytes, void* stream);
+int mmad_rotate(const float* d_d, int ld, long long n, int cols, const float* d_mu, const float* d_vt, int K,
+                float* d_out, int ldo, void* d_ws, size_t ws_bytes, void* stream);
+int mmad_standardize(const float* d_d, int ld, long long n, int cols, const float* d_mu, const float* d_var,
+                     float* d_out, int ldo, void* stream);
+
 /* ---- metrics: utils/metric.py:29-130 (sklearn roc_curve/auc, precision_recall_curve,
  * np.quantile, F1, confusion) on device.  d_score fp32, d_label uint8 (0/1).
  * h_out receives doubles; results are bit-identical to the reference given identical
