@@ -124,7 +124,8 @@ __global__ void gram_f64_accumulate_kernel(const float* __restrict__ g32, int ld
 // bias[j] = -(mu . v_j + mu2_j) * var_j^-1/2   (utils/normalize.py:36-45,72-103 folded)
 __global__ void nap_pack_kernel(const float* __restrict__ mu, const float* __restrict__ vt, const float* __restrict__ var,
                                 const float* __restrict__ mu2, int K, int D, int Dp, SegMap seg,
-                                float* __restrict__ B, float* __restrict__ colscale, float* __restrict__ bias) {
+                                float* __restrict__ B, float* __restrict__ colscale, float* __restrict__ bias,
+                                float* __restrict__ bias_rot) {
     const int j = blockIdx.x;
     double dot = 0.0;
     for (int c = threadIdx.x; c < Dp; c += blockDim.x) B[(size_t)j * Dp + c] = 0.f;
@@ -145,7 +146,33 @@ __global__ void nap_pack_kernel(const float* __restrict__ mu, const float* __res
         float inv = 1.0f / sqrtf(var[j]);
         colscale[j] = inv;
         bias[j] = -((float)sm[0] + mu2[j]) * inv;
+        bias_rot[j] = -(float)sm[0];          // Rotater.run alone: (d - mu) . v_j
     }
+}
+
+// Standardizer refit on rotated train rows (utils/normalize.py:25-34): colscale = var^-1/2,
+// bias = (bias_rot - mu2) * var^-1/2
+__global__ void nap_restandardize_kernel(const float* __restrict__ var, const float* __restrict__ mu2,
+                                         const float* __restrict__ bias_rot, int K, float* __restrict__ colscale,
+                                         float* __restrict__ bias) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    float inv = 1.0f / sqrtf(var[j]);
+    colscale[j] = inv;
+    bias[j] = (bias_rot[j] - mu2[j]) * inv;
+}
+
+// sum[c] += sum_r y[r,c];  sq[c] += sum_r y[r,c]^2   (fp64; grid: x over columns, y over row slabs)
+__global__ void col_sum_sq_f64_kernel(const float* __restrict__ y, int ld, int n, int cols, double* __restrict__ sum,
+                                      double* __restrict__ sq) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int rows_per = (n + gridDim.y - 1) / gridDim.y;
+    int r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    double a = 0.0, b = 0.0;
+    for (int r = r0; r < r1; ++r) { double v = (double)y[(size_t)r * ld + c]; a += v; b = fma(v, v, b); }
+    atomicAdd(&sum[c], a);
+    atomicAdd(&sq[c], b);
 }
 
 __global__ void center_rows_kernel(float* __restrict__ d, int ld, int n, int cols, SegMap sm,
@@ -155,6 +182,59 @@ __global__ void center_rows_kernel(float* __restrict__ d, int ld, int n, int col
         int r = (int)(i / cols), c = (int)(i % cols);
         d[(size_t)r * ld + seg_pad_col(sm, c)] -= mu[c];
     }
+}
+
+// G64[i, j] += sum_r dc[r, pad(i)] * dc[r, pad(j)] with fp64 products and accumulation (exact products of
+// fp32 inputs): the NAP fit needs eigenvalues ~1e-14 of the largest one, which an fp32 Gram
+// cannot resolve.  64x64 output tile per CTA, 4x4 doubles per thread, row slabs of 16 staged in smem.
+__global__ void __launch_bounds__(256)
+gram_f64_direct_kernel(const float* __restrict__ dc, int ld, int rows, int D, SegMap sm, double* __restrict__ g64) {
+    __shared__ float As[16][64 + 1];
+    __shared__ float Bs[16][64 + 1];
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    if (j0 + 63 < i0) return;                      // lower triangle is mirrored below
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    __shared__ int pa[64], pb[64];
+    if (threadIdx.x < 64) {
+        pa[threadIdx.x] = (i0 + threadIdx.x < D) ? seg_pad_col(sm, i0 + threadIdx.x) : -1;
+        pb[threadIdx.x] = (j0 + threadIdx.x < D) ? seg_pad_col(sm, j0 + threadIdx.x) : -1;
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int rr = e / 64, c = e % 64;
+            const int r = r0 + rr;
+            As[rr][c] = (r < rows && pa[c] >= 0) ? dc[(size_t)r * ld + pa[c]] : 0.f;
+            Bs[rr][c] = (r < rows && pb[c] >= 0) ? dc[(size_t)r * ld + pb[c]] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = (double)As[rr][ty * 4 + q]; b[q] = (double)Bs[rr][tx * 4 + q]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
+            if (i < D && j < D && i <= j) {
+                g64[(size_t)i * D + j] += acc[x][y];
+                if (i != j) g64[(size_t)j * D + i] += acc[x][y];
+            }
+        }
 }
 
 inline int grid_for(size_t total, int block = 256) {
@@ -231,8 +311,25 @@ int colsum_f64(const float* d, int ld, int n, int cols, const SegMap& sm, double
 }
 
 int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp,
-             const SegMap& sm, float* B, float* colscale, float* bias, cudaStream_t s) {
-    nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, sm, B, colscale, bias);
+             const SegMap& sm, float* B, float* colscale, float* bias, float* bias_rot, cudaStream_t s) {
+    nap_pack_kernel<<<K, 256, 0, s>>>(mu, vt, var, mu2, K, D, Dp, sm, B, colscale, bias, bias_rot);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int nap_restandardize(const float* var, const float* mu2, const float* bias_rot, int K, float* colscale, float* bias,
+                      cudaStream_t s) {
+    nap_restandardize_kernel<<<(K + 255) / 256, 256, 0, s>>>(var, mu2, bias_rot, K, colscale, bias);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int col_sum_sq_f64(const float* y, int ld, int n, int cols, double* sum, double* sq, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    dim3 grid((cols + 127) / 128, n >= 4096 ? 32 : (n >= 256 ? 8 : 1));
+    col_sum_sq_f64_kernel<<<grid, 128, 0, s>>>(y, ld, n, cols, sum, sq);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
@@ -241,6 +338,15 @@ int nap_pack(const float* mu, const float* vt, const float* var, const float* mu
 int gram_f64_accumulate(const float* g32, int ld32, int D, const SegMap& sm, double* g64, cudaStream_t s) {
     size_t total = (size_t)D * D;
     gram_f64_accumulate_kernel<<<grid_for(total), 256, 0, s>>>(g32, ld32, D, sm, g64);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int gram_f64_direct(const float* dc, int ld, int rows, int D, const SegMap& sm, double* g64, cudaStream_t s) {
+    if (rows <= 0) return MMAD_OK;
+    dim3 grid((D + 63) / 64, (D + 63) / 64);
+    gram_f64_direct_kernel<<<grid, 256, 0, s>>>(dc, ld, rows, D, sm, g64);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

@@ -41,6 +41,7 @@ struct NapFit {
     float* B = nullptr;         // [K, Dp] rows v_j
     float* colscale = nullptr;  // [K] var_j^-1/2
     float* bias = nullptr;      // [K] -(mu.v_j + mu2_j) var_j^-1/2
+    float* bias_rot = nullptr;  // [K] -mu.v_j  (rotation alone, for the Standardizer refit pass)
     float wscale = 256.f;
     __half* Bh = nullptr;
     __half* Bl = nullptr;
@@ -117,6 +118,7 @@ struct Plan {
     size_t rowpart = 0;
     size_t diffs = 0;
     size_t gram32 = 0;
+    size_t rot = 0;         // [R, Kp] rotated rows (Standardizer refit pass)
     // fp16 hi/lo twins (tensor-core modes)
     size_t xh = 0, xl = 0;
     size_t Hh[MMAD_MAX_LAYERS + 1] = {0}, Hl[MMAD_MAX_LAYERS + 1] = {0};
@@ -133,6 +135,7 @@ struct PlanOpts {
     int lo = 0, hi = 0;
     bool diffs_ws = false;   // concatenated diffs materialised in the workspace
     bool gram = false;
+    bool rot = false;        // rotated rows materialised (mmad_nap_rotate_stats)
     bool tc = false;
 };
 
@@ -172,6 +175,7 @@ static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
     p.Dselp = std::max(kPad, p.seg.pad_off[p.seg.n]);
     if (o.diffs_ws) p.diffs = take(RR * p.Dselp * 4);
     if (o.gram) p.gram32 = take((size_t)p.Dselp * p.Dselp * 4);
+    if (o.rot) p.rot = take(RR * round_up(nap_k, kPad) * 4);
     if (o.tc) {
         p.xh = take(RR * Dp * 2);
         p.xl = take(RR * Dp * 2);
@@ -413,7 +417,8 @@ int mmad_destroy(mmad_t h) {
     if (!h) return MMAD_OK;
     for (auto& L : h->enc) free_layer(L);
     for (auto& L : h->dec) free_layer(L);
-    cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.Bh); cudaFree(h->nap.Bl);
+    cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);
+    cudaFree(h->nap.Bh); cudaFree(h->nap.Bl);
     cudaFree(h->host_ws);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->host_x[i]); cudaFree(h->host_out[i]);
@@ -493,7 +498,7 @@ int mmad_fc_layer_forward(const float* d_x, int ldx, int n, int K, int N, const 
 size_t mmad_workspace_bytes(mmad_t h, int max_rows) {
     if (!h || max_rows < 1) return 0;
     PlanOpts o;
-    o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.gram = true; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
+    o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
     int R = round_up(std::min(max_rows, kMaxChunk), 128);
     return make_plan(h, R, o).total;
 }
@@ -552,16 +557,23 @@ int mmad_recon_loss(mmad_t h, const float* d_x, int ldx, int n, float* d_loss, v
     return MMAD_OK;
 }
 
+// d_nap != NULL: standardised squared-norm scores.  d_nap == NULL: the rotation alone,
+// rot = (d - mu) V (utils/normalize.py:72-103), written to the workspace [rows, round_up(K, 64)].
 static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, cudaStream_t s) {
     const NapFit& f = h->nap;
     const int L = h->desc.n_enc;
     ProfScope prof(h, s, 2.0 * rows * (double)f.K * (double)f.D);   // algorithmic: tight D'
     Epilogue e;
-    e.bias = f.bias;
-    e.col_scale = f.colscale;
-    e.sq_self = 1;
-    e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[L + 1] * p.R;
-    e.rowpart_stride = p.R;
+    if (d_nap) {
+        e.bias = f.bias;
+        e.col_scale = f.colscale;
+        e.sq_self = 1;
+        e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[L + 1] * p.R;
+        e.rowpart_stride = p.R;
+    } else {
+        e.bias = f.bias_rot;
+        e.Y = (float*)(ws + p.rot); e.ldy = round_up(f.K, kPad); e.y_cols = e.ldy;
+    }
     int rc;
     if (h->desc.precision == MMAD_PREC_FP32) {
         GemmShape g;
@@ -578,7 +590,7 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         e.acc_scale = 1.f / (f.wscale * kDiffScale);
         rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
     }
-    if (rc) return rc;
+    if (rc || !d_nap) return rc;
     return finalize_sum((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[L + 1], p.slot_off[L + 2], 1.f / f.K,
                         d_nap, s);
 }
@@ -685,16 +697,8 @@ int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lo,
         if (rc) return rc;
         rc = center_rows((float*)(ws + p.diffs), p.Dselp, rows, Dsel, p.seg, d_mu, s);
         if (rc) return rc;
-        // G32 = Dc^T Dc : both operands are the [rows, Dsel] diff matrix read "transposed"
-        GemmShape g;
-        g.M = p.Dselp; g.N = p.Dselp; g.K = rows;    // padded columns are zero -> zero rows/cols of G32
-        g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp; g.transA = true;
-        g.B = (const float*)(ws + p.diffs); g.ldb = p.Dselp; g.transB = true;
-        Epilogue e;
-        e.Y = (float*)(ws + p.gram32); e.ldy = p.Dselp; e.y_cols = p.Dselp;
-        rc = gemm_simt(g, e, s);
-        if (rc) return rc;
-        rc = gram_f64_accumulate((const float*)(ws + p.gram32), p.Dselp, Dsel, p.seg, d_gram, s);
+        // G64 += Dc^T Dc with fp64 products/accumulation (needed to resolve the near-null directions)
+        rc = gram_f64_direct((const float*)(ws + p.diffs), p.Dselp, rows, Dsel, p.seg, d_gram, s);
         if (rc) return rc;
         r0 += rows;
     }
@@ -711,16 +715,17 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
     cudaStream_t s = (cudaStream_t)stream;
     NapFit& f = h->nap;
     MMAD_CUDA_OK(cudaStreamSynchronize(s));
-    cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.Bh); cudaFree(f.Bl);
+    cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.bias_rot); cudaFree(f.Bh); cudaFree(f.Bl);
     f = NapFit();
     const SegMap seg = make_segmap(h, lo, hi);
     f.lo = lo; f.hi = hi; f.K = K; f.D = D; f.Dp = seg.pad_off[seg.n];
     MMAD_CUDA_OK(cudaMalloc(&f.B, (size_t)K * f.Dp * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.colscale, (size_t)round_up(K, kPad) * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.bias, (size_t)round_up(K, kPad) * 4));
+    MMAD_CUDA_OK(cudaMalloc(&f.bias_rot, (size_t)round_up(K, kPad) * 4));
     MMAD_CUDA_OK(cudaMalloc(&f.Bh, (size_t)K * f.Dp * 2));
     MMAD_CUDA_OK(cudaMalloc(&f.Bl, (size_t)K * f.Dp * 2));
-    rc = nap_pack(d_mu, d_vt, d_var, d_mu2, K, D, f.Dp, seg, f.B, f.colscale, f.bias, s);
+    rc = nap_pack(d_mu, d_vt, d_var, d_mu2, K, D, f.Dp, seg, f.B, f.colscale, f.bias, f.bias_rot, s);
     if (rc) return rc;
     rc = split_weights(f.B, K, f.Dp, f.Dp, f.wscale, f.Bh, f.Bl, s);
     if (rc) return rc;
@@ -732,6 +737,46 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
         f.tc_ready = true;
     }
     f.ready = true;
+    return MMAD_OK;
+}
+
+int mmad_nap_set_standardizer(mmad_t h, const float* d_var, const float* d_mu2, void* stream) {
+    if (!h || !d_var || !d_mu2) { set_error("null argument"); return MMAD_E_ARG; }
+    if (!h->nap.ready) { set_error("no NAP fit installed"); return MMAD_E_STATE; }
+    return nap_restandardize(d_var, d_mu2, h->nap.bias_rot, h->nap.K, h->nap.colscale, h->nap.bias, (cudaStream_t)stream);
+}
+
+int mmad_nap_rotate_stats(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, double* d_rsum, double* d_rsq,
+                          void* d_ws, size_t ws_bytes, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (n == 0) return MMAD_OK;
+    if (!d_x || !d_rsum || !d_rsq || n < 0 || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
+    if (!(h->nap.ready && h->nap.lo == lo && h->nap.hi == hi)) {
+        set_error("no NAP fit installed for layers [%d,%d)", lo, hi);
+        return MMAD_E_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tc = h->desc.precision != MMAD_PREC_FP32;
+    PlanOpts o; o.lo = lo; o.hi = hi; o.tc = tc; o.diffs_ws = true; o.rot = true;
+    Plan p;
+    for (int r0 = 0; r0 < n;) {
+        rc = pick_chunk(h, n - r0, ws_bytes, o, &p);
+        if (rc) return rc;
+        int rows = std::min(p.R, n - r0);
+        char* ws = (char*)d_ws;
+        ChainOut co; co.lo = lo; co.hi = hi;
+        if (tc) { co.dh = (__half*)(ws + p.dh); co.dl = (__half*)(ws + p.dl); co.lddh = p.Dselp; }
+        else { co.dout = (float*)(ws + p.diffs); co.lddout = p.Dselp; }
+        rc = run_chain(h, d_x + (size_t)r0 * ldx, ldx, rows, ws, p, co, s);
+        if (rc) return rc;
+        rc = nap_gemm(h, p, ws, rows, nullptr, s);
+        if (rc) return rc;
+        rc = col_sum_sq_f64((const float*)(ws + p.rot), round_up(h->nap.K, kPad), rows, h->nap.K, d_rsum, d_rsq, s);
+        if (rc) return rc;
+        r0 += rows;
+    }
     return MMAD_OK;
 }
 

@@ -113,7 +113,11 @@ int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s);
 int colsum_f64(const float* d, int ld, int n, int cols, const SegMap& sm, double* sum, cudaStream_t s);
 int gram_f64_accumulate(const float* g32, int ld32, int D, const SegMap& sm, double* g64, cudaStream_t s);
 int center_rows(float* d, int ld, int n, int cols, const SegMap& sm, const float* mu, cudaStream_t s);
+int gram_f64_direct(const float* dc, int ld, int rows, int D, const SegMap& sm, double* g64, cudaStream_t s);
 int nap_pack(const float* mu, const float* vt, const float* var, const float* mu2, int K, int D, int Dp,
-             const SegMap& sm, float* B, float* colscale, float* bias, cudaStream_t s);
+             const SegMap& sm, float* B, float* colscale, float* bias, float* bias_rot, cudaStream_t s);
+int nap_restandardize(const float* var, const float* mu2, const float* bias_rot, int K, float* colscale, float* bias,
+                      cudaStream_t s);
+int col_sum_sq_f64(const float* y, int ld, int n, int cols, double* sum, double* sq, cudaStream_t s);
 
 }  // namespace mmad

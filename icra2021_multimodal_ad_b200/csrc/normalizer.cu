@@ -112,15 +112,7 @@ int mmad_gram_accumulate(const float* d_d, int ld, long long n, int cols, const 
         const int rows = (int)std::min<long long>(kRows, n - r0);
         center_copy_kernel<<<grid_for((size_t)rows * cp), 256, 0, s>>>(d_d + (size_t)r0 * ld, ld, rows, cols, d_mu, nullptr, cen, cp, cp);
         MMAD_LAUNCHED();
-        GemmShape g;
-        g.M = cols; g.N = cols; g.K = rows;
-        g.A = cen; g.lda = cp; g.transA = true;
-        g.B = cen; g.ldb = cp; g.transB = true;
-        Epilogue e;
-        e.Y = g32; e.ldy = cp; e.y_cols = cols;
-        int rc = gemm_simt(g, e, s);
-        if (rc) return rc;
-        rc = gram_f64_accumulate(g32, cp, cols, ident, d_gram, s);
+        int rc = gram_f64_direct(cen, cp, rows, cols, ident, d_gram, s);
         if (rc) return rc;
     }
     return MMAD_OK;

@@ -201,6 +201,21 @@ class Engine:
                                                  x.shape[0], lo, hi, mu.data_ptr(), gram.data_ptr(), ws.data_ptr(),
                                                  ws.numel(), _stream()))
 
+    def nap_rotate_stats(self, x: torch.Tensor, lo: int, hi: int, rsum: torch.Tensor, rsq: torch.Tensor):
+        x = self._check_x(x)
+        ws = self.workspace(x.shape[0])
+        with torch.cuda.device(self.device):
+            check(lib().mmad_nap_rotate_stats(self._h, x.data_ptr(), x.stride(0) if x.shape[0] > 1 else self.D,
+                                              x.shape[0], lo, hi, rsum.data_ptr(), rsq.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()))
+
+    def nap_set_standardizer(self, var: torch.Tensor, mu2: torch.Tensor):
+        var = var.detach().to(self.device, torch.float32).contiguous()
+        mu2 = mu2.detach().to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib().mmad_nap_set_standardizer(self._h, var.data_ptr(), mu2.data_ptr(), _stream()))
+            torch.cuda.current_stream().synchronize()
+
     def nap_set_fit(self, lo: int, hi: int, mu: torch.Tensor, vt: torch.Tensor, var: torch.Tensor, mu2: torch.Tensor):
         f = lambda t: t.detach().to(self.device, torch.float32).contiguous()  # noqa: E731
         mu, vt, var, mu2 = f(mu), f(vt), f(var), f(mu2)
@@ -213,7 +228,8 @@ class Engine:
         self._ws_rows = 0
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
-                batch_rows: int = 16384, distributed: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+                batch_rows: int = 16384, distributed: Optional[bool] = None,
+                restandardize: bool = True) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
@@ -242,6 +258,20 @@ class Engine:
             dist.all_reduce(gram, group=group)
         fit = nap_fit_from_stats(mu, gram, N)
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
+        if restandardize:
+            # Standardizer.fit on Rotater.run(train) (utils/metric.py:214-216): third pass, the rotation done
+            # by the scoring kernels themselves so their rounding noise in near-null directions
+            # is normalised exactly like the reference normalises its own
+            K = fit["vt"].shape[0]
+            rs = torch.zeros(2, K, dtype=torch.float64, device=dev)
+            for r0 in range(0, n_local, batch_rows):
+                self.nap_rotate_stats(x_train[r0:r0 + batch_rows], lo, hi, rs[0], rs[1])
+            if use_dist:
+                dist.all_reduce(rs, group=group)
+            mu2 = rs[0] / N
+            var = (rs[1] - N * mu2 * mu2) / (N - 1)
+            fit["mu2"], fit["var_eig"], fit["var"] = mu2.float(), fit["var"], var.float()
+            self.nap_set_standardizer(fit["var"], fit["mu2"])
         return fit
 
 
@@ -249,7 +279,9 @@ def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int) -> Di
     """Eigendecomposition of the centred Gram matrix (fp64, cuSOLVER syevd through
     torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2)."""
     lam, V = torch.linalg.eigh(gram)            # ascending
-    lam = lam.flip(0)
+    # near-null directions (SURVEY F5) can come out slightly negative; floor at fp64 resolution of the
+    # largest eigenvalue so that var stays positive like the reference's np.cov diagonal
+    lam = lam.flip(0).clamp_min(lam.max() * 1e-16)
     V = V.flip(1)
     K = min(n_total, gram.shape[0])
     var = (lam[:K] / (n_total - 1)).float()

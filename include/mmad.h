@@ -146,6 +146,15 @@ int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lay
 int mmad_nap_set_fit(mmad_t h, int layer_lo, int layer_hi, int K, const float* d_mu,
                      const float* d_vt, const float* d_var, const float* d_mu2, void* stream);
 
+/* Standardizer.fit on the rotated train rows (utils/normalize.py:25-34), with the rotation done by
+ * the same kernels that score: d_rsum[K] += sum_r rot[r,j], d_rsq[K] += sum_r rot[r,j]^2 (fp64),
+ * rot = (d - mu) V from the installed fit.  After combining shards (all-reduce both), the caller
+ * forms mu2 = rsum/N, var = (rsq - N mu2^2)/(N-1) and installs them with mmad_nap_set_standardizer,
+ * so rounding noise of the rotation in near-null directions is normalised like the reference's. */
+int mmad_nap_rotate_stats(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int layer_hi,
+                          double* d_rsum, double* d_rsq, void* d_ws, size_t ws_bytes, void* stream);
+int mmad_nap_set_standardizer(mmad_t h, const float* d_var, const float* d_mu2, void* stream);
+
 /* ---- stand-alone normaliser ops (utils/normalize.py API compatibility: Rotater / Standardizer on
  * arbitrary device matrices d[n, cols], row stride ld) ----
  * mmad_col_stats: d_mean[cols] = column means (fp64 accumulation, utils/normalize.py:31,61);
