@@ -25,7 +25,7 @@ class Desc(C.Structure):
 
 class TrainLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("W", "b", "gamma", "beta", "run_mean", "run_var", "gW", "gb", "ggamma", "gbeta")]
+                ("W", "b", "gamma", "beta", "run_mean", "run_var", "num_batches_tracked", "gW", "gb", "ggamma", "gbeta")]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)

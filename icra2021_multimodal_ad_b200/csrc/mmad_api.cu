@@ -344,6 +344,8 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
     return MMAD_OK;
 }
 
+const mmad_desc_t* handle_desc(mmad_t h) { return &h->desc; }
+
 static int check_ready(mmad_t h) {
     if (!h) { set_error("null handle"); return MMAD_E_ARG; }
     for (auto& L : h->enc) if (!L.loaded) { set_error("encoder layer weights not loaded (mmad_set_layer)"); return MMAD_E_STATE; }

@@ -25,16 +25,22 @@ class AutoEncoder(AbstractModel):
     # ---- device engine ---------------------------------------------------------------
     def _state_key(self):
         ts = list(self.parameters()) + list(self.buffers())
-        return (tuple(t.data_ptr() for t in ts), tuple(t._version for t in ts), self.precision)
+        return (tuple(t.data_ptr() for t in ts), tuple(t._version for t in ts), self.precision,
+                getattr(self, "_train_steps", 0))
 
-    def engine(self) -> Engine:
-        """The packed device engine, re-packed whenever a parameter or BatchNorm buffer changed."""
+    def handle_engine(self) -> Engine:
+        """The device engine (library handle) without (re)packing the eval-mode weights."""
         p = next(self.parameters())
         if not p.is_cuda:
             raise _lib.MmadError("model is on the CPU; the B200 path has no CPU fallback (use gpu_id >= 0)")
         if self._eng is None or self._eng.device != p.device:
             self._eng = Engine(self.encoder.widths, self.decoder.widths, precision=self.precision, device=p.device)
             self._eng_key = None
+        return self._eng
+
+    def engine(self) -> Engine:
+        """The packed device engine, re-packed whenever a parameter or BatchNorm buffer changed."""
+        self.handle_engine()
         key = self._state_key()
         if key != self._eng_key:
             if self._eng.precision != self.precision:
@@ -91,7 +97,7 @@ class AutoEncoder(AbstractModel):
         loss = engine.model.get_loss_value(x, x)
         loss.backward(retain_graph=True)
         engine.optimizer.step()
-        return (float(loss), )
+        return (float(loss.detach()), )
 
     @staticmethod
     def validate(engine, mini_batch):

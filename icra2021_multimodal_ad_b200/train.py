@@ -1,0 +1,163 @@
+"""Fused training step: ``AutoEncoder.step`` of the reference (models/auto_encoder.py:57-77) with the
+forward, loss and backward executed by libmmad (``mmad_train_fwd_bwd``).
+
+``fused_train_loss(model, x)`` returns a 0-dim loss tensor attached to the autograd graph through a
+custom Function whose backward hands out the gradients the fused kernels already produced, so the
+reference's own step body -- ``loss.backward(); optimizer.step()`` -- works verbatim with any
+``torch.optim`` optimizer, and with ``icra2021_multimodal_ad_b200.optim.Adam`` (one multi-tensor launch).
+
+Gradients live in ONE flat fp32 buffer owned by the model (views per parameter, ``parameters()`` order):
+data-parallel training all-reduces that buffer once per step (SUM: the loss is a sum, model_builder.py:42).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import TrainLayer, check, lib
+
+
+def _module_layers(module) -> List:
+    return list(module.layer_list)
+
+
+class TrainState:
+    """Per-model device state of the fused step: flat gradient buffer, workspace, pointer tables."""
+
+    def __init__(self, model):
+        self.params = list(model.parameters())
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat_grad[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.view_of = {id(p): v for p, v in zip(self.params, self.views)}
+        self.ws: Optional[torch.Tensor] = None
+        self.ws_batch = 0
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.group = None            # torch.distributed group for BatchNorm statistics (SyncBN semantics)
+        self.world = 1
+        self._cb = None
+
+    def tables(self, model):
+        def table(module):
+            layers = _module_layers(module)
+            arr = (TrainLayer * len(layers))()
+            for i, fc in enumerate(layers):
+                t = arr[i]
+                t.W, t.b = fc.layer.weight.data_ptr(), fc.layer.bias.data_ptr()
+                t.gW, t.gb = self.view_of[id(fc.layer.weight)].data_ptr(), self.view_of[id(fc.layer.bias)].data_ptr()
+                if fc.bn is not None:
+                    t.gamma, t.beta = fc.bn.weight.data_ptr(), fc.bn.bias.data_ptr()
+                    t.run_mean, t.run_var = fc.bn.running_mean.data_ptr(), fc.bn.running_var.data_ptr()
+                    t.num_batches_tracked = fc.bn.num_batches_tracked.data_ptr()
+                    t.ggamma, t.gbeta = self.view_of[id(fc.bn.weight)].data_ptr(), self.view_of[id(fc.bn.bias)].data_ptr()
+            return arr
+        return table(model.encoder), table(model.decoder)
+
+    def workspace(self, h, batch: int) -> torch.Tensor:
+        if self.ws is None or batch > self.ws_batch:
+            nbytes = lib().mmad_train_workspace_bytes(h, batch)
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat_grad.device)
+            self.ws_batch = batch
+        return self.ws
+
+    def allreduce_callback(self):
+        """C callback handed to mmad_train_fwd_bwd: SUM-all-reduce of a BatchNorm statistics slice of
+        the workspace over ``self.group`` (NCCL, enqueued on the current stream)."""
+        if self.world <= 1:
+            return _lib.ALLREDUCE_FN(0), None
+        import torch.distributed as dist
+        state = self
+
+        def cb(ctx, d_buf, count, stream):
+            try:
+                off = d_buf - state.ws.data_ptr()
+                view = state.ws[off:off + 8 * count].view(torch.float64)
+                dist.all_reduce(view, group=state.group)
+                return 0
+            except Exception:      # never let an exception cross the C boundary
+                return -1
+        self._cb = _lib.ALLREDUCE_FN(cb)
+        return self._cb, None
+
+
+def train_state(model) -> TrainState:
+    st = getattr(model, "_train_state", None)
+    if st is None or any(a is not b for a, b in zip(st.params, model.parameters())) \
+            or st.flat_grad.device != next(model.parameters()).device:
+        st = TrainState(model)
+        model._train_state = st
+    return st
+
+
+def set_data_parallel(model, group=None):
+    """Make BatchNorm batch statistics global over ``group`` (N-GPU data parallel == 1 GPU on the
+    concatenated batch); gradients are combined by ``allreduce_gradients``."""
+    import torch.distributed as dist
+    st = train_state(model)
+    st.group = group
+    st.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    return st
+
+
+def allreduce_gradients(model):
+    """SUM-all-reduce of the flat gradient buffer (one collective per step)."""
+    import torch.distributed as dist
+    st = train_state(model)
+    if st.world > 1:
+        dist.all_reduce(st.flat_grad, group=st.group)
+
+
+class _FusedStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, eps, beta_kl, *params):
+        st = train_state(model)
+        eng = model.handle_engine()
+        B = x.shape[0]
+        ws = st.workspace(eng._h, B)
+        enc_t, dec_t = st.tables(model)
+        cb, _ = st.allreduce_callback()
+        momentum = 0.1
+        for fc in _module_layers(model.encoder):
+            if fc.bn is not None:
+                momentum = fc.bn.momentum
+                break
+        with torch.cuda.device(x.device):
+            check(lib().mmad_train_fwd_bwd(eng._h, x.data_ptr(), x.stride(0) if B > 1 else x.shape[1], B, B * st.world,
+                                           enc_t, dec_t, eps.data_ptr() if eps is not None else None, float(beta_kl),
+                                           float(momentum), st.loss.data_ptr(), ws.data_ptr(), ws.numel(), cb, None,
+                                           torch.cuda.current_stream().cuda_stream))
+        model._train_steps = getattr(model, "_train_steps", 0) + 1    # parameters/buffers changed under raw pointers
+        ctx.model = model
+        return st.loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        st = train_state(ctx.model)
+        flat = st.flat_grad
+        flat.mul_(gout)            # d(loss)/d(loss) scaling: one launch over the flat buffer
+        return (None, None, None, None) + tuple(st.views)
+
+
+def fused_train_loss(model, x: torch.Tensor, eps: Optional[torch.Tensor] = None, beta_kl: float = 0.0) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _lib.MmadError("training needs CUDA tensors (no CPU path)")
+    x = x.detach().float()
+    if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    if eps is not None:
+        eps = eps.detach().to(x.device, torch.float32).reshape(x.shape[0], -1).contiguous()
+    st = train_state(model)
+    for p, v in zip(st.params, st.views):
+        # a .grad left over from the previous step aliases the flat buffer this step overwrites: give it its
+        # own storage so autograd's accumulation (zero_grad(set_to_none=False) callers) stays correct
+        if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+            p.grad = p.grad.clone()
+    return _FusedStep.apply(model, x, eps, beta_kl, *st.params)

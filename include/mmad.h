@@ -199,13 +199,15 @@ int mmad_confusion(const float* d_score, const uint8_t* d_label, long long n, fl
  * (decorators/variational_info_bottleneck.py:19-42) and beta_kl * KL is added. */
 typedef struct {
     float* W; float* b; float* gamma; float* beta; float* run_mean; float* run_var;   /* params/buffers */
+    long long* num_batches_tracked;                                                  /* int64 scalar, += 1 (may be NULL) */
     float* gW; float* gb; float* ggamma; float* gbeta;                               /* gradients */
 } mmad_train_layer_t;
 
 size_t mmad_train_workspace_bytes(mmad_t h, int batch);
-/* allreduce hook: called (if non-NULL) on BN statistic buffers so that N-GPU data
- * parallel equals 1 GPU on the concatenated batch; count floats at d_buf on stream. */
-typedef int (*mmad_allreduce_fn)(void* ctx, float* d_buf, long long count, void* stream);
+/* allreduce hook: called (if non-NULL) on the BatchNorm statistic buffers (forward: column sum and
+ * sum of squares; backward: sum g and sum g*xhat) so that N-GPU data parallel equals 1 GPU on the
+ * concatenated batch; SUM-all-reduce count doubles at d_buf in place, ordered on stream. */
+typedef int (*mmad_allreduce_fn)(void* ctx, double* d_buf, long long count, void* stream);
 int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long global_batch,
                        const mmad_train_layer_t* enc, const mmad_train_layer_t* dec,
                        const float* d_eps, float beta_kl, float bn_momentum,

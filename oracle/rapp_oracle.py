@@ -281,3 +281,40 @@ def train_step(x: torch.Tensor, sd: Dict[str, torch.Tensor], opt: Dict[str, dict
         sd[k], st["m"], st["v"] = adam_update(sd[k], g, st["m"], st["v"], st["step"], lr=lr)
     sd.update(bufs)
     return loss
+
+
+# ----------------------------------------------------------------------------
+# VIB autoencoder training (BASELINE configs[3]) -- KL term PARITY-UNPINNED
+# ----------------------------------------------------------------------------
+def vib_train_forward_backward(x: torch.Tensor, sd: Dict[str, torch.Tensor], eps: torch.Tensor, beta_kl: float):
+    """Train-mode step of an autoencoder whose encoder output is split (mu | logvar) and
+    reparameterised exactly as decorators/variational_info_bottleneck.py:19-27 does (k = 1, noise given),
+    loss = sum (x_hat-x)^2 (modules/loss.py:31-32) + beta_kl * KL, KL = -1/2 sum(1+logvar-mu^2-exp(logvar)).
+    The reference defines no KL term and no VIB model: the reparameterisation is pinned by
+    tests/golden/vib_D64.pt, the KL by nothing -- this torch-autograd fp32 statement is the checker.
+    Returns (loss, grads{key}, new_buffers{key})."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    bufs: Dict[str, torch.Tensor] = {}
+
+    def run(h, prefix):
+        i = 0
+        while f"{prefix}.net.{i}.layer.weight" in sd:
+            key = f"{prefix}.net.{i}"
+            h = F.linear(h, params[key + ".layer.weight"], params[key + ".layer.bias"])
+            if key + ".bn.weight" in sd:
+                h = F.leaky_relu(h, LRELU_SLOPE)
+                rm, rv = sd[key + ".bn.running_mean"].clone(), sd[key + ".bn.running_var"].clone()
+                h = F.batch_norm(h, rm, rv, params[key + ".bn.weight"], params[key + ".bn.bias"], training=True,
+                                 momentum=BN_MOMENTUM, eps=BN_EPS)
+                bufs[key + ".bn.running_mean"], bufs[key + ".bn.running_var"] = rm, rv
+                bufs[key + ".bn.num_batches_tracked"] = sd[key + ".bn.num_batches_tracked"] + 1
+            i += 1
+        return h
+
+    out = run(x, "encoder")
+    r = vib_normal(out, eps.unsqueeze(0), k=1)
+    xhat = run(r["z"][0], "decoder")
+    kl = -0.5 * torch.sum(1 + r["logvar"] - r["mu"] ** 2 - r["logvar"].exp())
+    loss = F.mse_loss(xhat, x, reduction="sum") + beta_kl * kl
+    loss.backward()
+    return float(loss), {k: p.grad for k, p in params.items()}, bufs
