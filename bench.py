@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--precision", default=os.environ.get("MMAD_BENCH_PRECISION", "auto"))
     p.add_argument("--no-nap", action="store_true")
     p.add_argument("--cpu-sample", type=int, default=4096)
+    p.add_argument("--no-extras", action="store_true", help="skip the train-step and streaming-latency sections")
+    p.add_argument("--train-batch", type=int, default=256)
     return p.parse_args()
 
 
@@ -168,6 +170,83 @@ def workload_config(args, precision):
             "parallelism": f"sample-sharded x{args.gpus}, no data-path collective"}
 
 
+def bench_train(dev, local, world, batch, steps, warmup, precision):
+    """AE train samples/s (BASELINE metric, second half): AutoEncoder.step (models/auto_encoder.py:57-77) =
+    train-mode forward + backward + Adam, one call per step, loss read back to the host every step like the
+    reference.  Data parallel at world > 1: BatchNorm statistics and the flat gradient are all-reduced."""
+    import types
+    import torch.distributed as dist
+    from icra2021_multimodal_ad_b200 import train as T
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    from icra2021_multimodal_ad_b200.models.auto_encoder import AutoEncoder
+    from icra2021_multimodal_ad_b200.optim import Adam
+    from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+    cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
+    model = get_model(cfg)
+    model.load_state_dict(synth_state_dict(D, BTL, NL, 0))
+    opt = Adam(model.parameters(), lr=1e-3)
+    if world > 1:
+        T.set_data_parallel(model)
+    eng = types.SimpleNamespace(model=model, optimizer=opt, config=cfg)
+    xh, _ = synth_windows(batch, D, 1234 + int(os.environ.get("RANK", "0")), anomaly_rate=0.0)
+    xh = xh.pin_memory()
+    xd = xh.to(dev)
+
+    def step(x):
+        if world == 1:
+            return AutoEncoder.step(eng, (x, None))
+        model.train()
+        opt.zero_grad()
+        loss = model.get_loss_value(x.cuda(local), None)
+        loss.backward()
+        T.allreduce_gradients(model)
+        opt.step()
+        return (float(loss.detach()), )
+
+    def timed(x, n):
+        for _ in range(warmup):
+            step(x)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(x)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+    ms_dev = timed(xd, steps)
+    ms_e2e = timed(xh, steps)
+    flop = 56366196.0 * batch * world     # SURVEY 8(d): fwd + dW + dX per sample
+    return {"metric": "AE train samples/sec", "batch_per_gpu": batch, "value": world * batch / (ms_dev / 1e3),
+            "ms_per_step": ms_dev, "unit": "samples/s", "algorithmic_tflops": flop / (ms_dev / 1e3) / 1e12,
+            "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
+                    "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": "fp32 CUDA-core"}
+
+
+def bench_stream(eng, batches=(1, 8, 10, 64), calls=300, warm=50):
+    """configs[4]: realtime_tester-style scoring (test_file/realtime_tester.py:291-309): one host->device->host
+    call per window batch, base + SAP (nap=False there).  p50/p99 wall latency per call."""
+    out = {}
+    for b in batches:
+        x = np.ascontiguousarray(np.random.default_rng(b).random((b, D), dtype=np.float32))
+        for _ in range(warm):
+            eng.score_host(x, 0, NL + 1, base=True, sap=True, nap=False)
+        ts = []
+        for _ in range(calls):
+            t0 = time.perf_counter()
+            eng.score_host(x, 0, NL + 1, base=True, sap=True, nap=False)
+            ts.append(time.perf_counter() - t0)
+        ts = np.sort(np.asarray(ts)) * 1e6
+        out[str(b)] = {"p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)]),
+                       "p50_us_per_window": float(ts[len(ts) // 2] / b)}
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -278,6 +357,13 @@ def main():
            "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * 4 * (3 if want_nap else 2), "steps": e2e_steps}
     assert np.allclose(res["sap"][:1024], out["sap"][:1024].cpu().numpy(), rtol=1e-5)
 
+    extras = {}
+    if not args.no_extras:
+        tsteps = max(3, min(args.steps * 3, 30))
+        extras["train"] = bench_train(dev, local, world, args.train_batch, tsteps, 3, precision)
+        if world == 1:
+            extras["train_b7000"] = bench_train(dev, local, world, 7000, max(3, tsteps // 3), 2, precision)
+            extras["stream_latency"] = bench_stream(eng)
     if rank == 0:
         cpu_rate, cores = cpu_scoring_rate(args.cpu_sample, sd, fit, want_nap) if world == 1 else (None, None)
         flop_per_window = FLOP_SAP + (FLOP_NAP_ROT if want_nap else 0)
@@ -288,6 +374,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args, precision), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "clocks": clocks,
                 "algorithmic_tflops": value * flop_per_window / 1e12, "nap_fit_s": fit_s}
+        line.update(extras)
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} windows, oracle get_diffs(batch 256)+base+SAP" +
