@@ -191,9 +191,10 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
             if (rok) {
                 if (e.Y && c < e.y_cols) e.Y[(size_t)r * e.ldy + c] = v;
                 if (e.Yh && c < e.y_cols) {
-                    __half h = __float2half_rn(v);
+                    const float vs = v * e.y_split_scale;
+                    __half h = __float2half_rn(vs);
                     e.Yh[(size_t)r * e.ldh + c] = h;
-                    if (e.Yl) e.Yl[(size_t)r * e.ldh + c] = __float2half_rn(v - __half2float(h));
+                    if (e.Yl) e.Yl[(size_t)r * e.ldh + c] = __float2half_rn(vs - __half2float(h));
                 }
                 if (e.ref) {
                     float d = 0.f;

@@ -87,19 +87,24 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// smem matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (SM100 version 1)
+// smem matrix descriptor, 128-byte swizzle (SM100 descriptor version 1).
+//   K-major  (contraction dim contiguous): rows of 64 halfs; 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major (M/N dim contiguous): one 128-byte row per k holding 64 consecutive m (or n); 8-k groups
+//            SBO = 1024 B apart; the next 64 m/n start LBO = 8192 B further (one TMA box of 64 k rows).
+template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
     uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);                          // start address, 16-byte units
+    d |= (uint64_t)(MN_MAJOR ? (8192 >> 4) : 1) << 16;               // leading byte offset
+    d |= (uint64_t)(1024 >> 4) << 32;                                // stride byte offset
+    d |= (uint64_t)1 << 46;                                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                          // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = n; bits 15/16 select MN-major A / B
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -127,10 +132,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n;
+    int splits;          // split-K factor (plain epilogue only): work item = (tile, split), atomically accumulated
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int PASSES>
+template <int PASSES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -152,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.tiles_m * p.tiles_n * p.splits;     // work items: tile-major, split fastest
+    // k-block range of split sp: [sp * num_kb / splits, (sp + 1) * num_kb / splits)  (host guarantees splits <= num_kb)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -174,18 +181,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+                const int t = w / p.splits, sp = w % p.splits;
                 const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_lo = sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
                     mbar_expect_tx(fb, C::kStageBytes);
                     uint8_t* st = smem + stage * C::kStageBytes;
-                    tma_load_2d(smem_u32(st), &mapAh, fb, kb * BK, m0);
-                    tma_load_2d(smem_u32(st + A_TILE_BYTES), &mapBh, fb, kb * BK, n0);
+                    auto load_a = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if (A_MN) {   // [k rows, m contiguous]: boxes of 64 m x 64 k
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d(smem_u32(dst + j * 8192), map, fb, m0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d(smem_u32(dst), map, fb, kb * BK, m0);
+                        }
+                    };
+                    auto load_b = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(smem_u32(dst + j * 8192), map, fb, n0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d(smem_u32(dst), map, fb, kb * BK, n0);
+                        }
+                    };
+                    load_a(st, &mapAh);
+                    load_b(st + A_TILE_BYTES, &mapBh);
                     if (PASSES == 3) {
-                        tma_load_2d(smem_u32(st + A_TILE_BYTES + B_TILE_BYTES), &mapAl, fb, kb * BK, m0);
-                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &mapBl, fb, kb * BK, n0);
+                        load_a(st + A_TILE_BYTES + B_TILE_BYTES, &mapAl);
+                        load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -196,35 +221,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+                const int t = w / p.splits, sp = w % p.splits;
+                const int kb_lo = sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 const int n0 = (t % p.tiles_n) * BN;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
-                const uint32_t idesc = make_idesc(n_eff);
+                const uint32_t idesc = make_idesc(n_eff, A_MN, B_MN);
                 mbar_wait(smem_u32(&acc_empty[acc]), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&full[stage]), phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t dAh = make_smem_desc(st);
-                    const uint64_t dBh = make_smem_desc(st + A_TILE_BYTES);
-                    const uint64_t dAl = make_smem_desc(st + A_TILE_BYTES + B_TILE_BYTES);
-                    const uint64_t dBl = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint64_t dAh = make_smem_desc<A_MN>(st);
+                    const uint64_t dBh = make_smem_desc<B_MN>(st + A_TILE_BYTES);
+                    const uint64_t dAl = make_smem_desc<A_MN>(st + A_TILE_BYTES + B_TILE_BYTES);
+                    const uint64_t dBl = make_smem_desc<B_MN>(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, 16-byte units
+                        // K step of 16: 32 B inside the swizzle row (K-major) or 16 rows of 128 B (MN-major), 16-byte units
+                        const uint64_t advA = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+                        const uint64_t advB = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
                         if (PASSES == 3) {
-                            umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, (kb | k) != 0);
-                            umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1);
-                            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                            umma_f16(d_tmem, dAh + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16(d_tmem, dAl + advA, dBh + advB, idesc, 1);
+                            umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, 1);
                         } else {
-                            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | k) != 0);
+                            umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, ((kb - kb_lo) | k) != 0);
                         }
                     }
                     umma_commit(smem_u32(&empty[stage]));                        // frees the smem stage when the MMAs retire
-                    if (kb == num_kb - 1) umma_commit(smem_u32(&acc_full[acc])); // accumulator complete
+                    if (kb == kb_hi - 1) umma_commit(smem_u32(&acc_full[acc])); // accumulator complete
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -242,7 +271,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int rsub = lane >> 3;             // 0..3  row inside a group of 4
         const int c4 = (lane & 7) * 4;          // first of this lane's 4 columns inside the 32-column chunk
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+            const int t = w / p.splits, sp = w % p.splits;
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
             // stage the per-column epilogue vectors of this tile
             asm volatile("bar.sync 1, 128;");
@@ -250,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                 const int gc = n0 + c;
                 const bool ok = gc < p.N;
                 s_mul[c] = e.acc_scale * ((e.col_scale && ok) ? e.col_scale[gc] : 1.f);
-                s_bias[c] = (e.bias && ok) ? e.bias[gc] : 0.f;
+                s_bias[c] = (e.bias && ok && sp == 0) ? e.bias[gc] : 0.f;
                 s_sc[c] = (e.bn_scale && ok) ? e.bn_scale[gc] : 1.f;
                 s_sh[c] = (e.bn_scale && ok) ? e.bn_shift[gc] : 0.f;
             }
@@ -290,6 +320,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
                 __syncwarp();
+                if (e.plain) {
+                    // plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]):
+                    // lane <-> column, one coalesced 128-byte row segment per instruction
+                    const int c = c0 + lane;
+                    const int gc = n0 + c;
+                    if (gc < p.N) {
+                        const float mulc = s_mul[c], biac = s_bias[c];
+                        if (p.splits > 1) {     // split-K: partial products accumulate into the zeroed output
+#pragma unroll 8
+                            for (int rl = 0; rl < 32; ++rl) {
+                                const int r = row_base + rl;
+                                if (r < p.M) atomicAdd(e.Y + (size_t)r * e.ldy + gc, fmaf(stg[rl * STG_LD + lane], mulc, biac));
+                            }
+                        } else {
+#pragma unroll 8
+                            for (int rl = 0; rl < 32; ++rl) {
+                                const int r = row_base + rl;
+                                if (r < p.M) e.Y[(size_t)r * e.ldy + gc] = fmaf(stg[rl * STG_LD + lane], mulc, biac);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 const int cc = c0 + c4;                 // tile-local column of this lane's float4
                 const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
                 const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
@@ -306,10 +360,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
                     float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
                     if (r < p.M) {
-                        if (e.pre && k0) {     // train: pre-activation (scalar: caller-owned layout)
-                            float* pp = e.pre + (size_t)r * e.ldpre + gcol;
-                            pp[0] = x0; if (k1) pp[1] = x1; if (k2) pp[2] = x2; if (k3) pp[3] = x3;
-                        }
+                        if (e.pre && cc < e.ldpre - n0)     // train: pre-activation, zero padded to ldpre columns
+                            *reinterpret_cast<float4*>(e.pre + (size_t)r * e.ldpre + gcol) =
+                                make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
                         if (e.bn_scale) {
                             x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
                             x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
@@ -319,14 +372,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
                         if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
                         if (e.Yh && wy) {
-                            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                            const float ys = e.y_split_scale;
+                            const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
+                            const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
                             uint2 hv;
                             hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
                             *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
                             if (e.Yl) {
                                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                                const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
-                                const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                                const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
+                                const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
                                 uint2 lv;
                                 lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
                                 *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
@@ -413,8 +468,17 @@ int init_tc() {
         return 0;
     }
     g_encode = (EncodeTiledFn)fn;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes) != cudaSuccess) {
+    bool ok = true;
+    auto attr = [&](auto kern, int bytes) {
+        ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+    };
+    attr(gemm_tc_kernel<3, false, false>, Cfg<3>::kSmemBytes);
+    attr(gemm_tc_kernel<1, false, false>, Cfg<1>::kSmemBytes);
+    attr(gemm_tc_kernel<3, false, true>, Cfg<3>::kSmemBytes);
+    attr(gemm_tc_kernel<1, false, true>, Cfg<1>::kSmemBytes);
+    attr(gemm_tc_kernel<3, true, true>, Cfg<3>::kSmemBytes);
+    attr(gemm_tc_kernel<1, true, true>, Cfg<1>::kSmemBytes);
+    if (!ok) {
         cudaGetLastError();
         return 0;
     }
@@ -428,7 +492,8 @@ int tc_available() { return init_tc(); }
 int gemm_tc_tile_n() { return BN; }
 
 // 2-D map over a row-major fp16 matrix [rows, k] with row stride ld (elements): box = [64 x box_rows],
-// 128-byte swizzle, zero fill outside [rows, k].
+// 128-byte swizzle, zero fill outside [rows, k].  K-major operands: rows = M or N, k = contraction, box_rows =
+// 128 (A) / 256 (B).  MN-major operands: rows = contraction extent, k = M or N extent, box_rows = 64.
 int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int k, int ld, int box_rows) {
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8)) { set_error("TMA operand must be 16-byte aligned (ld=%d)", ld); return MMAD_E_ARG; }
@@ -447,8 +512,8 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
     auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
-    if (!al(e.Y, e.ldy, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) || !al(e.dout, e.lddout, 4) ||
-        !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (e.y_cols % 4) || (e.d_cols % 4)) {
+    if (!(e.plain || al(e.Y, e.ldy, 4)) || !al(e.pre, e.ldpre, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) || !al(e.dout, e.lddout, 4) ||
+        !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (!e.plain && (e.y_cols % 4)) || (e.d_cols % 4)) {
         set_error("gemm_tc: epilogue buffers must be 16-byte aligned with padded leading dimensions");
         return MMAD_E_ARG;
     }
@@ -457,11 +522,31 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    if (passes == 3)
-        gemm_tc_kernel<3><<<grid, NTHREADS, Cfg<3>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.lo, p, e);
-    else
-        gemm_tc_kernel<1><<<grid, NTHREADS, Cfg<1>::kSmemBytes, s>>>(A.hi, A.hi, B.hi, B.hi, p, e);
+    const int num_kb = (K + BK - 1) / BK;
+    p.splits = 1;
+    if (e.plain && e.split_k_ok && tiles * 2 <= g_num_sms) {
+        p.splits = g_num_sms / tiles;
+        if (p.splits > num_kb) p.splits = num_kb;
+        if (p.splits < 1) p.splits = 1;
+    }
+    if (p.splits > 1)    // partial sums are accumulated atomically: the output starts at zero
+        MMAD_CUDA_OK(cudaMemset2DAsync(e.Y, (size_t)e.ldy * 4, 0, (size_t)N * 4, M, s));
+    const int items = tiles * p.splits;
+    const int grid = items < g_num_sms ? items : g_num_sms;
+    if (A.mn && !B.mn) { set_error("gemm_tc: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
+#define MMAD_TC_LAUNCH(P, AM, BMN)                                                                          \
+    gemm_tc_kernel<P, AM, BMN><<<grid, NTHREADS, Cfg<P>::kSmemBytes, s>>>(A.hi, P == 3 ? A.lo : A.hi, B.hi, \
+                                                                          P == 3 ? B.lo : B.hi, p, e)
+    if (passes == 3) {
+        if (A.mn) MMAD_TC_LAUNCH(3, true, true);
+        else if (B.mn) MMAD_TC_LAUNCH(3, false, true);
+        else MMAD_TC_LAUNCH(3, false, false);
+    } else {
+        if (A.mn) MMAD_TC_LAUNCH(1, true, true);
+        else if (B.mn) MMAD_TC_LAUNCH(1, false, true);
+        else MMAD_TC_LAUNCH(1, false, false);
+    }
+#undef MMAD_TC_LAUNCH
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

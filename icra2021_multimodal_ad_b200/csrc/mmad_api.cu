@@ -346,6 +346,13 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
 
 const mmad_desc_t* handle_desc(mmad_t h) { return &h->desc; }
 
+LayerView handle_layer(mmad_t h, int module, int index) {
+    const Layer& L = (module == 0 ? h->enc : h->dec)[index];
+    LayerView v;
+    v.K = L.K; v.N = L.N; v.Kp = L.Kp; v.Np = L.Np; v.Wh = L.Wh; v.Wl = L.Wl; v.wscale = 256.f;
+    return v;
+}
+
 static int check_ready(mmad_t h) {
     if (!h) { set_error("null handle"); return MMAD_E_ARG; }
     for (auto& L : h->enc) if (!L.loaded) { set_error("encoder layer weights not loaded (mmad_set_layer)"); return MMAD_E_STATE; }

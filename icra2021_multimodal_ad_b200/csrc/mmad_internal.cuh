@@ -59,6 +59,9 @@ struct Epilogue {
     float* rowpart = nullptr; int rowpart_stride = 0;   // [tiles_n][rowpart_stride]
     int sq_self = 0;
     float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
+    int plain = 0;                                      // Y = acc * acc_scale + bias only, rows of Y may be unaligned
+    int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
+    float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)
 };
 
 struct GemmShape {
@@ -90,12 +93,18 @@ int gemm_simt_tile_n();   // columns covered by one rowpart slot
 struct TcOperand {
     CUtensorMap hi, lo;      // 2-D maps, box = [64 (K) x rows], 128B swizzle
     int rows = 0, k = 0;
+    bool mn = false;         // MN-major: the matrix is stored [contraction, M or N] (boxes of 64 x 64)
 };
 int tc_available();
 int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, int ld, int box_rows);
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
             const Epilogue& e, cudaStream_t s);
 int gemm_tc_tile_n();
+
+// handle internals shared with train.cu (defined in mmad_api.cu)
+struct LayerView { int K, N, Kp, Np; __half* Wh; __half* Wl; float wscale; };
+const mmad_desc_t* handle_desc(mmad_t h);
+LayerView handle_layer(mmad_t h, int module, int index);
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

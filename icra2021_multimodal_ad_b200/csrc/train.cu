@@ -16,97 +16,177 @@
 
 using namespace mmad;
 
-namespace mmad {
-// defined in mmad_api.cu
-const mmad_desc_t* handle_desc(mmad_t h);
-}
-
 namespace {
 
-constexpr int kColThreads = 128;
+// ---- column-statistic kernels --------------------------------------------------------------------------
+// One pattern for all of them: a CTA of 8 warps owns 128 columns x RS rows; lane <-> 4 consecutive columns
+// (one 16-byte load per row: 512 B per warp-row, fully coalesced), warp w walks rows w, w+8, ...;
+// per-thread fp64 accumulators, cross-warp reduction through shared memory, one atomic per column per CTA.
+constexpr int kCB = 128;      // columns per CTA
+constexpr int kCT = 256;      // threads per CTA
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-inline dim3 col_grid(int n_cols, int rows) {
-    int slabs = rows >= 4096 ? 32 : (rows >= 1024 ? 16 : (rows >= 128 ? 8 : 1));
-    return dim3((n_cols + kColThreads - 1) / kColThreads, slabs);
+inline int row_slab(int rows) { return rows >= 2048 ? 128 : (rows >= 512 ? 64 : 32); }
+inline dim3 col_grid(int n_cols, int rows) { return dim3((n_cols + kCB - 1) / kCB, (rows + row_slab(rows) - 1) / row_slab(rows)); }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// sum the per-warp partials of NS statistics; thread t < 128 returns the totals of column t of this CTA
+template <int NS>
+__device__ __forceinline__ void cta_col_reduce(const double (&acc)[NS][4], double* sm, double (&tot)[NS]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm[(warp * NS + s) * kCB + lane * 4 + j] = acc[s][j];
+    __syncthreads();
+    if (threadIdx.x < kCB) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCT / 32; ++w) t += sm[(w * NS + s) * kCB + threadIdx.x];
+            tot[s] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ void split4_store(const float (&v)[4], float scale, __half* __restrict__ h, __half* __restrict__ l,
+                                             size_t i) {
+    // saturating hi (a dead BatchNorm column can produce huge gradients; inf would poison the MMA)
+    __half hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float vc = fminf(fmaxf(v[j] * scale, -65504.f), 65504.f);
+        hh[j] = __float2half_rn(vc);
+        ll[j] = __float2half_rn(vc - __half2float(hh[j]));
+    }
+    *reinterpret_cast<uint2*>(h + i) = *reinterpret_cast<const uint2*>(hh);
+    *reinterpret_cast<uint2*>(l + i) = *reinterpret_cast<const uint2*>(ll);
 }
 
 // st[0][c] += sum_r a, st[1][c] += sum_r a^2 with a = lrelu(pre[r,c])
-__global__ void bn_fwd_stats_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope, double* __restrict__ st,
-                                    int st_stride) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const int per = (B + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(B, r0 + per);
-    double s = 0.0, q = 0.0;
-    for (int r = r0; r < r1; ++r) {
-        const double a = (double)lrelu(pre[(size_t)r * ld + c], slope);
-        s += a;
-        q = fma(a, a, q);
-    }
-    atomicAdd(&st[c], s);
-    atomicAdd(&st[st_stride + c], q);
-}
-
-// mean / inv-std of the (global) batch, running-stat update (torch BatchNorm1d: momentum, unbiased running var)
-__global__ void bn_fwd_finalize_kernel(const double* __restrict__ st, int st_stride, int N, int Np, double Bg, float eps,
-                                       float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
-                                       long long* __restrict__ nbt, float* __restrict__ mean_out, float* __restrict__ inv_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt) *nbt += 1;
-    if (c >= Np) return;
-    if (c >= N) { mean_out[c] = 0.f; inv_out[c] = 0.f; return; }
-    const double m = st[c] / Bg;
-    double var_b = st[st_stride + c] / Bg - m * m;
-    if (var_b < 0.0) var_b = 0.0;
-    mean_out[c] = (float)m;
-    inv_out[c] = (float)(1.0 / sqrt(var_b + (double)eps));
-    if (run_mean) {
-        const double unb = Bg > 1.0 ? var_b * (Bg / (Bg - 1.0)) : var_b;
-        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
-        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
-    }
-}
-
-// out[r,c] = (lrelu(pre) - mean) * inv * gamma + beta ; padding columns [N, Np) are zero filled
-__global__ void bn_fwd_apply_kernel(const float* __restrict__ pre, int ld, int B, int N, int Np, float slope,
-                                    const float* __restrict__ mean, const float* __restrict__ inv,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
-                                    int ldo) {
-    const size_t total = (size_t)B * Np;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / Np), c = (int)(i % Np);
-        float v = 0.f;
-        if (c < N) {
-            const float a = lrelu(pre[(size_t)r * ld + c], slope);
-            v = fmaf((a - mean[c]) * inv[c], gamma[c], beta[c]);
+__global__ void __launch_bounds__(kCT) bn_fwd_stats_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope,
+                                                           double* __restrict__ st, int st_stride, int RS) {
+    __shared__ double sm[(kCT / 32) * 2 * kCB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kCB + lane * 4;
+    const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
+    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    if (c0 < N) {
+#pragma unroll 4
+        for (int r = r_lo + warp; r < r_hi; r += kCT / 32) {
+            const float4 v = ld4(pre + (size_t)r * ld + c0);
+            const float a[4] = {lrelu(v.x, slope), lrelu(v.y, slope), lrelu(v.z, slope), lrelu(v.w, slope)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[0][j] += (double)a[j]; acc[1][j] = fma((double)a[j], (double)a[j], acc[1][j]); }
         }
-        out[(size_t)r * ldo + c] = v;
+    }
+    double tot[2];
+    cta_col_reduce<2>(acc, sm, tot);
+    const int c = blockIdx.x * kCB + threadIdx.x;
+    if (threadIdx.x < kCB && c < N) {
+        atomicAdd(&st[c], tot[0]);
+        atomicAdd(&st[st_stride + c], tot[1]);
     }
 }
 
-// st[0][c] += sum_r g, st[1][c] += sum_r g * xhat
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre, int ld, int B, int N,
-                                     float slope, float gscale, const float* __restrict__ mean, const float* __restrict__ inv,
-                                     double* __restrict__ st, int st_stride) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const int per = (B + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(B, r0 + per);
-    const float m = mean[c], iv = inv[c];
-    double s1 = 0.0, s2 = 0.0;
-    for (int r = r0; r < r1; ++r) {
-        const float gv = g[(size_t)r * ldg + c] * gscale;
-        const float xh = (lrelu(pre[(size_t)r * ld + c], slope) - m) * iv;
-        s1 += (double)gv;
-        s2 = fma((double)gv, (double)xh, s2);
+// mean / inv-std of the (global) batch from the statistics, running-stat update by the first row slab
+// (torch BatchNorm1d: momentum, unbiased running var), then out = (lrelu(pre) - mean) inv gamma + beta as fp32
+// and/or fp16 hi/lo twins (tensor-core operands of the next layer and of dW).
+__global__ void __launch_bounds__(kCT) bn_fwd_apply_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope,
+                                                           const double* __restrict__ st, int st_stride, double Bg, float eps,
+                                                           float momentum, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ run_mean,
+                                                           float* __restrict__ run_var, long long* __restrict__ nbt,
+                                                           float* __restrict__ mean_out, float* __restrict__ inv_out,
+                                                           float* __restrict__ out, int ldo, __half* __restrict__ oh,
+                                                           __half* __restrict__ ol, int RS) {
+    __shared__ float s_mean[kCB], s_inv[kCB], s_g[kCB], s_b[kCB];
+    if (threadIdx.x < kCB) {
+        const int c = blockIdx.x * kCB + threadIdx.x;
+        float m = 0.f, iv = 0.f, g = 0.f, b = 0.f;
+        if (c < N) {
+            const double md = st[c] / Bg;
+            double var_b = st[st_stride + c] / Bg - md * md;
+            if (var_b < 0.0) var_b = 0.0;
+            m = (float)md;
+            iv = (float)(1.0 / sqrt(var_b + (double)eps));
+            g = gamma[c]; b = beta[c];
+            if (blockIdx.y == 0) {
+                mean_out[c] = m;
+                inv_out[c] = iv;
+                if (run_mean) {
+                    const double unb = Bg > 1.0 ? var_b * (Bg / (Bg - 1.0)) : var_b;
+                    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+                    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+                }
+                if (c == 0 && nbt) *nbt += 1;
+            }
+        }
+        s_mean[threadIdx.x] = m; s_inv[threadIdx.x] = iv; s_g[threadIdx.x] = g; s_b[threadIdx.x] = b;
     }
-    atomicAdd(&st[c], s1);
-    atomicAdd(&st[st_stride + c], s2);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kCB + lane * 4;
+    if (c0 >= N) return;
+    float m[4], iv[4], g[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = s_mean[lane * 4 + j]; iv[j] = s_inv[lane * 4 + j]; g[j] = s_g[lane * 4 + j]; b[j] = s_b[lane * 4 + j]; }
+    const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
+#pragma unroll 4
+    for (int r = r_lo + warp; r < r_hi; r += kCT / 32) {
+        const float4 v = ld4(pre + (size_t)r * ld + c0);
+        const float p4[4] = {v.x, v.y, v.z, v.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (c0 + j < N) ? fmaf((lrelu(p4[j], slope) - m[j]) * iv[j], g[j], b[j]) : 0.f;
+        if (out) *reinterpret_cast<float4*>(out + (size_t)r * ldo + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (oh) split4_store(o, 1.f, oh, ol, (size_t)r * ldo + c0);
+    }
 }
 
-// local parameter gradients of BatchNorm (before any cross-rank combination of the statistics)
+// st[0][c] += sum_r g, st[1][c] += sum_r g * xhat ; the first row slab also clears the bias-gradient accumulator
+__global__ void __launch_bounds__(kCT) bn_bwd_reduce_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre,
+                                                            int ld, int B, int N, float slope, float gscale,
+                                                            const float* __restrict__ mean, const float* __restrict__ inv,
+                                                            double* __restrict__ st, int st_stride, float* __restrict__ gb,
+                                                            int RS) {
+    __shared__ double sm[(kCT / 32) * 2 * kCB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kCB + lane * 4;
+    const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
+    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    if (c0 < N) {
+        float m[4], iv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const bool ok = c0 + j < N; m[j] = ok ? mean[c0 + j] : 0.f; iv[j] = ok ? inv[c0 + j] : 0.f; }
+#pragma unroll 4
+        for (int r = r_lo + warp; r < r_hi; r += kCT / 32) {
+            const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
+            const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
+            const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
+            const float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (lrelu(pv[j], slope) - m[j]) * iv[j];
+                acc[0][j] += (double)gv[j];
+                acc[1][j] = fma((double)gv[j], (double)xh, acc[1][j]);
+            }
+        }
+    }
+    double tot[2];
+    cta_col_reduce<2>(acc, sm, tot);
+    const int c = blockIdx.x * kCB + threadIdx.x;
+    if (threadIdx.x < kCB && c < N) {
+        atomicAdd(&st[c], tot[0]);
+        atomicAdd(&st[st_stride + c], tot[1]);
+        if (blockIdx.y == 0) gb[c] = 0.f;
+    }
+}
+
+// local parameter gradients of BatchNorm (data parallel: before the cross-rank combination of the statistics)
 __global__ void bn_bwd_param_kernel(const double* __restrict__ st, int st_stride, int N, float* __restrict__ ggamma,
                                     float* __restrict__ gbeta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,45 +195,82 @@ __global__ void bn_bwd_param_kernel(const double* __restrict__ st, int st_stride
     ggamma[c] = (float)st[st_stride + c];
 }
 
-// g_pre = gamma inv (g - s1/Bg - xhat s2/Bg) * lrelu'(pre);  st[2][c] += sum_r g_pre (bias gradient)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre, int ld, int B, int N,
-                                    float slope, float gscale, const float* __restrict__ mean, const float* __restrict__ inv,
-                                    const float* __restrict__ gamma, double* __restrict__ st, int st_stride, double Bg,
-                                    float* __restrict__ gpre, int ldo) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const int per = (B + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(B, r0 + per);
-    const float m = mean[c], iv = inv[c];
-    const float k = gamma[c] * iv;
-    const float a1 = (float)(st[c] / Bg), a2 = (float)(st[st_stride + c] / Bg);
-    double sb = 0.0;
-    for (int r = r0; r < r1; ++r) {
-        const float p = pre[(size_t)r * ld + c];
-        const float xh = (lrelu(p, slope) - m) * iv;
-        float ga = k * (g[(size_t)r * ldg + c] * gscale - a1 - xh * a2);
-        ga = p > 0.f ? ga : ga * slope;
-        gpre[(size_t)r * ldo + c] = ga;
-        sb += (double)ga;
+// g_pre = gamma inv (g - s1/Bg - xhat s2/Bg) * lrelu'(pre), written as fp32 and/or fp16 twins (x twin_scale);
+// gb[c] += sum_r g_pre (bias gradient); ggamma/gbeta written here when write_params (single GPU)
+__global__ void __launch_bounds__(kCT) bn_bwd_apply_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre,
+                                                           int ld, int B, int N, float slope, float gscale,
+                                                           const float* __restrict__ mean, const float* __restrict__ inv,
+                                                           const float* __restrict__ gamma, const double* __restrict__ st,
+                                                           int st_stride, double Bg, float* __restrict__ gpre, int ldo,
+                                                           __half* __restrict__ gh, __half* __restrict__ gl, float twin_scale,
+                                                           float* __restrict__ gb, float* __restrict__ ggamma,
+                                                           float* __restrict__ gbeta, int write_params, int RS) {
+    __shared__ double sm[(kCT / 32) * 1 * kCB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kCB + lane * 4;
+    const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
+    double acc[1][4] = {{0.0, 0.0, 0.0, 0.0}};
+    if (c0 < N) {
+        float m[4], iv[4], k[4], a1[4], a2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = c0 + j < N;
+            m[j] = ok ? mean[c0 + j] : 0.f;
+            iv[j] = ok ? inv[c0 + j] : 0.f;
+            k[j] = ok ? gamma[c0 + j] * iv[j] : 0.f;
+            a1[j] = ok ? (float)(st[c0 + j] / Bg) : 0.f;
+            a2[j] = ok ? (float)(st[st_stride + c0 + j] / Bg) : 0.f;
+        }
+#pragma unroll 4
+        for (int r = r_lo + warp; r < r_hi; r += kCT / 32) {
+            const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
+            const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
+            const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
+            const float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+            float ga[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (lrelu(pv[j], slope) - m[j]) * iv[j];
+                float t = k[j] * (gv[j] - a1[j] - xh * a2[j]);
+                t = pv[j] > 0.f ? t : t * slope;
+                ga[j] = (c0 + j < N) ? t : 0.f;
+                acc[0][j] += (double)ga[j];
+            }
+            if (gpre) *reinterpret_cast<float4*>(gpre + (size_t)r * ldo + c0) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+            if (gh) split4_store(ga, twin_scale, gh, gl, (size_t)r * ldo + c0);
+        }
     }
-    atomicAdd(&st[2 * st_stride + c], sb);
+    double tot[1];
+    cta_col_reduce<1>(acc, sm, tot);
+    const int c = blockIdx.x * kCB + threadIdx.x;
+    if (threadIdx.x < kCB && c < N) {
+        atomicAdd(&gb[c], (float)tot[0]);
+        if (write_params && blockIdx.y == 0) {
+            gbeta[c] = (float)st[c];
+            ggamma[c] = (float)st[st_stride + c];
+        }
+    }
 }
 
-// st[2][c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer)
-__global__ void col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale, double* __restrict__ st,
-                                      int st_stride) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const int per = (B + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(B, r0 + per);
-    double s = 0.0;
-    for (int r = r0; r < r1; ++r) s += (double)g[(size_t)r * ldg + c];
-    atomicAdd(&st[2 * st_stride + c], s * (double)scale);
-}
-
-__global__ void bias_grad_out_kernel(const double* __restrict__ st, int st_stride, int N, float* __restrict__ gb) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < N) gb[c] = (float)st[2 * st_stride + c];
+// gb[c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer; gb zeroed by the caller)
+__global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale,
+                                                             float* __restrict__ gb, int RS) {
+    __shared__ double sm[(kCT / 32) * 1 * kCB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kCB + lane * 4;
+    const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
+    double acc[1][4] = {{0.0, 0.0, 0.0, 0.0}};
+    if (c0 < N) {
+#pragma unroll 4
+        for (int r = r_lo + warp; r < r_hi; r += kCT / 32) {
+            const float4 v = ld4(g + (size_t)r * ldg + c0);
+            acc[0][0] += (double)v.x; acc[0][1] += (double)v.y; acc[0][2] += (double)v.z; acc[0][3] += (double)v.w;
+        }
+    }
+    double tot[1];
+    cta_col_reduce<1>(acc, sm, tot);
+    const int c = blockIdx.x * kCB + threadIdx.x;
+    if (threadIdx.x < kCB && c < N) atomicAdd(&gb[c], (float)(tot[0] * (double)scale));
 }
 
 // VIB forward (decorators/variational_info_bottleneck.py:19-42, k = 1): enc_out [B, 2h] -> z = eps exp(logvar/2) + mu
@@ -244,18 +361,22 @@ struct TrainPlan {
     size_t out[2][MMAD_MAX_LAYERS] = {{0}};
     size_t mean[2][MMAD_MAX_LAYERS] = {{0}};
     size_t inv[2][MMAD_MAX_LAYERS] = {{0}};
-    size_t st[2][MMAD_MAX_LAYERS] = {{0}};    // [3][st_stride] doubles per layer
+    size_t st[2][MMAD_MAX_LAYERS] = {{0}};    // [4][Np] doubles per layer: forward sum / sum sq, backward sum g / sum g xhat
     size_t st_all = 0, st_bytes = 0;
     size_t g[2] = {0, 0};                      // gradient ping-pong [B, maxNp]
     size_t z = 0, genc = 0;                    // VIB: sampled code, gradient wrt the encoder output
     size_t rowpart = 0;
     size_t kl = 0;
     int maxNp = 0;
+    // tensor-core modes: fp16 hi/lo twins
+    size_t xh = 0, xl = 0, xp = 0;
+    size_t outh[2][MMAD_MAX_LAYERS] = {{0}}, outl[2][MMAD_MAX_LAYERS] = {{0}};
+    size_t gh[2] = {0, 0}, gl[2] = {0, 0};
 };
 
 int np_of(int n) { return round_up(n, kPad); }
 
-TrainPlan make_train_plan(const mmad_desc_t& d, int B) {
+TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
     TrainPlan p;
     p.B = B;
     size_t off = 0;
@@ -268,7 +389,7 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B) {
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
-        for (int i = 0; i < n; ++i) p.st[m][i] = take((size_t)3 * np_of(w[i + 1]) * 8);
+        for (int i = 0; i < n; ++i) p.st[m][i] = take((size_t)4 * np_of(w[i + 1]) * 8);
     }
     p.kl = take(8);
     p.st_bytes = off - p.st_all;
@@ -288,6 +409,20 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B) {
     p.z = take((size_t)B * np_of(d.dec_widths[0]) * 4);
     p.genc = take((size_t)B * np_of(d.enc_widths[d.n_enc]) * 4);
     p.rowpart = take((size_t)((d.enc_widths[0] + 63) / 64 + 1) * B * 4);
+    p.xp = take((size_t)B * np_of(d.enc_widths[0]) * 4);
+    if (tc) {
+        p.xh = take((size_t)B * np_of(d.enc_widths[0]) * 2);
+        p.xl = take((size_t)B * np_of(d.enc_widths[0]) * 2);
+        for (int m = 0; m < 2; ++m) {
+            const int n = m == 0 ? d.n_enc : d.n_dec;
+            const int* w = m == 0 ? d.enc_widths : d.dec_widths;
+            for (int i = 0; i < n; ++i) {
+                p.outh[m][i] = take((size_t)B * np_of(w[i + 1]) * 2);
+                p.outl[m][i] = take((size_t)B * np_of(w[i + 1]) * 2);
+            }
+        }
+        for (int i = 0; i < 2; ++i) { p.gh[i] = take((size_t)B * maxNp * 2); p.gl[i] = take((size_t)B * maxNp * 2); }
+    }
     p.total = off;
     return p;
 }
@@ -303,7 +438,7 @@ extern "C" {
 
 size_t mmad_train_workspace_bytes(mmad_t h, int batch) {
     if (!h || batch < 1) return 0;
-    return make_train_plan(*handle_desc(h), batch).total;
+    return make_train_plan(*handle_desc(h), batch, tc_available() != 0).total;
 }
 
 int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long global_batch,
@@ -321,7 +456,10 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         set_error("encoder output %d does not feed decoder input %d (%s)", enc_out, dec_in, vib ? "VIB expects 2x" : "pass eps for a VIB model");
         return MMAD_E_ARG;
     }
-    const TrainPlan p = make_train_plan(d, batch);
+    // tensor-core GEMMs for the plain autoencoder in the f16x3 / f16 modes; VIB and fp32 use the CUDA-core kernel
+    const bool tc = d.precision != MMAD_PREC_FP32 && !vib && tc_available();
+    const int passes = d.precision == MMAD_PREC_F16X3 ? 3 : 1;
+    const TrainPlan p = make_train_plan(d, batch, tc);
     if (ws_bytes < p.total) { set_error("train workspace too small: %zu < %zu", ws_bytes, p.total); return MMAD_E_WORKSPACE; }
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
@@ -339,34 +477,73 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
     const int B = batch;
     const double Bg = (double)global_batch;
     const float slope = d.lrelu_slope;
+    constexpr float GS = 16.f;       // gradients are scaled by 2^4 before the fp16 hi/lo split
     MMAD_CUDA_OK(cudaMemsetAsync(ws + p.st_all, 0, p.st_bytes, s));
     MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
 
-    struct Ref { int m, i, K, N, Np; const mmad_train_layer_t* L; const float* in; int ldin; bool bn; };
+    // an activation / gradient matrix: fp32 and (tensor-core modes) fp16 hi/lo twins, same leading dimension
+    struct Mat { const float* f; const __half* h; const __half* l; int ld; };
+    struct Ref { int m, i, K, N, Np; const mmad_train_layer_t* L; Mat in; bool bn; };
     std::vector<Ref> order;
+
+    // C[M,N] = A B^T-like product on the tensor cores.  a_mn / b_mn: operand stored [contraction, M|N].
+    auto tc_gemm = [&](const __half* Ah, const __half* Al, int lda, bool a_mn, const __half* Bh, const __half* Bl, int ldb,
+                       bool b_mn, int M, int N, int K, const Epilogue& e) -> int {
+        TcOperand A, Bo;
+        int rc;
+        if (a_mn) { rc = tc_make_operand_map(&A.hi, Ah, K, M, lda, 64); if (!rc) rc = tc_make_operand_map(&A.lo, Al, K, M, lda, 64); }
+        else { rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128); if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128); }
+        if (rc) return rc;
+        if (b_mn) { rc = tc_make_operand_map(&Bo.hi, Bh, K, N, ldb, 64); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, K, N, ldb, 64); }
+        else { rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, gemm_tc_tile_n()); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, gemm_tc_tile_n()); }
+        if (rc) return rc;
+        A.mn = a_mn; Bo.mn = b_mn;
+        return gemm_tc(A, Bo, M, N, K, passes, e, s);
+    };
+
     // ------------------------------- forward -------------------------------
-    const float* cur = d_x;
-    int ldcur = ldx;
+    const bool x_aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0);
+    Mat cur{d_x, nullptr, nullptr, ldx};
+    const float* xref = d_x;      // reference of the loss epilogue
+    int ldxref = ldx;
+    if (tc) {
+        const int Dp = np_of(D);
+        int rc = pad_split(d_x, ldx, B, D, x_aligned ? nullptr : (float*)(ws + p.xp), Dp, (__half*)(ws + p.xh), (__half*)(ws + p.xl), Dp, s);
+        if (rc) return rc;
+        if (!x_aligned) { xref = (const float*)(ws + p.xp); ldxref = Dp; }
+        cur = Mat{xref, (const __half*)(ws + p.xh), (const __half*)(ws + p.xl), Dp};
+        if (x_aligned) cur.f = d_x;
+        // the fp32 pointer of the input is only used by the CUDA-core path; twins share ld = Dp
+        for (int m = 0; m < 2; ++m) {      // weights changed since the last step: refresh their fp16 twins
+            const int n = m == 0 ? d.n_enc : d.n_dec;
+            const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
+            for (int i = 0; i < n; ++i) {
+                const LayerView lv = handle_layer(h, m, i);
+                rc = split_weights(Ls[i].W, lv.N, lv.K, lv.Kp, lv.wscale, lv.Wh, lv.Wl, s);
+                if (rc) return rc;
+            }
+        }
+    }
+    const int loss_tile_n = tc ? gemm_tc_tile_n() : gemm_simt_tile_n();
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
         const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
         if (m == 1 && vib) {
             const int hp = np_of(dec_in);
-            vib_train_fwd_kernel<<<ew_grid((size_t)B * hp), 256, 0, s>>>(cur, ldcur, B, dec_in, d_eps, (float*)(ws + p.z), hp,
+            vib_train_fwd_kernel<<<ew_grid((size_t)B * hp), 256, 0, s>>>(cur.f, cur.ld, B, dec_in, d_eps, (float*)(ws + p.z), hp,
                                                                         (double*)(ws + p.kl));
             MMAD_LAUNCHED();
-            cur = (const float*)(ws + p.z);
-            ldcur = hp;
+            cur = Mat{(const float*)(ws + p.z), nullptr, nullptr, hp};
         }
         for (int i = 0; i < n; ++i) {
             const int K = w[i], N = w[i + 1], Np = np_of(N);
             const bool bn = i < n - 1;
             const mmad_train_layer_t& L = Ls[i];
-            order.push_back({m, i, K, N, Np, &L, cur, ldcur, bn});
+            order.push_back({m, i, K, N, Np, &L, cur, bn});
             float* pre = (float*)(ws + p.pre[m][i]);
-            GemmShape g;
-            g.M = B; g.N = N; g.K = K; g.A = cur; g.lda = ldcur; g.B = L.W; g.ldb = K;
+            __half* oh = tc ? (__half*)(ws + p.outh[m][i]) : nullptr;
+            __half* ol = tc ? (__half*)(ws + p.outl[m][i]) : nullptr;
             Epilogue e;
             e.bias = L.b;
             e.slope = slope;
@@ -375,40 +552,51 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
                 e.pre = pre; e.ldpre = Np;
             } else {
                 e.Y = pre; e.ldy = Np; e.y_cols = Np;
-                if (last) {   // loss epilogue: d = xhat - x, row sums of d^2
-                    e.ref = d_x; e.ldref = ldx;
-                    e.dout = (float*)(ws + p.g[0]); e.lddout = p.maxNp; e.d_cols = N;
+                if (tc && !last) { e.Yh = oh; e.Yl = ol; e.ldh = Np; }
+                if (last) {   // loss epilogue: d = xhat - x, row sums of d^2; g = 2 d enters the backward pass
+                    e.ref = xref; e.ldref = ldxref;
+                    e.dout = (float*)(ws + p.g[0]); e.lddout = p.maxNp; e.d_cols = tc ? Np : N;
+                    if (tc) { e.Dh = (__half*)(ws + p.gh[0]); e.Dl = (__half*)(ws + p.gl[0]); e.lddh = p.maxNp; e.d_scale = 2.f * GS; e.Y = nullptr; }
                     e.rowpart = (float*)(ws + p.rowpart); e.rowpart_stride = B;
                 }
             }
-            int rc = gemm_simt(g, e, s);
+            int rc;
+            if (tc) {
+                const LayerView lv = handle_layer(h, m, i);
+                e.acc_scale = 1.f / lv.wscale;
+                if (bn) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
+                    e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1;
+                }
+                rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e);
+            } else {
+                GemmShape g;
+                g.M = B; g.N = N; g.K = K; g.A = cur.f; g.lda = cur.ld; g.B = L.W; g.ldb = K;
+                rc = gemm_simt(g, e, s);
+            }
             if (rc) return rc;
             if (bn) {
                 double* st = (double*)(ws + p.st[m][i]);
                 float* mean = (float*)(ws + p.mean[m][i]);
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
-                bn_fwd_stats_kernel<<<col_grid(N, B), kColThreads, 0, s>>>(pre, Np, B, N, slope, st, Np);
+                bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
                 MMAD_LAUNCHED();
                 if (allreduce) {
                     rc = allreduce(allreduce_ctx, st, 2LL * Np, s);
                     if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
                 }
-                bn_fwd_finalize_kernel<<<(Np + 127) / 128, 128, 0, s>>>(st, Np, N, Np, Bg, d.bn_eps, bn_momentum, L.run_mean,
-                                                                        L.run_var, L.num_batches_tracked, mean, inv);
+                bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
+                                                                   L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
+                                                                   tc ? nullptr : out, Np, oh, ol, row_slab(B));
                 MMAD_LAUNCHED();
-                bn_fwd_apply_kernel<<<ew_grid((size_t)B * Np), 256, 0, s>>>(pre, Np, B, N, Np, slope, mean, inv, L.gamma, L.beta,
-                                                                            out, Np);
-                MMAD_LAUNCHED();
-                cur = out;
+                cur = Mat{out, oh, ol, Np};
             } else {
-                cur = pre;
+                cur = Mat{pre, oh, ol, Np};
             }
-            ldcur = Np;
         }
     }
     {   // loss = sum d^2 (+ beta KL)
-        const int slots = (D + gemm_simt_tile_n() - 1) / gemm_simt_tile_n();
+        const int slots = (D + loss_tile_n - 1) / loss_tile_n;
         int rc = reduce_sum_all((const float*)(ws + p.rowpart), B, B, 0, slots, d_loss, s);
         if (rc) return rc;
         if (vib) {
@@ -417,72 +605,95 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         }
     }
     // ------------------------------- backward -------------------------------
-    // g (ping) holds d = xhat - x; dL/dxhat = 2 d enters through gscale of the first backward layer
+    // g (ping) holds d = xhat - x in fp32 (and 2 d GS as twins); dL/dxhat = 2 d enters through gscale
     int gi = 0;
     float gscale = 2.f;
     for (int idx = (int)order.size() - 1; idx >= 0; --idx) {
         const Ref& r = order[idx];
         const mmad_train_layer_t& L = *r.L;
         double* st = (double*)(ws + p.st[r.m][r.i]);
-        const float* gin = (const float*)(ws + p.g[gi]);
-        int ldg = p.maxNp;
-        if (vib && r.m == 0 && r.i == d.n_enc - 1) { gin = (const float*)(ws + p.genc); ldg = np_of(enc_out); }
-        const float* gpre = gin;
-        int ldgpre = ldg;
-        float gemm_scale = gscale;
+        Mat gin{(const float*)(ws + p.g[gi]), tc ? (const __half*)(ws + p.gh[gi]) : nullptr,
+                tc ? (const __half*)(ws + p.gl[gi]) : nullptr, p.maxNp};
+        if (vib && r.m == 0 && r.i == d.n_enc - 1) gin = Mat{(const float*)(ws + p.genc), nullptr, nullptr, np_of(enc_out)};
+        Mat gpre = gin;
+        float gemm_scale = gscale;       // CUDA-core path: factor still to be applied to g_pre
         if (r.bn) {
             const float* pre = (const float*)(ws + p.pre[r.m][r.i]);
             const float* mean = (const float*)(ws + p.mean[r.m][r.i]);
             const float* inv = (const float*)(ws + p.inv[r.m][r.i]);
-            MMAD_CUDA_OK(cudaMemsetAsync(st, 0, (size_t)2 * r.Np * 8, s));
-            bn_bwd_reduce_kernel<<<col_grid(r.N, B), kColThreads, 0, s>>>(gin, ldg, pre, r.Np, B, r.N, slope, gscale, mean, inv, st, r.Np);
+            double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
+            bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
+                                                                  L.gb, row_slab(B));
             MMAD_LAUNCHED();
-            bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(st, r.Np, r.N, L.ggamma, L.gbeta);
-            MMAD_LAUNCHED();
-            if (allreduce) {
-                int rc = allreduce(allreduce_ctx, st, 2LL * r.Np, s);
+            if (allreduce) {    // parameter gradients from the LOCAL sums, then the statistics are combined
+                bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
+                MMAD_LAUNCHED();
+                int rc = allreduce(allreduce_ctx, stb, 2LL * r.Np, s);
                 if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
             }
             float* go = (float*)(ws + p.g[gi ^ 1]);
-            bn_bwd_apply_kernel<<<col_grid(r.N, B), kColThreads, 0, s>>>(gin, ldg, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma,
-                                                                         st, r.Np, Bg, go, p.maxNp);
+            __half* goh = tc ? (__half*)(ws + p.gh[gi ^ 1]) : nullptr;
+            __half* gol = tc ? (__half*)(ws + p.gl[gi ^ 1]) : nullptr;
+            bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
+                                                                 r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
+                                                                 L.gbeta, allreduce ? 0 : 1, row_slab(B));
             MMAD_LAUNCHED();
-            gpre = go; ldgpre = p.maxNp;
+            gpre = Mat{go, goh, gol, p.maxNp};
             gi ^= 1;
             gemm_scale = 1.f;
         } else {
-            col_sum_scaled_kernel<<<col_grid(r.N, B), kColThreads, 0, s>>>(gin, ldg, B, r.N, gscale, st, r.Np);
+            MMAD_CUDA_OK(cudaMemsetAsync(L.gb, 0, (size_t)r.N * 4, s));
+            col_sum_scaled_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, B, r.N, gscale, L.gb, row_slab(B));
             MMAD_LAUNCHED();
         }
-        bias_grad_out_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(st, r.Np, r.N, L.gb);
-        MMAD_LAUNCHED();
         {   // gW[N,K] = g_pre^T in
-            GemmShape g;
-            g.M = r.N; g.N = r.K; g.K = B;
-            g.A = gpre; g.lda = ldgpre; g.transA = true;
-            g.B = r.in; g.ldb = r.ldin; g.transB = true;
             Epilogue e;
-            e.acc_scale = gemm_scale;
             e.Y = L.gW; e.ldy = r.K; e.y_cols = r.K;
-            int rc = gemm_simt(g, e, s);
+            int rc;
+            if (tc) {
+                e.plain = 1; e.split_k_ok = 1;
+                e.acc_scale = 1.f / GS;          // twins of g_pre carry GS (the 2 of dL/dxhat is inside the loss twins)
+                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e);
+            } else {
+                GemmShape g;
+                g.M = r.N; g.N = r.K; g.K = B;
+                g.A = gpre.f; g.lda = gpre.ld; g.transA = true;
+                g.B = r.in.f; g.ldb = r.in.ld; g.transB = true;
+                e.acc_scale = gemm_scale;
+                rc = gemm_simt(g, e, s);
+            }
             if (rc) return rc;
         }
         if (idx > 0) {   // g_in[B,K] = g_pre W
             const bool into_vib = vib && r.m == 1 && r.i == 0;
+            const Ref& prev = order[idx - 1];
             float* gout = (float*)(ws + p.g[gi ^ 1]);
-            GemmShape g;
-            g.M = B; g.N = r.K; g.K = r.N;
-            g.A = gpre; g.lda = ldgpre;
-            g.B = L.W; g.ldb = r.K; g.transB = true;
             Epilogue e;
-            e.acc_scale = gemm_scale;
-            e.Y = gout; e.ldy = p.maxNp; e.y_cols = r.K;
-            int rc = gemm_simt(g, e, s);
+            e.Y = gout; e.ldy = p.maxNp;
+            int rc;
+            if (tc) {
+                const LayerView lv = handle_layer(h, r.m, r.i);
+                e.y_cols = np_of(r.K);
+                e.acc_scale = 1.f / (GS * lv.wscale);
+                if (!prev.bn) {   // the consumer is a bare Linear: it needs the twins of g_pre = g_in directly
+                    e.Yh = (__half*)(ws + p.gh[gi ^ 1]); e.Yl = (__half*)(ws + p.gl[gi ^ 1]); e.ldh = p.maxNp; e.y_split_scale = GS;
+                } else {
+                    e.plain = 1; e.split_k_ok = 1; e.y_cols = r.K;
+                }
+                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, false, lv.Wh, lv.Wl, lv.Kp, true, B, r.K, r.N, e);
+            } else {
+                GemmShape g;
+                g.M = B; g.N = r.K; g.K = r.N;
+                g.A = gpre.f; g.lda = gpre.ld;
+                g.B = L.W; g.ldb = r.K; g.transB = true;
+                e.y_cols = r.K;
+                e.acc_scale = gemm_scale;
+                rc = gemm_simt(g, e, s);
+            }
             if (rc) return rc;
             gi ^= 1;
             if (into_vib) {
-                const Ref& er = order[idx - 1];
-                vib_train_bwd_kernel<<<ew_grid((size_t)B * dec_in), 256, 0, s>>>(gout, p.maxNp, (const float*)(ws + p.pre[0][er.i]), er.Np,
+                vib_train_bwd_kernel<<<ew_grid((size_t)B * dec_in), 256, 0, s>>>(gout, p.maxNp, (const float*)(ws + p.pre[0][prev.i]), prev.Np,
                                                                                  B, dec_in, d_eps, beta_kl, (float*)(ws + p.genc), np_of(enc_out));
                 MMAD_LAUNCHED();
             }
