@@ -27,20 +27,20 @@ namespace mmad {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BN_MAX = 256;            // CTA tile is 128 x BN with BN = 256 (throughput) or 128 (under-filled grids)
 constexpr int BK = 64;                 // halfs per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NTHREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
-constexpr int TMEM_COLS = 512;              // two 256-column fp32 accumulators
 constexpr int STG_LD = 36;                  // floats per row of an epilogue transpose tile (conflict-free float4)
 
-template <int PASSES> struct Cfg {
+template <int PASSES, int BN> struct Cfg {
     static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
-    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_TILE_BYTES);
-    static constexpr int kStages = PASSES == 3 ? 2 : 4;
-    static constexpr int kSmemTiles = kStages * kStageBytes;   // 192 KB
+    static constexpr int kBTileBytes = BN * BK * 2;            // 32 KB / 16 KB
+    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + kBTileBytes);
+    static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 2 / 3 / 4 / 6
+    static constexpr int kSmemTiles = kStages * kStageBytes;   // <= 192 KB
+    static constexpr int kTmemCols = 2 * BN;                   // two fp32 accumulators
     static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 4 * 32 * STG_LD * 4 /*transpose tiles*/ +
                                       256 /*barriers*/ + 1024 /*align*/;
 };
@@ -136,12 +136,14 @@ struct TcParams {
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <int PASSES, bool A_MN, bool B_MN>
+template <int PASSES, bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                TcParams p, Epilogue e) {
-    using C = Cfg<PASSES>;
+    using C = Cfg<PASSES, BN>;
+    constexpr int B_TILE_BYTES = C::kBTileBytes;
+    constexpr int TMEM_COLS = C::kTmemCols;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* s_mul = reinterpret_cast<float*>(smem + C::kSmemTiles);
@@ -472,12 +474,13 @@ int init_tc() {
     auto attr = [&](auto kern, int bytes) {
         ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
     };
-    attr(gemm_tc_kernel<3, false, false>, Cfg<3>::kSmemBytes);
-    attr(gemm_tc_kernel<1, false, false>, Cfg<1>::kSmemBytes);
-    attr(gemm_tc_kernel<3, false, true>, Cfg<3>::kSmemBytes);
-    attr(gemm_tc_kernel<1, false, true>, Cfg<1>::kSmemBytes);
-    attr(gemm_tc_kernel<3, true, true>, Cfg<3>::kSmemBytes);
-    attr(gemm_tc_kernel<1, true, true>, Cfg<1>::kSmemBytes);
+#define MMAD_TC_ATTR(P, AM, BMN)                                             \
+    attr(gemm_tc_kernel<P, AM, BMN, 256>, Cfg<P, 256>::kSmemBytes);           \
+    attr(gemm_tc_kernel<P, AM, BMN, 128>, Cfg<P, 128>::kSmemBytes)
+    MMAD_TC_ATTR(3, false, false); MMAD_TC_ATTR(1, false, false);
+    MMAD_TC_ATTR(3, false, true);  MMAD_TC_ATTR(1, false, true);
+    MMAD_TC_ATTR(3, true, true);   MMAD_TC_ATTR(1, true, true);
+#undef MMAD_TC_ATTR
     if (!ok) {
         cudaGetLastError();
         return 0;
@@ -489,7 +492,14 @@ int init_tc() {
 }  // namespace
 
 int tc_available() { return init_tc(); }
-int gemm_tc_tile_n() { return BN; }
+int gemm_tc_tile_n() { return BN_MAX; }
+
+// Tile width for an M x N problem: 256 unless that leaves SMs idle, then 128 (twice the CTAs, deeper pipeline).
+int gemm_tc_pick_bn(int M, int N) {
+    init_tc();
+    const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
+    return tiles256 >= g_num_sms ? 256 : 128;
+}
 
 // 2-D map over a row-major fp16 matrix [rows, k] with row stride ld (elements): box = [64 x box_rows],
 // 128-byte swizzle, zero fill outside [rows, k].  K-major operands: rows = M or N, k = contraction, box_rows =
@@ -508,7 +518,7 @@ int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int k, i
     return MMAD_OK;
 }
 
-int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s) {
+int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s, int bn) {
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
     auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
@@ -520,7 +530,8 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     TcParams p;
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = (M + BM - 1) / BM;
-    p.tiles_n = (N + BN - 1) / BN;
+    if (bn != 128 && bn != 256) { set_error("gemm_tc: tile width %d not instantiated", bn); return MMAD_E_ARG; }
+    p.tiles_n = (N + bn - 1) / bn;
     const int tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (K + BK - 1) / BK;
     p.splits = 1;
@@ -534,9 +545,14 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int items = tiles * p.splits;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (A.mn && !B.mn) { set_error("gemm_tc: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
-#define MMAD_TC_LAUNCH(P, AM, BMN)                                                                          \
-    gemm_tc_kernel<P, AM, BMN><<<grid, NTHREADS, Cfg<P>::kSmemBytes, s>>>(A.hi, P == 3 ? A.lo : A.hi, B.hi, \
-                                                                          P == 3 ? B.lo : B.hi, p, e)
+#define MMAD_TC_LAUNCH2(P, AM, BMN, BNV)                                                                              \
+    gemm_tc_kernel<P, AM, BMN, BNV><<<grid, NTHREADS, Cfg<P, BNV>::kSmemBytes, s>>>(A.hi, P == 3 ? A.lo : A.hi, B.hi, \
+                                                                                   P == 3 ? B.lo : B.hi, p, e)
+#define MMAD_TC_LAUNCH(P, AM, BMN)                  \
+    do {                                            \
+        if (bn == 256) MMAD_TC_LAUNCH2(P, AM, BMN, 256); \
+        else MMAD_TC_LAUNCH2(P, AM, BMN, 128);      \
+    } while (0)
     if (passes == 3) {
         if (A.mn) MMAD_TC_LAUNCH(3, true, true);
         else if (B.mn) MMAD_TC_LAUNCH(3, false, true);
@@ -546,6 +562,7 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
         else if (B.mn) MMAD_TC_LAUNCH(1, false, true);
         else MMAD_TC_LAUNCH(1, false, false);
     }
+#undef MMAD_TC_LAUNCH2
 #undef MMAD_TC_LAUNCH
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());

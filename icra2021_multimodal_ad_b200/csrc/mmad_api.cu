@@ -4,6 +4,7 @@
 // (reference: reconstruction_aggregation.py:6-37, utils/metric.py:132-222).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -70,6 +71,10 @@ struct mmad_handle {
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; };
     std::vector<ProfRec> prof_recs;
+    // cached CUDA graphs of launch-bound sequences
+    struct GraphRec { std::string key; cudaGraphExec_t exec; unsigned long long launches; };
+    std::vector<GraphRec> graphs;
+    cudaStream_t s_capture = nullptr;
 };
 
 namespace mmad {
@@ -346,6 +351,34 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
 
 const mmad_desc_t* handle_desc(mmad_t h) { return &h->desc; }
 
+bool graphs_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMAD_NO_GRAPHS"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+cudaGraphExec_t handle_graph_find(mmad_t h, const std::string& key, unsigned long long* launches) {
+    for (auto& g : h->graphs)
+        if (g.key == key) { if (launches) *launches = g.launches; return g.exec; }
+    return nullptr;
+}
+
+void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsigned long long launches) {
+    if (h->graphs.size() >= 32) {          // bounded: drop the oldest
+        cudaGraphExecDestroy(h->graphs.front().exec);
+        h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back({key, g, launches});
+}
+
+cudaStream_t handle_capture_stream(mmad_t h) {
+    if (!h->s_capture && cudaStreamCreateWithFlags(&h->s_capture, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cannot create the capture stream");
+        return nullptr;
+    }
+    return h->s_capture;
+}
+
 LayerView handle_layer(mmad_t h, int module, int index) {
     const Layer& L = (module == 0 ? h->enc : h->dec)[index];
     LayerView v;
@@ -435,6 +468,8 @@ int mmad_destroy(mmad_t h) {
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->s_capture) cudaStreamDestroy(h->s_capture);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     delete h;

@@ -98,13 +98,20 @@ struct TcOperand {
 int tc_available();
 int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, int ld, int box_rows);
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
-            const Epilogue& e, cudaStream_t s);
-int gemm_tc_tile_n();
+            const Epilogue& e, cudaStream_t s, int bn = 256);   // bn: CTA tile width; K-major B maps need box_rows == bn
+int gemm_tc_tile_n();                    // the default (256)
+int gemm_tc_pick_bn(int M, int N);       // 256, or 128 when 256 would leave SMs idle
 
 // handle internals shared with train.cu (defined in mmad_api.cu)
 struct LayerView { int K, N, Kp, Np; __half* Wh; __half* Wl; float wscale; };
 const mmad_desc_t* handle_desc(mmad_t h);
 LayerView handle_layer(mmad_t h, int module, int index);
+
+// CUDA-graph cache of a handle (launch-bound sequences: the train step, small-batch scoring)
+bool graphs_enabled();                       // MMAD_NO_GRAPHS=1 disables
+cudaGraphExec_t handle_graph_find(mmad_t h, const std::string& key, unsigned long long* launches);
+void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsigned long long launches);
+cudaStream_t handle_capture_stream(mmad_t h);
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

@@ -11,6 +11,7 @@
 // Parameters / gradients / running stats are the caller's fp32 tensors (state_dict layout), used in place.
 #include <algorithm>
 #include <math.h>
+#include <string>
 
 #include "mmad_internal.cuh"
 
@@ -364,7 +365,7 @@ struct TrainPlan {
     size_t st[2][MMAD_MAX_LAYERS] = {{0}};    // [4][Np] doubles per layer: forward sum / sum sq, backward sum g / sum g xhat
     size_t st_all = 0, st_bytes = 0;
     size_t g[2] = {0, 0};                      // gradient ping-pong [B, maxNp]
-    size_t z = 0, genc = 0;                    // VIB: sampled code, gradient wrt the encoder output
+    size_t z = 0, genc = 0, eps = 0;           // VIB: sampled code, gradient wrt the encoder output, staged noise
     size_t rowpart = 0;
     size_t kl = 0;
     int maxNp = 0;
@@ -408,6 +409,7 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
     p.g[1] = take((size_t)B * maxNp * 4);
     p.z = take((size_t)B * np_of(d.dec_widths[0]) * 4);
     p.genc = take((size_t)B * np_of(d.enc_widths[d.n_enc]) * 4);
+    p.eps = take((size_t)B * np_of(d.dec_widths[0]) * 4);
     p.rowpart = take((size_t)((d.enc_widths[0] + 63) / 64 + 1) * B * 4);
     p.xp = take((size_t)B * np_of(d.enc_widths[0]) * 4);
     if (tc) {
@@ -441,39 +443,16 @@ size_t mmad_train_workspace_bytes(mmad_t h, int batch) {
     return make_train_plan(*handle_desc(h), batch, tc_available() != 0).total;
 }
 
-int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long global_batch,
-                       const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, const float* d_eps, float beta_kl,
-                       float bn_momentum, float* d_loss, void* d_ws, size_t ws_bytes, mmad_allreduce_fn allreduce,
-                       void* allreduce_ctx, void* stream) {
-    if (!h || !d_x || !enc || !dec || !d_loss || !d_ws) { set_error("null argument"); return MMAD_E_ARG; }
-    const mmad_desc_t& d = *handle_desc(h);
+// The whole step as a sequence of launches on stream s.  Inputs were staged into the workspace by the caller
+// (x as padded fp32 + fp16 twins, VIB noise), so every pointer used here is stable from step to step and the
+// sequence can be captured into a CUDA graph.
+static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool tc, bool vib, int batch, long long global_batch,
+                      const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, float beta_kl, float bn_momentum,
+                      float* d_loss, char* ws, mmad_allreduce_fn allreduce, void* allreduce_ctx, cudaStream_t s) {
     const int D = d.enc_widths[0];
-    if (batch < 1 || ldx < D) { set_error("bad batch/ldx"); return MMAD_E_ARG; }
-    if (global_batch < batch) global_batch = batch;
     const int enc_out = d.enc_widths[d.n_enc], dec_in = d.dec_widths[0];
-    const bool vib = d_eps != nullptr;
-    if (vib ? (enc_out != 2 * dec_in) : (enc_out != dec_in)) {
-        set_error("encoder output %d does not feed decoder input %d (%s)", enc_out, dec_in, vib ? "VIB expects 2x" : "pass eps for a VIB model");
-        return MMAD_E_ARG;
-    }
-    // tensor-core GEMMs for the plain autoencoder in the f16x3 / f16 modes; VIB and fp32 use the CUDA-core kernel
-    const bool tc = d.precision != MMAD_PREC_FP32 && !vib && tc_available();
     const int passes = d.precision == MMAD_PREC_F16X3 ? 3 : 1;
-    const TrainPlan p = make_train_plan(d, batch, tc);
-    if (ws_bytes < p.total) { set_error("train workspace too small: %zu < %zu", ws_bytes, p.total); return MMAD_E_WORKSPACE; }
-    for (int m = 0; m < 2; ++m) {
-        const int n = m == 0 ? d.n_enc : d.n_dec;
-        const mmad_train_layer_t* L = m == 0 ? enc : dec;
-        for (int i = 0; i < n; ++i) {
-            const bool bn = i < n - 1;
-            if (!L[i].W || !L[i].b || !L[i].gW || !L[i].gb || (bn && (!L[i].gamma || !L[i].beta || !L[i].ggamma || !L[i].gbeta))) {
-                set_error("layer %d.%d: missing parameter/gradient pointer", m, i);
-                return MMAD_E_ARG;
-            }
-        }
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    char* ws = (char*)d_ws;
+    const float* d_eps = vib ? (const float*)(ws + p.eps) : nullptr;
     const int B = batch;
     const double Bg = (double)global_batch;
     const float slope = d.lrelu_slope;
@@ -491,35 +470,29 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
                        bool b_mn, int M, int N, int K, const Epilogue& e) -> int {
         TcOperand A, Bo;
         int rc;
+        const int bn = e.rowpart ? gemm_tc_tile_n() : gemm_tc_pick_bn(M, N);   // loss partials are indexed by 256-wide tiles
         if (a_mn) { rc = tc_make_operand_map(&A.hi, Ah, K, M, lda, 64); if (!rc) rc = tc_make_operand_map(&A.lo, Al, K, M, lda, 64); }
         else { rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128); if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128); }
         if (rc) return rc;
         if (b_mn) { rc = tc_make_operand_map(&Bo.hi, Bh, K, N, ldb, 64); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, K, N, ldb, 64); }
-        else { rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, gemm_tc_tile_n()); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, gemm_tc_tile_n()); }
+        else { rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, bn); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, bn); }
         if (rc) return rc;
         A.mn = a_mn; Bo.mn = b_mn;
-        return gemm_tc(A, Bo, M, N, K, passes, e, s);
+        return gemm_tc(A, Bo, M, N, K, passes, e, s, bn);
     };
 
     // ------------------------------- forward -------------------------------
-    const bool x_aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0);
-    Mat cur{d_x, nullptr, nullptr, ldx};
-    const float* xref = d_x;      // reference of the loss epilogue
-    int ldxref = ldx;
+    const int Dp = np_of(D);
+    const float* xref = (const float*)(ws + p.xp);      // staged input: reference of the loss epilogue
+    const int ldxref = Dp;
+    Mat cur{xref, tc ? (const __half*)(ws + p.xh) : nullptr, tc ? (const __half*)(ws + p.xl) : nullptr, Dp};
     if (tc) {
-        const int Dp = np_of(D);
-        int rc = pad_split(d_x, ldx, B, D, x_aligned ? nullptr : (float*)(ws + p.xp), Dp, (__half*)(ws + p.xh), (__half*)(ws + p.xl), Dp, s);
-        if (rc) return rc;
-        if (!x_aligned) { xref = (const float*)(ws + p.xp); ldxref = Dp; }
-        cur = Mat{xref, (const __half*)(ws + p.xh), (const __half*)(ws + p.xl), Dp};
-        if (x_aligned) cur.f = d_x;
-        // the fp32 pointer of the input is only used by the CUDA-core path; twins share ld = Dp
         for (int m = 0; m < 2; ++m) {      // weights changed since the last step: refresh their fp16 twins
             const int n = m == 0 ? d.n_enc : d.n_dec;
             const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
             for (int i = 0; i < n; ++i) {
                 const LayerView lv = handle_layer(h, m, i);
-                rc = split_weights(Ls[i].W, lv.N, lv.K, lv.Kp, lv.wscale, lv.Wh, lv.Wl, s);
+                int rc = split_weights(Ls[i].W, lv.N, lv.K, lv.Kp, lv.wscale, lv.Wh, lv.Wl, s);
                 if (rc) return rc;
             }
         }
@@ -701,6 +674,82 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         gscale = 1.f;
     }
     MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long global_batch,
+                       const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, const float* d_eps, float beta_kl,
+                       float bn_momentum, float* d_loss, void* d_ws, size_t ws_bytes, mmad_allreduce_fn allreduce,
+                       void* allreduce_ctx, void* stream) {
+    if (!h || !d_x || !enc || !dec || !d_loss || !d_ws) { set_error("null argument"); return MMAD_E_ARG; }
+    const mmad_desc_t& d = *handle_desc(h);
+    const int D = d.enc_widths[0];
+    if (batch < 1 || ldx < D) { set_error("bad batch/ldx"); return MMAD_E_ARG; }
+    if (global_batch < batch) global_batch = batch;
+    const int enc_out = d.enc_widths[d.n_enc], dec_in = d.dec_widths[0];
+    const bool vib = d_eps != nullptr;
+    if (vib ? (enc_out != 2 * dec_in) : (enc_out != dec_in)) {
+        set_error("encoder output %d does not feed decoder input %d (%s)", enc_out, dec_in, vib ? "VIB expects 2x" : "pass eps for a VIB model");
+        return MMAD_E_ARG;
+    }
+    // tensor-core GEMMs for the plain autoencoder in the f16x3 / f16 modes; VIB and fp32 use the CUDA-core kernel
+    const bool tc = d.precision != MMAD_PREC_FP32 && !vib && tc_available();
+    const TrainPlan p = make_train_plan(d, batch, tc_available() != 0);
+    if (ws_bytes < p.total) { set_error("train workspace too small: %zu < %zu", ws_bytes, p.total); return MMAD_E_WORKSPACE; }
+    for (int m = 0; m < 2; ++m) {
+        const int n = m == 0 ? d.n_enc : d.n_dec;
+        const mmad_train_layer_t* L = m == 0 ? enc : dec;
+        for (int i = 0; i < n; ++i) {
+            const bool bn = i < n - 1;
+            if (!L[i].W || !L[i].b || !L[i].gW || !L[i].gb || (bn && (!L[i].gamma || !L[i].beta || !L[i].ggamma || !L[i].gbeta))) {
+                set_error("layer %d.%d: missing parameter/gradient pointer", m, i);
+                return MMAD_E_ARG;
+            }
+        }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    // ---- stage the per-step inputs into the workspace (everything after this uses stable pointers) ----
+    const int Dp = np_of(D);
+    int rc = pad_split(d_x, ldx, batch, D, (float*)(ws + p.xp), Dp, tc ? (__half*)(ws + p.xh) : nullptr,
+                       tc ? (__half*)(ws + p.xl) : nullptr, Dp, s);
+    if (rc) return rc;
+    if (vib) MMAD_CUDA_OK(cudaMemcpyAsync(ws + p.eps, d_eps, (size_t)batch * dec_in * 4, cudaMemcpyDeviceToDevice, s));
+
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    const bool use_graph = !allreduce && graphs_enabled() && cap == cudaStreamCaptureStatusNone;
+    if (!use_graph)
+        return train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, allreduce, allreduce_ctx, s);
+
+    // ---- CUDA graph of the step, keyed by everything the launch sequence depends on ----
+    std::string key("train");
+    auto add = [&](const void* q, size_t n) { key.append((const char*)q, n); };
+    add(&batch, sizeof batch); add(&global_batch, sizeof global_batch); add(&d.precision, sizeof d.precision);
+    add(enc, sizeof(mmad_train_layer_t) * d.n_enc); add(dec, sizeof(mmad_train_layer_t) * d.n_dec);
+    add(&beta_kl, sizeof beta_kl); add(&bn_momentum, sizeof bn_momentum); add(&d_loss, sizeof d_loss); add(&d_ws, sizeof d_ws);
+    add(&vib, sizeof vib);
+    unsigned long long n_launch = 0;
+    cudaGraphExec_t exec = handle_graph_find(h, key, &n_launch);
+    if (!exec) {
+        cudaStream_t cs = handle_capture_stream(h);
+        if (!cs) return MMAD_E_CUDA;
+        const unsigned long long l0 = g_launches;
+        MMAD_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, nullptr, nullptr, cs);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        n_launch = g_launches - l0;
+        g_launches = l0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || !graph) { set_error("graph capture of the train step failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return MMAD_E_CUDA; }
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return MMAD_E_CUDA; }
+        handle_graph_put(h, key, exec, n_launch);
+    }
+    MMAD_CUDA_OK(cudaGraphLaunch(exec, s));
+    g_launches += n_launch;
     return MMAD_OK;
 }
 
