@@ -51,6 +51,7 @@ SIGNATURES = {
     "mmad_nap_set_fit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmad_nap_rotate_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmad_nap_set_standardizer": (_i, [_vp, _vp, _vp, _vp]),
+    "mmad_nap_set_structure": (_i, [_vp, _i]),
     "mmad_fc_layer_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp]),
     "mmad_sq_diff_sum": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "mmad_row_mean_sq": (_i, [_vp, _i, _i, _i, _vp, _vp]),

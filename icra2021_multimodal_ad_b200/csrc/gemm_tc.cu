@@ -132,6 +132,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n;
+    int tri;             // B is upper triangular (B[n,k] = 0 for k < n): k-blocks left of the tile's first row are skipped
     int splits;          // split-K factor (plain epilogue only): work item = (tile, split), atomically accumulated
 };
 
@@ -186,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w % p.splits;
                 const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
-                const int kb_lo = sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
@@ -225,8 +226,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             int acc = 0; uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w % p.splits;
-                const int kb_lo = sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 const int n0 = (t % p.tiles_n) * BN;
+                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
                 const uint32_t idesc = make_idesc(n_eff, A_MN, B_MN);
@@ -535,7 +536,8 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (K + BK - 1) / BK;
     p.splits = 1;
-    if (e.plain && e.split_k_ok && tiles * 2 <= g_num_sms) {
+    p.tri = e.b_upper_tri ? 1 : 0;
+    if (!p.tri && e.plain && e.split_k_ok && tiles * 2 <= g_num_sms) {
         p.splits = g_num_sms / tiles;
         if (p.splits > num_kb) p.splits = num_kb;
         if (p.splits < 1) p.splits = 1;

@@ -44,6 +44,7 @@ struct NapFit {
     float* bias = nullptr;      // [K] -(mu.v_j + mu2_j) var_j^-1/2
     float* bias_rot = nullptr;  // [K] -mu.v_j  (rotation alone, for the Standardizer refit pass)
     float wscale = 256.f;
+    bool upper_tri = false;     // rows are an upper-triangular whitening factor (mmad_nap_set_structure)
     __half* Bh = nullptr;
     __half* Bl = nullptr;
     TcOperand tcB;
@@ -64,6 +65,7 @@ struct mmad_handle {
     size_t host_ws_bytes = 0;
     float* host_x[2] = {nullptr, nullptr};
     float* host_out[2] = {nullptr, nullptr};
+    float* host_pin[2] = {nullptr, nullptr};   // pinned staging of the scores (D2H never blocks the issuing thread)
     int host_chunk = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -80,6 +82,7 @@ struct mmad_handle {
 namespace mmad {
 
 constexpr int kMaxChunk = 16384;
+constexpr int kStreamRows = 2048;     // host calls up to this many rows take the graph-replay latency path
 constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
 
 static int D_of(mmad_t h) { return h->desc.enc_widths[0]; }
@@ -371,6 +374,11 @@ void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsig
     h->graphs.push_back({key, g, launches});
 }
 
+void handle_graph_clear(mmad_t h) {
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
 cudaStream_t handle_capture_stream(mmad_t h) {
     if (!h->s_capture && cudaStreamCreateWithFlags(&h->s_capture, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cannot create the capture stream");
@@ -464,6 +472,7 @@ int mmad_destroy(mmad_t h) {
     cudaFree(h->host_ws);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->host_x[i]); cudaFree(h->host_out[i]);
+        if (h->host_pin[i]) cudaFreeHost(h->host_pin[i]);
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -483,6 +492,7 @@ int mmad_set_precision(mmad_t h, int precision) {
         set_error("tensor-core precision requested but the device is not sm_100"); return MMAD_E_UNSUPPORTED;
     }
     h->desc.precision = precision;
+    handle_graph_clear(h);
     return MMAD_OK;
 }
 
@@ -632,6 +642,7 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         if (rc) return rc;
         A.rows = rows; A.k = f.Dp;
         e.acc_scale = 1.f / (f.wscale * kDiffScale);
+        e.b_upper_tri = f.upper_tri ? 1 : 0;
         rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
     }
     if (rc || !d_nap) return rc;
@@ -758,7 +769,8 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
     if (K < 1 || K > D) { set_error("NAP fit: K=%d must be in [1,%d]", K, D); return MMAD_E_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     NapFit& f = h->nap;
-    MMAD_CUDA_OK(cudaStreamSynchronize(s));
+    MMAD_CUDA_OK(cudaDeviceSynchronize());
+    handle_graph_clear(h);          // cached graphs hold the old fit's pointers
     cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.bias_rot); cudaFree(f.Bh); cudaFree(f.Bl);
     f = NapFit();
     const SegMap seg = make_segmap(h, lo, hi);
@@ -781,6 +793,15 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
         f.tc_ready = true;
     }
     f.ready = true;
+    return MMAD_OK;
+}
+
+int mmad_nap_set_structure(mmad_t h, int upper_triangular) {
+    if (!h) { set_error("null handle"); return MMAD_E_ARG; }
+    if (!h->nap.ready) { set_error("no NAP fit installed"); return MMAD_E_STATE; }
+    if (upper_triangular && h->nap.K > h->nap.D) { set_error("triangular factor needs K <= D'"); return MMAD_E_ARG; }
+    h->nap.upper_tri = upper_triangular != 0;
+    handle_graph_clear(h);
     return MMAD_OK;
 }
 
@@ -851,22 +872,88 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
     if (h->host_chunk < chunk || h->host_ws_bytes < need_ws) {
         MMAD_CUDA_OK(cudaDeviceSynchronize());
         cudaFree(h->host_ws); h->host_ws = nullptr;
-        for (int i = 0; i < 2; ++i) { cudaFree(h->host_x[i]); cudaFree(h->host_out[i]); h->host_x[i] = h->host_out[i] = nullptr; }
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->host_x[i]); cudaFree(h->host_out[i]); h->host_x[i] = h->host_out[i] = nullptr;
+            if (h->host_pin[i]) { cudaFreeHost(h->host_pin[i]); h->host_pin[i] = nullptr; }
+        }
         MMAD_CUDA_OK(cudaMalloc(&h->host_ws, need_ws));
         for (int i = 0; i < 2; ++i) {
             MMAD_CUDA_OK(cudaMalloc(&h->host_x[i], (size_t)chunk * D * 4));
             MMAD_CUDA_OK(cudaMalloc(&h->host_out[i], (size_t)chunk * 3 * 4));
+            MMAD_CUDA_OK(cudaMallocHost(&h->host_pin[i], (size_t)chunk * 3 * 4));
         }
         h->host_ws_bytes = need_ws;
         h->host_chunk = chunk;
     }
+    if (n <= kStreamRows && graphs_enabled() && !h->prof) {
+        // ---- latency path (realtime_tester-style calls): one H2D, one graph replay, one D2H ----
+        const int rows = (int)n;
+        cudaStream_t s = h->s_comp;
+        if (ldx == D)
+            MMAD_CUDA_OK(cudaMemcpyAsync(h->host_x[0], h_x, (size_t)rows * D * 4, cudaMemcpyHostToDevice, s));
+        else
+            MMAD_CUDA_OK(cudaMemcpy2DAsync(h->host_x[0], (size_t)D * 4, h_x, (size_t)ldx * 4, (size_t)D * 4, rows,
+                                           cudaMemcpyHostToDevice, s));
+        float* o = h->host_out[0];
+        float* ob = h_base ? o : nullptr;
+        float* os = h_sap ? o + rows : nullptr;
+        float* on = h_nap ? o + 2 * (size_t)rows : nullptr;
+        std::string key("score");
+        auto add = [&](const void* q, size_t nb) { key.append((const char*)q, nb); };
+        const int mask = (h_base ? 1 : 0) | (h_sap ? 2 : 0) | (h_nap ? 4 : 0);
+        add(&rows, sizeof rows); add(&lo, sizeof lo); add(&hi, sizeof hi); add(&mask, sizeof mask);
+        add(&h->desc.precision, sizeof h->desc.precision); add(&h->host_ws, sizeof h->host_ws); add(&o, sizeof o);
+        unsigned long long n_launch = 0;
+        cudaGraphExec_t exec = handle_graph_find(h, key, &n_launch);
+        if (!exec) {
+            cudaStream_t cs = handle_capture_stream(h);
+            if (!cs) return MMAD_E_CUDA;
+            const unsigned long long l0 = g_launches;
+            MMAD_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            rc = mmad_score(h, h->host_x[0], D, rows, lo, hi, ob, os, on, nullptr, h->host_ws, h->host_ws_bytes, cs);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+            n_launch = g_launches - l0;
+            g_launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess || !graph) { set_error("graph capture of the scoring chain failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return MMAD_E_CUDA; }
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return MMAD_E_CUDA; }
+            handle_graph_put(h, key, exec, n_launch);
+        }
+        MMAD_CUDA_OK(cudaGraphLaunch(exec, s));
+        g_launches += n_launch;
+        MMAD_CUDA_OK(cudaMemcpyAsync(h->host_pin[0], o, (size_t)rows * 3 * 4, cudaMemcpyDeviceToHost, s));
+        MMAD_CUDA_OK(cudaStreamSynchronize(s));
+        const float* pin = h->host_pin[0];
+        if (h_base) memcpy(h_base, pin, (size_t)rows * 4);
+        if (h_sap) memcpy(h_sap, pin + rows, (size_t)rows * 4);
+        if (h_nap) memcpy(h_nap, pin + 2 * (size_t)rows, (size_t)rows * 4);
+        return MMAD_OK;
+    }
     long long r0 = 0;
     int it = 0;
+    long long past_r0[2] = {0, 0};
+    int past_rows[2] = {0, 0};
+    const size_t hc = (size_t)h->host_chunk;
+    // scores of the chunk that used staging buffer b have landed in pinned memory: hand them to the caller
+    auto drain = [&](int b) -> int {
+        MMAD_CUDA_OK(cudaEventSynchronize(h->ev_done[b]));
+        const float* o = h->host_pin[b];
+        const size_t bytes = (size_t)past_rows[b] * 4;
+        if (h_base) memcpy(h_base + past_r0[b], o, bytes);
+        if (h_sap) memcpy(h_sap + past_r0[b], o + hc, bytes);
+        if (h_nap) memcpy(h_nap + past_r0[b], o + 2 * hc, bytes);
+        return MMAD_OK;
+    };
     for (; r0 < n; ++it) {
         const int b = it & 1;
         const int rows = (int)std::min<long long>(h->host_chunk, n - r0);
-        // input buffer b is free once the compute that read it two iterations ago is done
-        if (it >= 2) MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_free[b], 0));
+        if (it >= 2) {   // buffers b are free once the chunk of two iterations ago is done and drained
+            rc = drain(b);
+            if (rc) return rc;
+        }
         if (ldx == D)
             MMAD_CUDA_OK(cudaMemcpyAsync(h->host_x[b], h_x + (size_t)r0 * ldx, (size_t)rows * D * 4,
                                          cudaMemcpyHostToDevice, h->s_copy));
@@ -876,17 +963,21 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         MMAD_CUDA_OK(cudaEventRecord(h->ev_in[b], h->s_copy));
         MMAD_CUDA_OK(cudaStreamWaitEvent(h->s_comp, h->ev_in[b], 0));
         float* o = h->host_out[b];
-        rc = mmad_score(h, h->host_x[b], D, rows, lo, hi, h_base ? o : nullptr, h_sap ? o + h->host_chunk : nullptr,
-                        h_nap ? o + 2 * (size_t)h->host_chunk : nullptr, nullptr, h->host_ws, h->host_ws_bytes, h->s_comp);
+        rc = mmad_score(h, h->host_x[b], D, rows, lo, hi, h_base ? o : nullptr, h_sap ? o + hc : nullptr,
+                        h_nap ? o + 2 * hc : nullptr, nullptr, h->host_ws, h->host_ws_bytes, h->s_comp);
         if (rc) return rc;
-        MMAD_CUDA_OK(cudaEventRecord(h->ev_free[b], h->s_comp));
-        if (h_base) MMAD_CUDA_OK(cudaMemcpyAsync(h_base + r0, o, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
-        if (h_sap) MMAD_CUDA_OK(cudaMemcpyAsync(h_sap + r0, o + h->host_chunk, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
-        if (h_nap) MMAD_CUDA_OK(cudaMemcpyAsync(h_nap + r0, o + 2 * (size_t)h->host_chunk, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        float* pin = h->host_pin[b];
+        if (h_base) MMAD_CUDA_OK(cudaMemcpyAsync(pin, o, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        if (h_sap) MMAD_CUDA_OK(cudaMemcpyAsync(pin + hc, o + hc, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        if (h_nap) MMAD_CUDA_OK(cudaMemcpyAsync(pin + 2 * hc, o + 2 * hc, (size_t)rows * 4, cudaMemcpyDeviceToHost, h->s_comp));
+        MMAD_CUDA_OK(cudaEventRecord(h->ev_done[b], h->s_comp));
+        past_r0[b] = r0; past_rows[b] = rows;
         r0 += rows;
     }
-    MMAD_CUDA_OK(cudaStreamSynchronize(h->s_comp));
-    MMAD_CUDA_OK(cudaStreamSynchronize(h->s_copy));
+    for (int k = std::max(0, it - 2); k < it; ++k) {
+        rc = drain(k & 1);
+        if (rc) return rc;
+    }
     return MMAD_OK;
 }
 

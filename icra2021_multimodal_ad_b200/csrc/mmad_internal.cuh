@@ -60,6 +60,7 @@ struct Epilogue {
     int sq_self = 0;
     float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
     int plain = 0;                                      // Y = acc * acc_scale + bias only, rows of Y may be unaligned
+    int b_upper_tri = 0;                                // B[n, k] == 0 for k < n (tensor-core kernel skips those k-blocks)
     int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
     float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)
 };
@@ -112,6 +113,7 @@ bool graphs_enabled();                       // MMAD_NO_GRAPHS=1 disables
 cudaGraphExec_t handle_graph_find(mmad_t h, const std::string& key, unsigned long long* launches);
 void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsigned long long launches);
 cudaStream_t handle_capture_stream(mmad_t h);
+void handle_graph_clear(mmad_t h);
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

@@ -229,7 +229,7 @@ class Engine:
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
                 batch_rows: int = 16384, distributed: Optional[bool] = None,
-                restandardize: bool = True) -> Dict[str, torch.Tensor]:
+                restandardize: bool = True, factor: str = "triangular") -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
@@ -256,8 +256,9 @@ class Engine:
             self.nap_accumulate_gram(x_train[r0:r0 + batch_rows], lo, hi, mu, gram)
         if use_dist:
             dist.all_reduce(gram, group=group)
-        fit = nap_fit_from_stats(mu, gram, N)
+        fit = nap_fit_from_stats(mu, gram, N, factor=factor)
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
+        check(lib().mmad_nap_set_structure(self._h, 1 if fit["factor"] == "triangular" else 0))
         if restandardize:
             # Standardizer.fit on Rotater.run(train) (utils/metric.py:214-216): third pass, the rotation done
             # by the scoring kernels themselves so their rounding noise in near-null directions
@@ -275,16 +276,33 @@ class Engine:
         return fit
 
 
-def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int) -> Dict[str, torch.Tensor]:
+def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "eigen") -> Dict[str, torch.Tensor]:
     """Eigendecomposition of the centred Gram matrix (fp64, cuSOLVER syevd through
-    torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2)."""
+    torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2).
+
+    factor="eigen": rows of ``vt`` are the right singular vectors v_j like the reference's Rotater
+    (utils/normalize.py:67) and ``var`` their variances.
+    factor="triangular": the same score sum_j ((d-mu).v_j)^2 / var_j = |R (d-mu)|^2 through the upper
+    triangular factor R of the whitening matrix diag(var^-1/2) V^T = Q R (fp64 Householder QR): half of R is
+    zero, so the scoring GEMM does half the products.  Rows are normalised to unit max (the scale goes into
+    ``var``) so they split cleanly into fp16 pairs."""
     lam, V = torch.linalg.eigh(gram)            # ascending
     # near-null directions (SURVEY F5) can come out slightly negative; floor at fp64 resolution of the
     # largest eigenvalue so that var stays positive like the reference's np.cov diagonal
     lam = lam.flip(0).clamp_min(lam.max() * 1e-16)
     V = V.flip(1)
     K = min(n_total, gram.shape[0])
-    var = (lam[:K] / (n_total - 1)).float()
-    vt = V[:, :K].t().contiguous().float()
+    var64 = lam[:K] / (n_total - 1)
+    if factor == "triangular":
+        W = V[:, :K].t() / var64.sqrt().unsqueeze(1)                     # K x D' whitening matrix
+        R = torch.linalg.qr(W, mode="r").R                                 # K x D', upper triangular / trapezoidal
+        scale = R.abs().amax(dim=1).clamp_min(1e-300)
+        vt = torch.triu(R / scale.unsqueeze(1)).contiguous().float()
+        var = (1.0 / (scale * scale)).float()
+    elif factor == "eigen":
+        vt = V[:, :K].t().contiguous().float()
+        var = var64.float()
+    else:
+        raise ValueError("factor must be 'eigen' or 'triangular'")
     return {"mu": mu.float(), "vt": vt, "var": var, "mu2": torch.zeros(K, dtype=torch.float32, device=mu.device),
-            "n": n_total}
+            "n": n_total, "factor": factor}

@@ -108,8 +108,9 @@ def test_layer_by_layer_api_matches_fused_chain():
     assert _rel_max(xh.cpu(), RO.ae_forward_eval(x, sd)) < 1e-5
 
 
+@pytest.mark.parametrize("factor", ["eigen", "triangular"])
 @pytest.mark.parametrize("precision", PRECISIONS)
-def test_nap_single_layers_match_reference(precision):
+def test_nap_single_layers_match_reference(precision, factor):
     g = load_golden("score_D64.pt")
     D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
     m = _model(D, btl, nl, seed, precision)
@@ -118,9 +119,25 @@ def test_nap_single_layers_match_reference(precision):
     xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
     for sel in ("0:1", "1:2"):
         lo, hi = map(int, sel.split(":"))
-        eng.nap_fit(xtr.cuda(), lo, hi, distributed=False)
+        eng.nap_fit(xtr.cuda(), lo, hi, distributed=False, factor=factor)
         s = eng.score(xte.cuda(), lo, hi, base=False, sap=False, nap=True)["nap"].cpu().numpy()
         np.testing.assert_allclose(s, g["nap"][sel]["score"].numpy(), rtol=1e-3)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_nap_triangular_equals_eigen_at_headline_width(precision):
+    """D = 1728, layer selection [0:1] (well conditioned, D' = 1728 > 1 tile row): the triangular whitening
+    factor (half the products) and the eigenvector rotation give the same scores to 1e-4."""
+    D, btl, nl, seed = 1728, 100, 5, 31
+    m = _model(D, btl, nl, seed, precision)
+    eng = m.engine()
+    xtr, _ = synth_windows(4096, D, seed + 1, anomaly_rate=0.0)
+    xte, _ = synth_windows(300, D, seed + 3, anomaly_rate=0.15)
+    out = {}
+    for factor in ("eigen", "triangular"):
+        eng.nap_fit(xtr.cuda(), 0, 1, distributed=False, factor=factor)
+        out[factor] = eng.score(xte.cuda(), 0, 1, base=False, sap=False, nap=True)["nap"].cpu().numpy()
+    np.testing.assert_allclose(out["triangular"], out["eigen"], rtol=1e-4)
 
 
 def test_f16_single_pass_stated_tolerance():
