@@ -81,7 +81,8 @@ struct mmad_handle {
 
 namespace mmad {
 
-constexpr int kMaxChunk = 16384;
+constexpr int kMaxChunk = 65536;      // rows per device-side chunk (as many as the workspace allows)
+constexpr int kHostChunk = 16384;     // rows per pipelined host->device chunk of mmad_score_host
 constexpr int kStreamRows = 2048;     // host calls up to this many rows take the graph-replay latency path
 constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
 
@@ -858,7 +859,7 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         return MMAD_E_STATE;
     }
     const int D = D_of(h);
-    const int chunk = (int)std::min<long long>(kMaxChunk, std::max<long long>(128, (n + 127) / 128 * 128));
+    const int chunk = (int)std::min<long long>(kHostChunk, std::max<long long>(128, (n + 127) / 128 * 128));
     if (!h->s_copy) {
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
