@@ -309,11 +309,13 @@ def main():
     sampler.start()
     launches0 = L.mmad_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()        # ncu --profile-from-start off captures exactly the timed region
     ev0.record()
     for _ in range(args.steps):
         out = step_dev()
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = L.mmad_launch_count() - launches0
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -335,8 +337,15 @@ def main():
     pk, pk_kind = peaks()
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused GEMM, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj.get("precision") == precision and tj.get("batch") == args.batch:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                 "kernel": "fused layer GEMM (%s)" % precision, "peak_source": pk_kind + " bf16 sustained",
                 "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / args.steps)}
 

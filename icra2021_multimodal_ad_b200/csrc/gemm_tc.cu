@@ -20,114 +20,13 @@
 // activation tile in L2.  All mbarrier waits are bounded and trap instead of hanging the GPU.
 #include <dlfcn.h>
 
-#include "mmad_internal.cuh"
+#include "gemm_tc_common.cuh"
 
 namespace mmad {
 
+using namespace tc;
+
 namespace {
-
-constexpr int BM = 128;
-constexpr int BN_MAX = 256;            // CTA tile is 128 x BN with BN = 256 (throughput) or 128 (under-filled grids)
-constexpr int BK = 64;                 // halfs per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;
-constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int STG_LD = 36;                  // floats per row of an epilogue transpose tile (conflict-free float4)
-
-template <int PASSES, int BN> struct Cfg {
-    static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
-    static constexpr int kBTileBytes = BN * BK * 2;            // 32 KB / 16 KB
-    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + kBTileBytes);
-    static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 2 / 3 / 4 / 6
-    static constexpr int kSmemTiles = kStages * kStageBytes;   // <= 192 KB
-    static constexpr int kTmemCols = 2 * BN;                   // two fp32 accumulators
-    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 4 * 32 * STG_LD * 4 /*transpose tiles*/ +
-                                      256 /*barriers*/ + 1024 /*align*/;
-};
-
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < 4000000000LL)     // ~2 s at 2 GHz
-        if (mbar_try_wait(bar, parity)) return;
-    printf("mmad gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-    __trap();
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// smem matrix descriptor, 128-byte swizzle (SM100 descriptor version 1).
-//   K-major  (contraction dim contiguous): rows of 64 halfs; 8-row groups SBO = 1024 B apart; LBO unused.
-//   MN-major (M/N dim contiguous): one 128-byte row per k holding 64 consecutive m (or n); 8-k groups
-//            SBO = 1024 B apart; the next 64 m/n start LBO = 8192 B further (one TMA box of 64 k rows).
-template <bool MN_MAJOR>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFF) >> 4);                          // start address, 16-byte units
-    d |= (uint64_t)(MN_MAJOR ? (8192 >> 4) : 1) << 16;               // leading byte offset
-    d |= (uint64_t)(1024 >> 4) << 32;                                // stride byte offset
-    d |= (uint64_t)1 << 46;                                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                                          // SWIZZLE_128B
-    return d;
-}
-// instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = n; bits 15/16 select MN-major A / B
-__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct TcParams {
     int M, N, K;
@@ -271,170 +170,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int et = threadIdx.x - 64;        // 0..127
         float* stg = s_stage + q * (32 * STG_LD);
-        const int rsub = lane >> 3;             // 0..3  row inside a group of 4
-        const int c4 = (lane & 7) * 4;          // first of this lane's 4 columns inside the 32-column chunk
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
             const int t = w / p.splits, sp = w % p.splits;
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
             // stage the per-column epilogue vectors of this tile
             asm volatile("bar.sync 1, 128;");
-            for (int c = et; c < BN; c += 128) {
-                const int gc = n0 + c;
-                const bool ok = gc < p.N;
-                s_mul[c] = e.acc_scale * ((e.col_scale && ok) ? e.col_scale[gc] : 1.f);
-                s_bias[c] = (e.bias && ok && sp == 0) ? e.bias[gc] : 0.f;
-                s_sc[c] = (e.bn_scale && ok) ? e.bn_scale[gc] : 1.f;
-                s_sh[c] = (e.bn_scale && ok) ? e.bn_shift[gc] : 0.f;
-            }
+            epi_stage_vectors<BN>(e, p.N, n0, sp, et, s_mul, s_bias, s_sc, s_sh);
             asm volatile("bar.sync 1, 128;");
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             float sq[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sq[i] = 0.f;
-            int n_cols = p.N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
-            int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
-            int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
-            const int c_end = (max(max(n_cols, w_cols), dw_cols) + 31) & ~31;
-            for (int c0 = 0; c0 < c_end && c0 < BN; c0 += 32) {
-                // issue this chunk's reference loads first: 8 independent 16-byte loads per lane in
-                // flight while the accumulator chunk is fetched from TMEM and transposed
-                float4 rf[8];
-                if (e.ref) {
-                    const int ccp = c0 + c4;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = row_base + it * 4 + rsub;
-                        rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < p.M && ccp + 3 < n_cols)
-                            rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + ccp));
-                    }
-                }
-                {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    float4* wr = reinterpret_cast<float4*>(stg + lane * STG_LD);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        wr[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                }
-                __syncwarp();
-                if (e.plain) {
-                    // plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]):
-                    // lane <-> column, one coalesced 128-byte row segment per instruction
-                    const int c = c0 + lane;
-                    const int gc = n0 + c;
-                    if (gc < p.N) {
-                        const float mulc = s_mul[c], biac = s_bias[c];
-                        if (p.splits > 1) {     // split-K: partial products accumulate into the zeroed output
-#pragma unroll 8
-                            for (int rl = 0; rl < 32; ++rl) {
-                                const int r = row_base + rl;
-                                if (r < p.M) atomicAdd(e.Y + (size_t)r * e.ldy + gc, fmaf(stg[rl * STG_LD + lane], mulc, biac));
-                            }
-                        } else {
-#pragma unroll 8
-                            for (int rl = 0; rl < 32; ++rl) {
-                                const int r = row_base + rl;
-                                if (r < p.M) e.Y[(size_t)r * e.ldy + gc] = fmaf(stg[rl * STG_LD + lane], mulc, biac);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                const int cc = c0 + c4;                 // tile-local column of this lane's float4
-                const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
-                const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
-                const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc);
-                const float4 sh = *reinterpret_cast<const float4*>(s_sh + cc);
-                const bool k0 = cc < n_cols, k1 = cc + 1 < n_cols, k2 = cc + 2 < n_cols, k3 = cc + 3 < n_cols;
-                const bool wy = cc < w_cols, wd = cc < dw_cols;   // widths are multiples of 4 (padded to 64)
-                const size_t gcol = (size_t)n0 + cc;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rl = it * 4 + rsub;
-                    const int r = row_base + rl;
-                    const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
-                    float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
-                    float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
-                    if (r < p.M) {
-                        if (e.pre && cc < e.ldpre - n0)     // train: pre-activation, zero padded to ldpre columns
-                            *reinterpret_cast<float4*>(e.pre + (size_t)r * e.ldpre + gcol) =
-                                make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
-                        if (e.bn_scale) {
-                            x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
-                            x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
-                            x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
-                            x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
-                        }
-                        x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
-                        if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
-                        if (e.Yh && wy) {
-                            const float ys = e.y_split_scale;
-                            const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
-                            const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                            uint2 hv;
-                            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                            *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
-                            if (e.Yl) {
-                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                                const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
-                                const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
-                                uint2 lv;
-                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                                *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
-                            }
-                        }
-                        if (e.ref) {
-                            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-                            if (k3) {
-                                const float4 f = rf[it];
-                                d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
-                            } else if (k0) {
-                                const float* rp = e.ref + (size_t)r * e.ldref + gcol;
-                                d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
-                            }
-                            sq[it] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq[it]))));
-                            if (e.dout && wd) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + gcol) = make_float4(d0, d1, d2, d3);
-                            if (e.Dh && wd) {
-                                const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
-                                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
-                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
-                                const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
-                                uint2 hv, lv;
-                                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                                *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + gcol) = hv;
-                                *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + gcol) = lv;
-                            }
-                        } else if (e.sq_self) {
-                            sq[it] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq[it]))));
-                        }
-                    }
-                }
-                __syncwarp();     // the staging tile is rewritten by the next chunk
-            }
+            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, sq);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc]));
-            if (e.rowpart) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    float v = sq[it];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    const int r = row_base + it * 4 + rsub;
-                    if ((lane & 7) == 0 && r < p.M) e.rowpart[(size_t)tn * e.rowpart_stride + r] = v;
-                }
-            }
+            epi_rowpart(e, p.M, row_base, tn, lane, sq);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

@@ -1,0 +1,279 @@
+// tcgen05 fused layer GEMM on CTA PAIRS (cta_group::2) -- the bulk-scoring kernel.
+//
+// Same math and epilogue as gemm_tc.cu, but one 256 x 256 output tile is computed by two CTAs on adjacent
+// SMs (a cluster of 2): each CTA stages ITS 128 rows of A and ITS half of the B tile (128 of the 256 weight
+// rows), one elected thread of the even CTA issues tcgen05.mma.cta_group::2 (M = 256), and each CTA keeps its
+// 128 accumulator rows in its own TMEM and runs its own epilogue.
+//
+// Why: in the f16x3 mode every k-block needs the hi AND lo halves of both operands.  With one CTA per tile
+// that is 96 KB of shared memory per stage -- two stages, one load in flight, and a load latency of ~1 us
+// against ~1 us of MMA work per k-block leaves the tensor pipe ~60-80 % busy (profiles/r1_ncu_full_gemm_tc_v3.md).
+// A CTA pair needs 64 KB per CTA per stage: three stages, two loads in flight, and a third less L2->SMEM
+// traffic per FLOP because B is not duplicated.
+//
+// Barrier protocol (s = stage, a = accumulator buffer):
+//   full[s]      in the EVEN CTA: armed by its producer with expect_tx of both CTAs' bytes; both producers' TMA
+//                loads complete on it (cta_group::2 loads address the even CTA's barrier)
+//   empty[s]     in each CTA: tcgen05.commit.multicast from the MMA thread frees the stage in both CTAs
+//   acc_full[a]  in each CTA: commit.multicast after the last k-block
+//   acc_empty[a] in the EVEN CTA: 8 arrivals (4 epilogue warps x 2 CTAs; the odd CTA arrives remotely)
+#include <stdlib.h>
+
+#include "gemm_tc_common.cuh"
+
+namespace mmad {
+
+using namespace tc;
+
+namespace {
+
+constexpr int BN2 = 256;                       // tile width; each CTA holds BN2/2 rows of B
+constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;   // 16 KB
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> even CTA
+
+template <int PASSES> struct Cfg2 {
+    static constexpr int kOperands = PASSES == 3 ? 2 : 1;
+    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_HALF_BYTES);        // 64 KB / 32 KB per CTA
+    static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 3 / 6
+    static constexpr int kSmemTiles = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kSmemTiles + 4 * BN2 * 4 + 4 * 32 * STG_LD * 4 + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_even), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_even(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// instruction descriptor: fp16 x fp16 -> fp32, K-major A and B, M = 256 (pair), N = n
+__device__ __forceinline__ uint32_t make_idesc_pair(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+struct Tc2Params {
+    int M, N, K;
+    int tiles_m, tiles_n;     // tiles of 256 x 256
+    int tri;
+};
+
+template <int PASSES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                Tc2Params p, Epilogue e) {
+    using C = Cfg2<PASSES>;
+    constexpr int BN = BN2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_mul = reinterpret_cast<float*>(smem + C::kSmemTiles);
+    float* s_bias = s_mul + BN;
+    float* s_sc = s_bias + BN;
+    float* s_sh = s_sc + BN;
+    float* s_stage = s_sh + BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * STG_LD);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::kStages;
+    uint64_t* acc_full = empty + C::kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
+        if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
+    }
+    if (warp == 1) {   // the same logical warp of both CTAs allocates (and later frees) the pair's TMEM
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised before anything is signalled remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                const int n0 = (t % p.tiles_n) * BN;
+                int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
+                n_eff = (n_eff + 15) & ~15;
+                const int m0 = (t / p.tiles_n) * 256 + (int)rank * BM;       // this CTA's 128 rows of A
+                const int nb0 = n0 + (int)rank * (n_eff >> 1);                // this CTA's half of the B rows
+                const int kb_lo = p.tri ? n0 / BK : 0;
+                for (int kb = kb_lo; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(smem_u32(&full[stage]), 2 * C::kStageBytes);
+                    const uint32_t fb = smem_u32(&full[stage]) & kPeerBitMask;
+                    uint8_t* st = smem + stage * C::kStageBytes;
+                    tma_load_2d_pair(smem_u32(st), &mapAh, fb, kb * BK, m0);
+                    tma_load_2d_pair(smem_u32(st + A_TILE_BYTES), &mapBh, fb, kb * BK, nb0);
+                    if (PASSES == 3) {
+                        tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * BK, m0);
+                        tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * BK, nb0);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (even CTA only) =================
+        if (lane == 0 && rank == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                const int n0 = (t % p.tiles_n) * BN;
+                const int kb_lo = p.tri ? n0 / BK : 0;
+                int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
+                n_eff = (n_eff + 15) & ~15;
+                const uint32_t idesc = make_idesc_pair(n_eff);
+                mbar_wait(smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb_lo; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t dAh = make_smem_desc<false>(st);
+                    const uint64_t dBh = make_smem_desc<false>(st + A_TILE_BYTES);
+                    const uint64_t dAl = make_smem_desc<false>(st + A_TILE_BYTES + B_HALF_BYTES);
+                    const uint64_t dBl = make_smem_desc<false>(st + 2 * A_TILE_BYTES + B_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        if (PASSES == 3) {
+                            umma_f16_pair(d_tmem, dAh + adv, dBl + adv, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16_pair(d_tmem, dAl + adv, dBh + adv, idesc, 1);
+                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                        } else {
+                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, ((kb - kb_lo) | k) != 0);
+                        }
+                    }
+                    umma_commit_pair(smem_u32(&empty[stage]));
+                    if (kb == num_kb - 1) umma_commit_pair(smem_u32(&acc_full[acc]));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 of both CTAs): this CTA's 128 accumulator rows =================
+        const int q = warp & 3;
+        const int et = threadIdx.x - 64;
+        float* stg = s_stage + q * (32 * STG_LD);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = pair; t < num_tiles; t += npairs) {
+            const int m0 = (t / p.tiles_n) * 256 + (int)rank * BM, tn = t % p.tiles_n, n0 = tn * BN;
+            asm volatile("bar.sync 1, 128;");
+            epi_stage_vectors<BN>(e, p.N, n0, 0, et, s_mul, s_bias, s_sc, s_sh);
+            asm volatile("bar.sync 1, 128;");
+            mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
+            tc_fence_after();
+            const int row_base = m0 + q * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            float sq[8];
+            epi_tile<BN>(e, p.M, p.N, 1, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, sq);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_even(smem_u32(&acc_empty[acc]));
+            epi_rowpart(e, p.M, row_base, tn, lane, sq);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // both CTAs are done with both TMEMs and no multicast arrival is in flight
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+int g_tc2_state = -1;
+int g_sms = 148;
+
+int init_tc2() {
+    if (g_tc2_state >= 0) return g_tc2_state;
+    g_tc2_state = 0;
+    if (!tc_available()) return 0;
+    const char* env = getenv("MMAD_NO_PAIR");
+    if (env && env[0] == '1') return 0;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    g_sms = prop.multiProcessorCount;
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<3>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    g_tc2_state = 1;
+    return 1;
+}
+
+}  // namespace
+
+int tc2_available() { return init_tc2(); }
+
+// A maps: box 64 x 128 (rows of A).  B maps: box 64 x 128 (HALF of the 256-wide tile; tc_make_operand_map(.., 128)).
+int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s) {
+    if (!init_tc2()) { set_error("cta_group::2 GEMM unavailable"); return MMAD_E_UNSUPPORTED; }
+    if (M <= 0 || N <= 0) return MMAD_OK;
+    if (A.mn || B.mn || e.plain) { set_error("gemm_tc2: K-major operands and the fused epilogue only"); return MMAD_E_ARG; }
+    auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
+    if (!al(e.Y, e.ldy, 4) || !al(e.pre, e.ldpre, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) ||
+        !al(e.dout, e.lddout, 4) || !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (e.y_cols % 4) || (e.d_cols % 4)) {
+        set_error("gemm_tc2: epilogue buffers must be 16-byte aligned with padded leading dimensions");
+        return MMAD_E_ARG;
+    }
+    Tc2Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + 255) / 256;
+    p.tiles_n = (N + BN2 - 1) / BN2;
+    p.tri = e.b_upper_tri ? 1 : 0;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int max_pairs = g_sms / 2;
+    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+    if (passes == 3)
+        gemm_tc2_kernel<3><<<grid, NTHREADS, Cfg2<3>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.lo, p, e);
+    else
+        gemm_tc2_kernel<1><<<grid, NTHREADS, Cfg2<1>::kSmemBytes, s>>>(A.hi, A.hi, B.hi, B.hi, p, e);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+}  // namespace mmad

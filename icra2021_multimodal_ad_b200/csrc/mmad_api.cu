@@ -32,7 +32,8 @@ struct Layer {
     __half* Wh = nullptr;     // [N, Kp] fp16 hi of W * wscale
     __half* Wl = nullptr;     // [N, Kp] fp16 lo
     float wscale = 1.f;
-    TcOperand tcB;
+    TcOperand tcB;            // box 64 x 256: one CTA per 128 x 256 tile
+    TcOperand tcB2;           // box 64 x 128: CTA pairs, each CTA stages half of the tile's weight rows
     bool tc_ready = false;
 };
 
@@ -47,7 +48,7 @@ struct NapFit {
     bool upper_tri = false;     // rows are an upper-triangular whitening factor (mmad_nap_set_structure)
     __half* Bh = nullptr;
     __half* Bl = nullptr;
-    TcOperand tcB;
+    TcOperand tcB, tcB2;
     bool tc_ready = false;
 };
 
@@ -83,6 +84,7 @@ namespace mmad {
 
 constexpr int kMaxChunk = 65536;      // rows per device-side chunk (as many as the workspace allows)
 constexpr int kHostChunk = 16384;     // rows per pipelined host->device chunk of mmad_score_host
+constexpr int kPairMinRows = 2048;    // chunks at least this tall run on CTA pairs (gemm_tc2.cu)
 constexpr int kStreamRows = 2048;     // host calls up to this many rows take the graph-replay latency path
 constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
 
@@ -252,7 +254,9 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     if (rc) return rc;
     A.rows = rows; A.k = Lr.K;
     e.acc_scale = 1.f / Lr.wscale;
-    return gemm_tc(A, Lr.tcB, rows, Lr.N, Lr.K, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
+    const int passes = h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1;
+    if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
+    return gemm_tc(A, Lr.tcB, rows, Lr.N, Lr.K, passes, e, s);
 }
 
 // What a chain invocation should produce for one chunk.
@@ -527,8 +531,10 @@ int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const floa
     if (tc_available()) {
         rc = tc_make_operand_map(&L.tcB.hi, L.Wh, L.N, L.K, L.Kp, gemm_tc_tile_n());
         if (!rc) rc = tc_make_operand_map(&L.tcB.lo, L.Wl, L.N, L.K, L.Kp, gemm_tc_tile_n());
+        if (!rc) rc = tc_make_operand_map(&L.tcB2.hi, L.Wh, L.N, L.K, L.Kp, 128);
+        if (!rc) rc = tc_make_operand_map(&L.tcB2.lo, L.Wl, L.N, L.K, L.Kp, 128);
         if (rc) return rc;
-        L.tcB.rows = L.N; L.tcB.k = L.K;
+        L.tcB.rows = L.tcB2.rows = L.N; L.tcB.k = L.tcB2.k = L.K;
         L.tc_ready = true;
     }
     L.loaded = true;
@@ -644,7 +650,9 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         A.rows = rows; A.k = f.Dp;
         e.acc_scale = 1.f / (f.wscale * kDiffScale);
         e.b_upper_tri = f.upper_tri ? 1 : 0;
-        rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1, e, s);
+        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1;
+        if (rows >= kPairMinRows && tc2_available()) rc = gemm_tc2(A, f.tcB2, rows, f.K, f.Dp, passes, e, s);
+        else rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, passes, e, s);
     }
     if (rc || !d_nap) return rc;
     return finalize_sum((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[L + 1], p.slot_off[L + 2], 1.f / f.K,
@@ -789,8 +797,10 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
     if (tc_available()) {
         rc = tc_make_operand_map(&f.tcB.hi, f.Bh, K, f.Dp, f.Dp, gemm_tc_tile_n());
         if (!rc) rc = tc_make_operand_map(&f.tcB.lo, f.Bl, K, f.Dp, f.Dp, gemm_tc_tile_n());
+        if (!rc) rc = tc_make_operand_map(&f.tcB2.hi, f.Bh, K, f.Dp, f.Dp, 128);
+        if (!rc) rc = tc_make_operand_map(&f.tcB2.lo, f.Bl, K, f.Dp, f.Dp, 128);
         if (rc) return rc;
-        f.tcB.rows = K; f.tcB.k = f.Dp;
+        f.tcB.rows = f.tcB2.rows = K; f.tcB.k = f.tcB2.k = f.Dp;
         f.tc_ready = true;
     }
     f.ready = true;

@@ -172,3 +172,29 @@ def test_tensor_core_gemm_tile_edges():
             assert _rel_max(b["diffs"], a["diffs"]) < 2e-5, (D, n)
             np.testing.assert_allclose(b["sap"], a["sap"], rtol=5e-5)
             np.testing.assert_allclose(b["base"], a["base"], rtol=5e-5)
+
+
+@pytest.mark.parametrize("D,btl,nl,n", [(1728, 100, 5, 2048 + 300), (300, 17, 2, 4096 + 129), (93, 10, 3, 2500)])
+def test_cta_pair_kernel_matches_fp32_on_tall_chunks(D, btl, nl, n):
+    """Chunks of >= 2048 rows run on the cta_group::2 kernel (gemm_tc2.cu): 256-row pair tiles with a ragged last
+    tile (n not a multiple of 256 nor 128), partial N tiles, and the triangular NAP factor, against the fp32
+    CUDA-core kernel on the same rows."""
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    sd = synth_state_dict(D, btl, nl, 77)
+    x, _ = synth_windows(n, D, 5)
+    xtr, _ = synth_windows(max(2 * D, 700), D, 6, anomaly_rate=0.0)
+    outs = {}
+    for prec in ("fp32", "f16x3"):
+        m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=prec)).eval()
+        m.load_state_dict(sd)
+        eng = m.engine()
+        eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+        o = eng.score(x.cuda(), 0, 1, nap=True, diffs=True)
+        o2 = eng.score(x.cuda(), 0, nl + 1)
+        outs[prec] = {k: v.cpu().numpy() for k, v in o.items()}
+        outs[prec]["sap_all"] = o2["sap"].cpu().numpy()
+    a, b = outs["fp32"], outs["f16x3"]
+    assert _rel_max(b["diffs"], a["diffs"]) < 2e-5
+    np.testing.assert_allclose(b["sap_all"], a["sap_all"], rtol=5e-5)
+    np.testing.assert_allclose(b["base"], a["base"], rtol=5e-5)
+    np.testing.assert_allclose(b["nap"], a["nap"], rtol=1e-3)
