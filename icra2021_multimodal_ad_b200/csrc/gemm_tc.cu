@@ -50,8 +50,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     float* s_bias = s_mul + BN;
     float* s_sc = s_bias + BN;
     float* s_sh = s_sc + BN;
-    float* s_stage = s_sh + BN;                  // 4 warps x [32][STG_LD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * STG_LD);
+    float4* s_stage = reinterpret_cast<float4*>(s_sh + BN);      // 8 warps x 32 x 16 floats, XOR swizzled
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + EPI_WARPS * STG_FLOAT4);
     uint64_t* full = bars;                       // [kStages]  TMA -> MMA
     uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> TMA
     uint64_t* acc_full = empty + C::kStages;     // [2]        MMA -> epilogue
@@ -65,7 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
         if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
@@ -162,33 +162,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
-        // TMEM hands each thread one accumulator ROW (32 columns per tcgen05.ld).  Row-per-thread
-        // global accesses would touch 32 different rows per instruction, so every 32x32 chunk is
-        // transposed through a warp-private smem tile and re-read as (4 rows x 8 float4 columns)
-        // per instruction: every global load/store of a warp then covers whole 128-byte row segments.
+        // ================= epilogue (warps 2..9) =================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int et = threadIdx.x - 64;        // 0..127
-        float* stg = s_stage + q * (32 * STG_LD);
+        const int half = (warp - 2) >> 2;       // column half of the tile this warp drains (BN = 128: half 1 idles)
+        const int et = threadIdx.x - 64;        // 0..255
+        float4* stg = s_stage + (warp - 2) * STG_FLOAT4;
+        const int col_lo = BN == 256 ? half * 128 : 0;
+        const int col_hi = BN == 256 ? col_lo + 128 : (half == 0 ? 128 : 0);
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
             const int t = w / p.splits, sp = w % p.splits;
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
             // stage the per-column epilogue vectors of this tile
-            asm volatile("bar.sync 1, 128;");
+            asm volatile("bar.sync 1, 256;");
             epi_stage_vectors<BN>(e, p.N, n0, sp, et, s_mul, s_bias, s_sc, s_sh);
-            asm volatile("bar.sync 1, 128;");
+            asm volatile("bar.sync 1, 256;");
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            float sq[8];
-            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, sq);
+            float sq[4];
+            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc]));
-            epi_rowpart(e, p.M, row_base, tn, lane, sq);
+            if (col_hi > col_lo && n0 + col_lo < p.N) epi_rowpart(e, p.M, row_base, (n0 + col_lo) / ROWPART_COLS, lane, sq);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -248,6 +247,7 @@ int init_tc() {
 
 int tc_available() { return init_tc(); }
 int gemm_tc_tile_n() { return BN_MAX; }
+int gemm_tc_rowpart_cols() { return ROWPART_COLS; }
 
 // Tile width for an M x N problem: 256 unless that leaves SMs idle, then 128 (twice the CTAs, deeper pipeline).
 int gemm_tc_pick_bn(int M, int N) {

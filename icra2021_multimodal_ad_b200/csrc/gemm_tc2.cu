@@ -16,7 +16,7 @@
 //                loads complete on it (cta_group::2 loads address the even CTA's barrier)
 //   empty[s]     in each CTA: tcgen05.commit.multicast from the MMA thread frees the stage in both CTAs
 //   acc_full[a]  in each CTA: commit.multicast after the last k-block
-//   acc_empty[a] in the EVEN CTA: 8 arrivals (4 epilogue warps x 2 CTAs; the odd CTA arrives remotely)
+//   acc_empty[a] in the EVEN CTA: 16 arrivals (8 epilogue warps x 2 CTAs; the odd CTA arrives remotely)
 #include <stdlib.h>
 
 #include "gemm_tc_common.cuh"
@@ -36,7 +36,7 @@ template <int PASSES> struct Cfg2 {
     static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_HALF_BYTES);        // 64 KB / 32 KB per CTA
     static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 3 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kSmemTiles + 4 * BN2 * 4 + 4 * 32 * STG_LD * 4 + 256 + 1024;
+    static constexpr int kSmemBytes = kSmemTiles + 4 * BN2 * 4 + EPI_WARPS * STG_FLOAT4 * 16 + 256 + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -91,8 +91,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     float* s_bias = s_mul + BN;
     float* s_sc = s_bias + BN;
     float* s_sh = s_sc + BN;
-    float* s_stage = s_sh + BN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * STG_LD);
+    float4* s_stage = reinterpret_cast<float4*>(s_sh + BN);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + EPI_WARPS * STG_FLOAT4);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::kStages;
     uint64_t* acc_full = empty + C::kStages;
@@ -107,7 +107,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 2 * EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
         if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
@@ -189,26 +189,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             }
         }
     } else {
-        // ================= epilogue (warps 2..5 of both CTAs): this CTA's 128 accumulator rows =================
+        // ================= epilogue (warps 2..9 of both CTAs): this CTA's 128 accumulator rows =================
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;       // column half of the tile this warp drains
         const int et = threadIdx.x - 64;
-        float* stg = s_stage + q * (32 * STG_LD);
+        float4* stg = s_stage + (warp - 2) * STG_FLOAT4;
+        const int col_lo = half * 128, col_hi = col_lo + 128;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = pair; t < num_tiles; t += npairs) {
             const int m0 = (t / p.tiles_n) * 256 + (int)rank * BM, tn = t % p.tiles_n, n0 = tn * BN;
-            asm volatile("bar.sync 1, 128;");
+            asm volatile("bar.sync 1, 256;");
             epi_stage_vectors<BN>(e, p.N, n0, 0, et, s_mul, s_bias, s_sc, s_sh);
-            asm volatile("bar.sync 1, 128;");
+            asm volatile("bar.sync 1, 256;");
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            float sq[8];
-            epi_tile<BN>(e, p.M, p.N, 1, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, sq);
+            float sq[4];
+            epi_tile<BN>(e, p.M, p.N, 1, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even(smem_u32(&acc_empty[acc]));
-            epi_rowpart(e, p.M, row_base, tn, lane, sq);
+            if (n0 + col_lo < p.N) epi_rowpart(e, p.M, row_base, (n0 + col_lo) / ROWPART_COLS, lane, sq);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

@@ -6,13 +6,16 @@
 namespace mmad {
 namespace tc {
 
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int STG_FLOAT4 = 32 * 4;          // float4 slots of one warp's transpose tile (32 rows x 16 columns)
+constexpr int ROWPART_COLS = 128;           // columns covered by one row-partial slot
 constexpr int BM = 128;
 constexpr int BN_MAX = 256;            // CTA tile is 128 x BN with BN = 256 (throughput) or 128 (under-filled grids)
 constexpr int BK = 64;                 // halfs per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 64 + 256;          // TMA warp, MMA warp, eight epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int STG_LD = 36;                  // floats per row of an epilogue transpose tile (conflict-free float4)
 
 template <int PASSES, int BN> struct Cfg {
     static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
@@ -21,7 +24,7 @@ template <int PASSES, int BN> struct Cfg {
     static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 2 / 3 / 4 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;   // <= 192 KB
     static constexpr int kTmemCols = 2 * BN;                   // two fp32 accumulators
-    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + 4 * 32 * STG_LD * 4 /*transpose tiles*/ +
+    static constexpr int kSmemBytes = kSmemTiles + 4 * BN * 4 /*epilogue vectors*/ + EPI_WARPS * STG_FLOAT4 * 16 /*transpose tiles*/ +
                                       256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -115,7 +118,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int BN>
 __device__ __forceinline__ void epi_stage_vectors(const Epilogue& e, int N, int n0, int sp, int et, float* s_mul, float* s_bias,
                                                   float* s_sc, float* s_sh) {
-    for (int c = et; c < BN; c += 128) {
+    for (int c = et; c < BN; c += EPI_THREADS) {
         const int gc = n0 + c;
         const bool ok = gc < N;
         s_mul[c] = e.acc_scale * ((e.col_scale && ok) ? e.col_scale[gc] : 1.f);
@@ -125,72 +128,85 @@ __device__ __forceinline__ void epi_stage_vectors(const Epilogue& e, int N, int 
     }
 }
 
-// One epilogue warp drains its 32 accumulator rows (TMEM lanes) of a tile: row_base = first global row,
-// taddr = TMEM address of (lane quarter, first column).  TMEM hands each thread one accumulator ROW, so every
-// 32x32 chunk is transposed through the warp-private tile `stg` and re-read as (4 rows x 8 float4 columns):
-// every global access of the warp then covers whole 128-byte row segments.  sq[it] returns this lane's partial
-// row sums of squares (rows row_base + it*4 + lane/8).
+// Eight epilogue warps per CTA: warps 2-5 drain columns [0, 128) of a tile, warps 6-9 columns [128, 256); warp w may
+// only touch TMEM lanes 32*(w%4).., so each lane quarter has one warp per column half.  (With four warps -- one per
+// scheduler -- the epilogue is ALU-latency bound and paces the diff layers; two per scheduler hide each other.)
+// A warp works in 32-row x 16-column pieces: tcgen05.ld hands each thread one accumulator ROW (16 columns), the
+// piece is transposed through a 2 KB XOR-swizzled shared tile and re-read as (8 rows x 4 float4 columns), so every
+// global access of the warp covers whole 64-byte (fp32) / 32-byte (fp16) row segments.
+// sq[it] returns this lane's partial row sums of squares for rows row_base + it*8 + lane/4.
+
+__device__ __forceinline__ int stg_slot(int row, int j) { return row * 4 + (j ^ ((row >> 1) & 3)); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int BN>
 __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
-                                         float* stg, const float* s_mul, const float* s_bias, const float* s_sc,
-                                         const float* s_sh, int lane, float (&sq)[8]) {
-    const int rsub = lane >> 3;             // 0..3  row inside a group of 4
-    const int c4 = (lane & 7) * 4;          // first of this lane's 4 columns inside the 32-column chunk
+                                         float4* stg, const float* s_mul, const float* s_bias, const float* s_sc,
+                                         const float* s_sh, int lane, int col_lo, int col_hi, float (&sq)[4]) {
+    const int rsub = lane >> 2;             // 0..7  row inside a group of 8
+    const int cg = lane & 3;                // float4 column group inside the 16-column piece
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sq[i] = 0.f;
+    for (int i = 0; i < 4; ++i) sq[i] = 0.f;
     int n_cols = N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
     int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
     int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
-    const int c_end = (max(max(n_cols, w_cols), dw_cols) + 31) & ~31;
-    for (int c0 = 0; c0 < c_end && c0 < BN; c0 += 32) {
-        // issue this chunk's reference loads first: 8 independent 16-byte loads per lane in
-        // flight while the accumulator chunk is fetched from TMEM and transposed
-        float4 rf[8];
+    int c_end = (max(max(n_cols, w_cols), dw_cols) + 15) & ~15;
+    if (c_end > col_hi) c_end = col_hi;
+    for (int c0 = col_lo; c0 < c_end; c0 += 16) {
+        const int cc = c0 + cg * 4;             // tile-local column of this lane's float4
+        // issue this piece's reference loads first: 4 independent 16-byte loads per lane in flight while the
+        // accumulator piece is fetched from TMEM and transposed
+        float4 rf[4];
         if (e.ref) {
-            const int ccp = c0 + c4;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = row_base + it * 4 + rsub;
+            for (int it = 0; it < 4; ++it) {
+                const int r = row_base + it * 8 + rsub;
                 rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < M && ccp + 3 < n_cols)
-                    rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + ccp));
+                if (r < M && cc + 3 < n_cols)
+                    rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + cc));
             }
         }
         {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            float4* wr = reinterpret_cast<float4*>(stg + lane * STG_LD);
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                wr[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+                stg[stg_slot(lane, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
         __syncwarp();
         if (e.plain) {
             // plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]):
-            // lane <-> column, one coalesced 128-byte row segment per instruction
-            const int c = c0 + lane;
+            // half-warp <-> one row, lane <-> column: two coalesced 64-byte row segments per instruction
+            const int c = c0 + (lane & 15);
             const int gc = n0 + c;
+            const int rpar = lane >> 4;
             if (gc < N) {
                 const float mulc = s_mul[c], biac = s_bias[c];
-                if (splits > 1) {     // split-K: partial products accumulate into the zeroed output
-#pragma unroll 8
-                    for (int rl = 0; rl < 32; ++rl) {
-                        const int r = row_base + rl;
-                        if (r < M) atomicAdd(e.Y + (size_t)r * e.ldy + gc, fmaf(stg[rl * STG_LD + lane], mulc, biac));
-                    }
-                } else {
-#pragma unroll 8
-                    for (int rl = 0; rl < 32; ++rl) {
-                        const int r = row_base + rl;
-                        if (r < M) e.Y[(size_t)r * e.ldy + gc] = fmaf(stg[rl * STG_LD + lane], mulc, biac);
+                const float* stf = reinterpret_cast<const float*>(stg);
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int rl = i * 2 + rpar;
+                    const int r = row_base + rl;
+                    const float val = fmaf(stf[stg_slot(rl, (lane & 15) >> 2) * 4 + (lane & 3)], mulc, biac);
+                    if (r < M) {
+                        if (splits > 1) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);   // split-K partial sums
+                        else e.Y[(size_t)r * e.ldy + gc] = val;
                     }
                 }
             }
             __syncwarp();
             continue;
         }
-        const int cc = c0 + c4;                 // tile-local column of this lane's float4
         const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
         const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
         const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc);
@@ -199,10 +215,10 @@ __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int sp
         const bool wy = cc < w_cols, wd = cc < dw_cols;   // widths are multiples of 4 (padded to 64)
         const size_t gcol = (size_t)n0 + cc;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + rsub;
+        for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + rsub;
             const int r = row_base + rl;
-            const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c4);
+            const float4 a = stg[stg_slot(rl, cg)];
             float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
             float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
             if (r < M) {
@@ -261,22 +277,21 @@ __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int sp
                 }
             }
         }
-        __syncwarp();     // the staging tile is rewritten by the next chunk
+        __syncwarp();     // the staging tile is rewritten by the next piece
     }
 }
 
-__device__ __forceinline__ void epi_rowpart(const Epilogue& e, int M, int row_base, int tn, int lane, const float (&sq)[8]) {
-    const int rsub = lane >> 3;
-    if (e.rowpart) {
+// row partial sums of squares of this warp's column half: slot = 128-column block index
+__device__ __forceinline__ void epi_rowpart(const Epilogue& e, int M, int row_base, int slot, int lane, const float (&sq)[4]) {
+    if (!e.rowpart) return;
+    const int rsub = lane >> 2;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            float v = sq[it];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            const int r = row_base + it * 4 + rsub;
-            if ((lane & 7) == 0 && r < M) e.rowpart[(size_t)tn * e.rowpart_stride + r] = v;
-        }
+    for (int it = 0; it < 4; ++it) {
+        float v = sq[it];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int r = row_base + it * 8 + rsub;
+        if ((lane & 3) == 0 && r < M) e.rowpart[(size_t)slot * e.rowpart_stride + r] = v;
     }
 }
 

@@ -151,7 +151,7 @@ struct PlanOpts {
 };
 
 static int tile_n_for(mmad_t h) {
-    return h->desc.precision == MMAD_PREC_FP32 ? gemm_simt_tile_n() : gemm_tc_tile_n();
+    return h->desc.precision == MMAD_PREC_FP32 ? gemm_simt_tile_n() : gemm_tc_rowpart_cols();
 }
 
 static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {

@@ -101,6 +101,7 @@ int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, 
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
             const Epilogue& e, cudaStream_t s, int bn = 256);   // bn: CTA tile width; K-major B maps need box_rows == bn
 int gemm_tc_tile_n();                    // the default (256)
+int gemm_tc_rowpart_cols();              // columns per row-partial slot written by the tensor-core epilogues (128)
 int gemm_tc_pick_bn(int M, int N);
 // CTA-pair (cta_group::2) kernel for bulk scoring (gemm_tc2.cu): K-major operands, fused epilogue;
 // B maps with box_rows == 128 (each CTA of the pair stages half of the 256-wide tile)

@@ -470,7 +470,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                        bool b_mn, int M, int N, int K, const Epilogue& e) -> int {
         TcOperand A, Bo;
         int rc;
-        const int bn = e.rowpart ? gemm_tc_tile_n() : gemm_tc_pick_bn(M, N);   // loss partials are indexed by 256-wide tiles
+        const int bn = gemm_tc_pick_bn(M, N);
         if (a_mn) { rc = tc_make_operand_map(&A.hi, Ah, K, M, lda, 64); if (!rc) rc = tc_make_operand_map(&A.lo, Al, K, M, lda, 64); }
         else { rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128); if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128); }
         if (rc) return rc;
@@ -497,7 +497,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             }
         }
     }
-    const int loss_tile_n = tc ? gemm_tc_tile_n() : gemm_simt_tile_n();
+    const int loss_tile_n = tc ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
