@@ -38,7 +38,8 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="mmad", choices=["mmad", "reference"])
-    p.add_argument("--batch", type=int, default=65536, help="windows per rank per step")
+    p.add_argument("--batch", type=int, default=4 * 148 * 128,
+                   help="windows per rank per step (default 75 776 = four waves of 148 SMs x 128-row tiles)")
     p.add_argument("--precision", default=os.environ.get("MMAD_BENCH_PRECISION", "auto"))
     p.add_argument("--no-nap", action="store_true")
     p.add_argument("--cpu-sample", type=int, default=4096)

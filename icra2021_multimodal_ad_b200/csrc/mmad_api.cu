@@ -82,8 +82,20 @@ struct mmad_handle {
 
 namespace mmad {
 
-constexpr int kMaxChunk = 65536;      // rows per device-side chunk (as many as the workspace allows)
-constexpr int kHostChunk = 16384;     // rows per pipelined host->device chunk of mmad_score_host
+// Chunk heights are whole waves: one wave of 128-row tiles (or 64 pair tiles of 256 rows) over all SMs is
+// n_sm * 128 rows (18 944 on a 148-SM B200), so every layer's tile count is a multiple of the grid.
+static int wave_rows() {
+    static int v = 0;
+    if (!v) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaGetLastError();
+        v = (sms > 0 ? sms : 148) * 128;
+    }
+    return v;
+}
+static int max_chunk() { return 4 * wave_rows(); }     // rows per device-side chunk (as many as the workspace allows)
+static int host_chunk() { return wave_rows(); }        // rows per pipelined host->device chunk of mmad_score_host
 constexpr int kPairMinRows = 2048;    // chunks at least this tall run on CTA pairs (gemm_tc2.cu)
 constexpr int kStreamRows = 2048;     // host calls up to this many rows take the graph-replay latency path
 constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
@@ -200,7 +212,7 @@ static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
 }
 
 static int pick_chunk(mmad_t h, int n, size_t ws_bytes, const PlanOpts& o, Plan* out) {
-    int R = std::min(std::max(n, 1), kMaxChunk);
+    int R = std::min(std::max(n, 1), max_chunk());
     R = round_up(R, 128);
     while (true) {
         Plan p = make_plan(h, R, o);
@@ -560,7 +572,7 @@ size_t mmad_workspace_bytes(mmad_t h, int max_rows) {
     if (!h || max_rows < 1) return 0;
     PlanOpts o;
     o.lo = 0; o.hi = h->desc.n_enc + 1; o.diffs_ws = true; o.tc = h->desc.precision != MMAD_PREC_FP32 || tc_available();
-    int R = round_up(std::min(max_rows, kMaxChunk), 128);
+    int R = round_up(std::min(max_rows, max_chunk()), 128);
     return make_plan(h, R, o).total;
 }
 
@@ -869,7 +881,7 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         return MMAD_E_STATE;
     }
     const int D = D_of(h);
-    const int chunk = (int)std::min<long long>(kHostChunk, std::max<long long>(128, (n + 127) / 128 * 128));
+    const int chunk = (int)std::min<long long>(host_chunk(), std::max<long long>(128, (n + 127) / 128 * 128));
     if (!h->s_copy) {
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));

@@ -99,7 +99,7 @@ class Engine:
 
     # ---- workspace ---------------------------------------------------------------------
     def workspace(self, rows: int) -> torch.Tensor:
-        rows = max(128, min(int(rows), 65536))
+        rows = max(128, min(int(rows), 4 * 148 * 128))
         if self._ws is None or rows > self._ws_rows:
             nbytes = lib().mmad_workspace_bytes(self._h, rows)
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
