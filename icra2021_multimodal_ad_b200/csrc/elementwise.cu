@@ -116,6 +116,24 @@ __global__ void finalize_scores_kernel(const float* __restrict__ part, int strid
     }
 }
 
+// same sums for a handful of rows and many slots (streaming calls: one 16-column slot per CTA of the skinny GEMM):
+// one warp per row, lanes stride over the slots, fixed-order shuffle reduction -> deterministic
+__global__ void finalize_scores_warp_kernel(const float* __restrict__ part, int stride, int n, int b_lo, int b_hi,
+                                            int s_lo, int s_hi, float inv_base, float inv_sap, float* __restrict__ base,
+                                            float* __restrict__ sap) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (r >= n) return;
+    float a = 0.f, b = 0.f;
+    if (base) for (int s = b_lo + lane; s < b_hi; s += 32) a += part[(size_t)s * stride + r];
+    if (sap) for (int s = s_lo + lane; s < s_hi; s += 32) b += part[(size_t)s * stride + r];
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) {
+        if (base) base[r] = a * inv_base;
+        if (sap) sap[r] = b * inv_sap;
+    }
+}
+
 __global__ void reduce_sum_all_kernel(const float* __restrict__ part, int stride, int n, int s_lo, int s_hi,
                                       float* __restrict__ acc) {
     // double accumulation inside the block, one atomic per block
@@ -316,8 +334,12 @@ int copy_pad_vec(const float* src, int N, int Np, float* dst, cudaStream_t s) {
 int finalize_scores(const float* rowpart, int stride, int n, int b_lo, int b_hi, int s_lo, int s_hi, float inv_base,
                     float inv_sap, float* base, float* sap, cudaStream_t s) {
     if (n <= 0) return MMAD_OK;
-    finalize_scores_kernel<<<(n + 255) / 256, 256, 0, s>>>(rowpart, stride, n, b_lo, b_hi, s_lo, s_hi, inv_base,
-                                                           inv_sap, base, sap);
+    if (n <= 64)
+        finalize_scores_warp_kernel<<<(n + 7) / 8, 256, 0, s>>>(rowpart, stride, n, b_lo, b_hi, s_lo, s_hi, inv_base, inv_sap,
+                                                                base, sap);
+    else
+        finalize_scores_kernel<<<(n + 255) / 256, 256, 0, s>>>(rowpart, stride, n, b_lo, b_hi, s_lo, s_hi, inv_base,
+                                                               inv_sap, base, sap);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

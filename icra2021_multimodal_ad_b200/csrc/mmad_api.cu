@@ -78,6 +78,9 @@ struct mmad_handle {
     struct GraphRec { std::string key; cudaGraphExec_t exec; unsigned long long launches; };
     std::vector<GraphRec> graphs;
     cudaStream_t s_capture = nullptr;
+    // set for the duration of a call of <= 64 rows: exact-fp32 weight-streaming kernels (gemm_skinny.cu) instead
+    // of 128-row tensor-core tiles, whatever the handle's precision mode
+    bool skinny = false;
 };
 
 namespace mmad {
@@ -162,8 +165,11 @@ struct PlanOpts {
     bool tc = false;
 };
 
+static bool use_tc(mmad_t h) { return h->desc.precision != MMAD_PREC_FP32 && !h->skinny; }
+
 static int tile_n_for(mmad_t h) {
-    return h->desc.precision == MMAD_PREC_FP32 ? gemm_simt_tile_n() : gemm_tc_rowpart_cols();
+    if (h->skinny) return gemm_skinny_tile_n();
+    return use_tc(h) ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
 }
 
 static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
@@ -250,12 +256,13 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     e.bias = Lr.bias;
     if (Lr.has_bn) { e.bn_scale = Lr.scale; e.bn_shift = Lr.shift; }
     e.slope = h->desc.lrelu_slope;
-    if (h->desc.precision == MMAD_PREC_FP32) {
+    if (!use_tc(h)) {
         GemmShape g;
         g.M = rows; g.N = Lr.N; g.K = Lr.K;
         g.A = in.f; g.lda = in.ld;
         g.B = Lr.W; g.ldb = Lr.Kp;
         e.acc_scale = 1.f;
+        if (h->skinny) return gemm_skinny(g, e, s);
         return gemm_simt(g, e, s);
     }
     // tensor-core path: TMA descriptors over the fp16 hi/lo twins
@@ -286,7 +293,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
                      cudaStream_t s) {
     const int L = h->desc.n_enc, Ld = h->desc.n_dec, D = D_of(h);
     const int Dp = round_up(D, kPad);
-    const bool tc = h->desc.precision != MMAD_PREC_FP32;
+    const bool tc = use_tc(h);
     const bool x_aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const bool x_direct = !tc && x_aligned;
     Act a0;
@@ -648,12 +655,12 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         e.Y = (float*)(ws + p.rot); e.ldy = round_up(f.K, kPad); e.y_cols = e.ldy;
     }
     int rc;
-    if (h->desc.precision == MMAD_PREC_FP32) {
+    if (!use_tc(h)) {
         GemmShape g;
         g.M = rows; g.N = f.K; g.K = f.Dp;
         g.A = (const float*)(ws + p.diffs); g.lda = p.Dselp;
         g.B = f.B; g.ldb = f.Dp;
-        rc = gemm_simt(g, e, s);
+        rc = h->skinny ? gemm_skinny(g, e, s) : gemm_simt(g, e, s);
     } else {
         TcOperand A;
         rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.Dp, p.Dselp, 128);
@@ -671,10 +678,23 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
                         d_nap, s);
 }
 
+static int score_impl(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float* d_nap,
+                      float* d_diffs, void* d_ws, size_t ws_bytes, void* stream);
+
 int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float* d_nap,
                float* d_diffs, void* d_ws, size_t ws_bytes, void* stream) {
     int rc = check_ready(h);
     if (rc) return rc;
+    // <= 64 rows (the realtime caller): exact-fp32 weight-streaming kernels on all SMs instead of one 128-row tile
+    h->skinny = n > 0 && n <= gemm_skinny_max_rows() && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0);
+    rc = score_impl(h, d_x, ldx, n, lo, hi, d_base, d_sap, d_nap, d_diffs, d_ws, ws_bytes, stream);
+    h->skinny = false;
+    return rc;
+}
+
+static int score_impl(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float* d_nap,
+                      float* d_diffs, void* d_ws, size_t ws_bytes, void* stream) {
+    int rc;
     if ((rc = check_range(h, lo, hi))) return rc;
     if (n == 0) return MMAD_OK;
     if (n < 0 || !d_x || ldx < D_of(h)) { set_error("bad input"); return MMAD_E_ARG; }
@@ -683,7 +703,7 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
         return MMAD_E_STATE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const bool tc = h->desc.precision != MMAD_PREC_FP32;
+    const bool tc = use_tc(h);
     PlanOpts o;
     o.lo = lo; o.hi = hi; o.tc = tc; o.diffs_ws = d_nap != nullptr || d_diffs != nullptr;
     const int Dsel = concat_width(h, lo, hi);

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -89,6 +90,12 @@ __host__ __device__ inline int seg_pad_col(const SegMap& m, int c) {
 // CUDA-core fp32 GEMM with the fused epilogue (gemm_simt.cu)
 int gemm_simt(const GemmShape& g, const Epilogue& e, cudaStream_t s);
 int gemm_simt_tile_n();   // columns covered by one rowpart slot
+
+// weight-streaming fp32 GEMM for <= 64 rows (gemm_skinny.cu): one 16-column row-partial slot per CTA
+int gemm_skinny(const GemmShape& g, const Epilogue& e, cudaStream_t s);
+bool gemm_skinny_ok(const GemmShape& g, const Epilogue& e);
+int gemm_skinny_max_rows();
+int gemm_skinny_tile_n();
 
 // tcgen05 GEMM (gemm_tc.cu): operands are fp16 hi/lo pairs described by TMA maps.
 struct TcOperand {

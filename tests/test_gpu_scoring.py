@@ -77,7 +77,7 @@ def test_against_oracle_ragged_and_edges(precision):
     out = eng.score(torch.empty(0, D, device="cuda"), 0, nl + 1)
     assert out["sap"].numel() == 0
     # strided rows (a column slice of a wider matrix)
-    wide = torch.rand(50, D + 7, device="cuda")
+    wide = torch.rand(100, D + 7, device="cuda")      # > 64 rows: both calls take the same kernel family
     o1 = eng.score(wide[:, :D], 0, nl + 1)["sap"]
     o2 = eng.score(wide[:, :D].contiguous(), 0, nl + 1)["sap"]
     assert torch.equal(o1, o2)
@@ -198,3 +198,38 @@ def test_cta_pair_kernel_matches_fp32_on_tall_chunks(D, btl, nl, n):
     np.testing.assert_allclose(b["sap_all"], a["sap_all"], rtol=5e-5)
     np.testing.assert_allclose(b["base"], a["base"], rtol=5e-5)
     np.testing.assert_allclose(b["nap"], a["nap"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("n", [1, 8, 10, 33, 64])
+def test_streaming_batches_take_the_fp32_weight_streaming_path(n, precision):
+    """realtime_tester-style calls (test_file/realtime_tester.py:291-309): up to 32 windows run on the exact-fp32
+    weight-streaming kernels whatever the handle's precision (33 and 64 rows: tensor-core kernels, graph replay);
+    device and host entry points, base/SAP/NAP and diffs against the oracle."""
+    from oracle import rapp_oracle as RO
+    D, btl, nl, seed = 1728, 100, 5, 31
+    sd = synth_state_dict(D, btl, nl, seed)
+    m = _model(D, btl, nl, seed, precision)
+    eng = m.engine()
+    xtr, _ = synth_windows(2000, D, seed + 1, anomaly_rate=0.0)
+    eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+    x, _ = synth_windows(n, D, 100 + n)
+    ref = RO.get_diffs(x, sd)
+    o = eng.score(x.cuda(), 0, nl + 1, diffs=True)
+    got = o["diffs"].cpu().numpy()
+    off = 0
+    tol = 1e-5 if n <= 32 else 2e-5
+    for d in ref:
+        assert _rel_max(got[:, off:off + d.shape[1]], d) < tol
+        off += d.shape[1]
+    np.testing.assert_allclose(o["sap"].cpu().numpy(), RO.sap_score(ref), rtol=5 * tol)
+    np.testing.assert_allclose(o["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=5 * tol)
+    big, _ = synth_windows(300, D, 100 + n)          # same first rows through the tensor-core path
+    big[:n] = x
+    nap_small = eng.score(x.cuda(), 0, 1, base=False, sap=False, nap=True)["nap"].cpu().numpy()
+    nap_big = eng.score(big.cuda(), 0, 1, base=False, sap=False, nap=True)["nap"].cpu().numpy()[:n]
+    np.testing.assert_allclose(nap_small, nap_big, rtol=1e-3)
+    h = eng.score_host(x.numpy(), 0, nl + 1, base=True, sap=True, nap=False)
+    np.testing.assert_allclose(h["sap"], o["sap"].cpu().numpy(), rtol=1e-6)
+    h2 = eng.score_host(x.numpy(), 0, nl + 1, base=True, sap=True, nap=False)      # graph replay
+    np.testing.assert_array_equal(h2["sap"], h["sap"])
