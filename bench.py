@@ -155,8 +155,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "anomaly-scored samples/sec (SAP+NAP)", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, "cpu"),
-            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+            "config": workload_config(args, os.environ.get("MMAD_DEFAULT_PRECISION", "f16x3") if args.precision == "auto" else args.precision),
+            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "arithmetic": "fp32 (torch CPU)",
                              "sample": f"{n} windows per step, get_diffs(batch 256)+base+SAP" + ("" if args.no_nap else "+NAP score (K=5482 fit)")},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
