@@ -171,7 +171,7 @@ def workload_config(args, precision):
             "parallelism": f"sample-sharded x{args.gpus}, no data-path collective"}
 
 
-def bench_train(dev, local, world, batch, steps, warmup, precision):
+def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
     """AE train samples/s (BASELINE metric, second half): AutoEncoder.step (models/auto_encoder.py:57-77) =
     train-mode forward + backward + Adam, one call per step, loss read back to the host every step like the
     reference.  Data parallel at world > 1: BatchNorm statistics and the flat gradient are all-reduced."""
@@ -182,9 +182,9 @@ def bench_train(dev, local, world, batch, steps, warmup, precision):
     from icra2021_multimodal_ad_b200.models.auto_encoder import AutoEncoder
     from icra2021_multimodal_ad_b200.optim import Adam
     from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
-    cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
+    cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision, vib=vib, beta_kl=1.0)
     model = get_model(cfg)
-    model.load_state_dict(synth_state_dict(D, BTL, NL, 0))
+    model.load_state_dict(synth_state_dict(D, BTL, NL, 0, enc_out=2 * BTL if vib else None))
     opt = Adam(model.parameters(), lr=1e-3)
     if world > 1:
         T.set_data_parallel(model)
@@ -223,7 +223,7 @@ def bench_train(dev, local, world, batch, steps, warmup, precision):
     ms_dev = timed(xd, steps)
     ms_e2e = timed(xh, steps)
     flop = 56366196.0 * batch * world     # fwd + dW + dX per sample
-    return {"metric": "AE train samples/sec", "batch_per_gpu": batch, "value": world * batch / (ms_dev / 1e3),
+    return {"metric": "VIB-AE train samples/sec" if vib else "AE train samples/sec", "batch_per_gpu": batch, "value": world * batch / (ms_dev / 1e3),
             "ms_per_step": ms_dev, "unit": "samples/s", "algorithmic_tflops": flop / (ms_dev / 1e3) / 1e12,
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
                     "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16"}[precision],
@@ -372,6 +372,7 @@ def main():
     if not args.no_extras:
         tsteps = max(3, min(args.steps * 3, 30))
         extras["train"] = bench_train(dev, local, world, args.train_batch, tsteps, 3, precision)
+        extras["train_vib"] = bench_train(dev, local, world, args.train_batch, tsteps, 3, precision, vib=True)   # configs[3]
         if world == 1:
             extras["train_b7000"] = bench_train(dev, local, world, 7000, max(3, tsteps // 3), 2, precision)
             extras["stream_latency"] = bench_stream(eng)

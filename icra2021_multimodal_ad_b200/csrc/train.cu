@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __rest
 // VIB forward (decorators/variational_info_bottleneck.py:19-42, k = 1): enc_out [B, 2h] -> z = eps exp(logvar/2) + mu
 // (zero padded to ldz columns); kl_acc += -1/2 sum (1 + logvar - mu^2 - exp(logvar))
 __global__ void vib_train_fwd_kernel(const float* __restrict__ o, int ldo, int B, int h, const float* __restrict__ eps,
-                                     float* __restrict__ z, int ldz, double* __restrict__ kl_acc) {
+                                     float* __restrict__ z, int ldz, __half* __restrict__ zh, __half* __restrict__ zl,
+                                     double* __restrict__ kl_acc) {
     const size_t total = (size_t)B * ldz;
     double kl = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -289,6 +290,11 @@ __global__ void vib_train_fwd_kernel(const float* __restrict__ o, int ldo, int B
             kl += -0.5 * (1.0 + (double)lv - (double)m * (double)m - exp((double)lv));
         }
         z[i] = v;
+        if (zh) {
+            const __half hh = __float2half_rn(v);
+            zh[i] = hh;
+            zl[i] = __float2half_rn(v - __half2float(hh));
+        }
     }
     __shared__ double sm[256];
     sm[threadIdx.x] = kl;
@@ -302,15 +308,24 @@ __global__ void vib_train_fwd_kernel(const float* __restrict__ o, int ldo, int B
 
 // VIB backward: g_out[:, :h] = g_z + beta mu ;  g_out[:, h:] = g_z eps exp(logvar/2)/2 - beta (1 - exp(logvar))/2
 __global__ void vib_train_bwd_kernel(const float* __restrict__ gz, int ldg, const float* __restrict__ o, int ldo, int B, int h,
-                                     const float* __restrict__ eps, float beta, float* __restrict__ gout, int ldgo) {
+                                     const float* __restrict__ eps, float beta, float* __restrict__ gout, int ldgo,
+                                     __half* __restrict__ gh, __half* __restrict__ gl, float twin_scale) {
     const size_t total = (size_t)B * h;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / h), j = (int)(i % h);
         const float m = o[(size_t)b * ldo + j], lv = o[(size_t)b * ldo + h + j];
         const float g = gz[(size_t)b * ldg + j];
         const float sg = expf(0.5f * lv);
-        gout[(size_t)b * ldgo + j] = fmaf(beta, m, g);
-        gout[(size_t)b * ldgo + h + j] = g * eps[i] * 0.5f * sg - 0.5f * beta * (1.f - expf(lv));
+        const float g_mu = fmaf(beta, m, g);
+        const float g_lv = g * eps[i] * 0.5f * sg - 0.5f * beta * (1.f - expf(lv));
+        gout[(size_t)b * ldgo + j] = g_mu;
+        gout[(size_t)b * ldgo + h + j] = g_lv;
+        if (gh) {
+            const float a = fminf(fmaxf(g_mu * twin_scale, -65504.f), 65504.f), c = fminf(fmaxf(g_lv * twin_scale, -65504.f), 65504.f);
+            const __half ha = __float2half_rn(a), hc = __float2half_rn(c);
+            gh[(size_t)b * ldgo + j] = ha; gl[(size_t)b * ldgo + j] = __float2half_rn(a - __half2float(ha));
+            gh[(size_t)b * ldgo + h + j] = hc; gl[(size_t)b * ldgo + h + j] = __float2half_rn(c - __half2float(hc));
+        }
     }
 }
 
@@ -373,6 +388,7 @@ struct TrainPlan {
     size_t xh = 0, xl = 0, xp = 0;
     size_t outh[2][MMAD_MAX_LAYERS] = {{0}}, outl[2][MMAD_MAX_LAYERS] = {{0}};
     size_t gh[2] = {0, 0}, gl[2] = {0, 0};
+    size_t zh = 0, zl = 0, gench = 0, gencl = 0;   // VIB twins: sampled code, gradient wrt the encoder output
 };
 
 int np_of(int n) { return round_up(n, kPad); }
@@ -424,6 +440,10 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
             }
         }
         for (int i = 0; i < 2; ++i) { p.gh[i] = take((size_t)B * maxNp * 2); p.gl[i] = take((size_t)B * maxNp * 2); }
+        p.zh = take((size_t)B * np_of(d.dec_widths[0]) * 2);
+        p.zl = take((size_t)B * np_of(d.dec_widths[0]) * 2);
+        p.gench = take((size_t)B * np_of(d.enc_widths[d.n_enc]) * 2);
+        p.gencl = take((size_t)B * np_of(d.enc_widths[d.n_enc]) * 2);
     }
     p.total = off;
     return p;
@@ -504,10 +524,12 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
         if (m == 1 && vib) {
             const int hp = np_of(dec_in);
-            vib_train_fwd_kernel<<<ew_grid((size_t)B * hp), 256, 0, s>>>(cur.f, cur.ld, B, dec_in, d_eps, (float*)(ws + p.z), hp,
+            __half* zh = tc ? (__half*)(ws + p.zh) : nullptr;
+            __half* zl = tc ? (__half*)(ws + p.zl) : nullptr;
+            vib_train_fwd_kernel<<<ew_grid((size_t)B * hp), 256, 0, s>>>(cur.f, cur.ld, B, dec_in, d_eps, (float*)(ws + p.z), hp, zh, zl,
                                                                         (double*)(ws + p.kl));
             MMAD_LAUNCHED();
-            cur = Mat{(const float*)(ws + p.z), nullptr, nullptr, hp};
+            cur = Mat{(const float*)(ws + p.z), zh, zl, hp};
         }
         for (int i = 0; i < n; ++i) {
             const int K = w[i], N = w[i + 1], Np = np_of(N);
@@ -587,7 +609,9 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         double* st = (double*)(ws + p.st[r.m][r.i]);
         Mat gin{(const float*)(ws + p.g[gi]), tc ? (const __half*)(ws + p.gh[gi]) : nullptr,
                 tc ? (const __half*)(ws + p.gl[gi]) : nullptr, p.maxNp};
-        if (vib && r.m == 0 && r.i == d.n_enc - 1) gin = Mat{(const float*)(ws + p.genc), nullptr, nullptr, np_of(enc_out)};
+        if (vib && r.m == 0 && r.i == d.n_enc - 1)
+            gin = Mat{(const float*)(ws + p.genc), tc ? (const __half*)(ws + p.gench) : nullptr,
+                      tc ? (const __half*)(ws + p.gencl) : nullptr, np_of(enc_out)};
         Mat gpre = gin;
         float gemm_scale = gscale;       // CUDA-core path: factor still to be applied to g_pre
         if (r.bn) {
@@ -667,7 +691,9 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             gi ^= 1;
             if (into_vib) {
                 vib_train_bwd_kernel<<<ew_grid((size_t)B * dec_in), 256, 0, s>>>(gout, p.maxNp, (const float*)(ws + p.pre[0][prev.i]), prev.Np,
-                                                                                 B, dec_in, d_eps, beta_kl, (float*)(ws + p.genc), np_of(enc_out));
+                                                                                 B, dec_in, d_eps, beta_kl, (float*)(ws + p.genc), np_of(enc_out),
+                                                                                 tc ? (__half*)(ws + p.gench) : nullptr,
+                                                                                 tc ? (__half*)(ws + p.gencl) : nullptr, GS);
                 MMAD_LAUNCHED();
             }
         }
@@ -692,8 +718,8 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         set_error("encoder output %d does not feed decoder input %d (%s)", enc_out, dec_in, vib ? "VIB expects 2x" : "pass eps for a VIB model");
         return MMAD_E_ARG;
     }
-    // tensor-core GEMMs for the plain autoencoder in the f16x3 / f16 modes; VIB and fp32 use the CUDA-core kernel
-    const bool tc = d.precision != MMAD_PREC_FP32 && !vib && tc_available();
+    // tensor-core GEMMs in the f16x3 / f16 modes, CUDA-core fp32 otherwise
+    const bool tc = d.precision != MMAD_PREC_FP32 && tc_available();
     const TrainPlan p = make_train_plan(d, batch, tc_available() != 0);
     if (ws_bytes < p.total) { set_error("train workspace too small: %zu < %zu", ws_bytes, p.total); return MMAD_E_WORKSPACE; }
     for (int m = 0; m < 2; ++m) {

@@ -143,7 +143,8 @@ def test_zero_grad_set_to_none_false_does_not_double_count():
         torch.testing.assert_close(p.grad, a, rtol=1e-4, atol=1e-6)
 
 
-def test_vib_training_step_matches_autograd_restatement():
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+def test_vib_training_step_matches_autograd_restatement(precision):
     """VIB autoencoder (BASELINE configs[3]): reparameterisation pinned by the reference, KL
     parity-unpinned -- compared with the oracle's torch-autograd fp32 statement."""
     from oracle import rapp_oracle as RO
@@ -152,7 +153,7 @@ def test_vib_training_step_matches_autograd_restatement():
     x, _ = synth_windows(B, D, 21, anomaly_rate=0.0)
     eps = torch.randn(B, btl, generator=torch.Generator().manual_seed(99))
     ref_loss, ref_grads, ref_bufs = RO.vib_train_forward_backward(x, dict(sd), eps, beta)
-    m = _model(D, btl, nl, seed, vib=True, beta_kl=beta)
+    m = _model(D, btl, nl, seed, vib=True, beta_kl=beta, precision=precision)
     m.load_state_dict(sd)
     m.train()
     loss = m.get_loss_value(x.cuda(), x.cuda(), eps=eps.cuda())
