@@ -28,6 +28,13 @@ class TrainLayer(C.Structure):
                 ("W", "b", "gamma", "beta", "run_mean", "run_var", "num_batches_tracked", "gW", "gb", "ggamma", "gbeta")]
 
 
+class FeatureWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("conv1r_w", "conv1r_b", "conv2r_w", "conv2r_b", "conv3r_w", "conv3r_b",
+                 "conv1d_w", "conv1d_b", "conv2d_w", "conv2d_b", "conv3d_w", "conv3d_b",
+                 "conv1l_w", "conv1l_b", "conv2l_w", "conv2l_b")]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)
 
 _vp, _i, _sz, _ll, _f = C.c_void_p, C.c_int, C.c_size_t, C.c_longlong, C.c_float
@@ -66,6 +73,8 @@ SIGNATURES = {
     "mmad_auc_prc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "mmad_quantile": (_i, [_vp, _ll, _f, C.POINTER(C.c_float), _vp, _sz, _vp]),
     "mmad_confusion": (_i, [_vp, _vp, _ll, _f, _i, C.POINTER(C.c_longlong), _vp, _sz, _vp]),
+    "mmad_multisensory_width": (_i, [_i, _i, _i, _i]),
+    "mmad_multisensory_forward": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(FeatureWeights), C.POINTER(C.c_float), _vp, _i, _vp]),
     "mmad_profile_begin": (_i, [_vp]),
     "mmad_profile_end": (_i, [_vp, C.POINTER(C.c_double)]),
     "mmad_launch_count": (C.c_ulonglong, []),

@@ -223,6 +223,24 @@ int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads,
                    float* const* h_v, const long long* h_numel, int step, float lr, float beta1,
                    float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- multimodal feature extractor in front of the autoencoder ----
+ * utils/data_loaders.py:152-229 (HSR_Net.forward) / 601-674 (Multisensory_module.forward): per sample
+ * conv stacks on the 32x32 RGB and depth images, broadcast force-torque scalar, two 1-d convolutions on the 13
+ * MFCC coefficients, concatenated as [rgb 1024 | depth 512 | force-torque 64 | mic 128] -- one launch for the batch.
+ * d_r [B,3,32,32], d_d [B,1,32,32], d_t [B], d_m [B,13]; a NULL input drops that modality (the reference's
+ * unimodal variants) and the remaining blocks are packed in the same order.  Weights: nn.Conv2d / nn.Conv1d
+ * tensors in PyTorch layout.  h_affine (host, 8 floats, may be NULL): (scale, shift) applied to r, d, t, m on load
+ * = norm_vec (utils/data_loaders.py:703-712). */
+typedef struct {
+    const float *conv1r_w, *conv1r_b, *conv2r_w, *conv2r_b, *conv3r_w, *conv3r_b;
+    const float *conv1d_w, *conv1d_b, *conv2d_w, *conv2d_b, *conv3d_w, *conv3d_b;
+    const float *conv1l_w, *conv1l_b, *conv2l_w, *conv2l_b;
+} mmad_feature_weights_t;
+int mmad_multisensory_width(int has_r, int has_d, int has_t, int has_m);
+int mmad_multisensory_forward(const float* d_r, const float* d_d, const float* d_t, const float* d_m, int batch,
+                              const mmad_feature_weights_t* w, const float* h_affine, float* d_out, int ldo,
+                              void* stream);
+
 /* ---- measurement hooks (bench.py) ----
  * mmad_profile_begin: record a CUDA-event pair around every fused-GEMM launch of this handle.
  * mmad_profile_end: synchronise; h_out[0] = sum of GEMM kernel durations (ms), h_out[1] = their

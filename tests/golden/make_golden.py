@@ -134,6 +134,44 @@ def vib_case(name):
     print(name)
 
 
+def feature_case(name):
+    """utils/data_loaders.py: Multisensory_module / HSR_Net / norm_vec, run unmodified on CPU.  Extra shims for this
+    module only: stub ``librosa`` (imported at the top of utils/data_loaders.py, used by the wav loader only) and a
+    no-op ``.cuda()`` (the forward allocates its output with ``torch.Tensor().cuda(gpu_id)``)."""
+    for mod in ("librosa", "librosa.display", "librosa.feature"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    tcuda, mcuda = torch.Tensor.cuda, torch.nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        import utils.data_loaders as DL
+        B = 5
+        g = torch.Generator().manual_seed(77)
+        torch.manual_seed(3)
+        cfg = argparse.Namespace(batch_size=B, slicing_size=B, gpu_id=0)
+        net = DL.Multisensory_module(cfg)
+        r = torch.rand(B, 1, 3, 32, 32, generator=g) * 2 - 1
+        d = torch.rand(B, 1, 1, 32, 32, generator=g) * 2 - 1
+        t = torch.rand(B, generator=g) * 2 - 1
+        m = torch.rand(B, 1, 1, 13, generator=g) * 2 - 1
+        with torch.no_grad():
+            fused = quiet(net, r, d, t, m)
+            hsr = DL.HSR_Net(True, cfg)
+            hsr.load_state_dict(net.state_dict())
+            rgb_only = quiet(hsr, r, None, None, None, None)
+            depth_only = quiet(hsr, None, d, None, None, None)
+            # HsrDataset normalisation (raw sensor ranges)
+            raw_r = torch.rand(B, 3 * 32 * 32, generator=g) * 255
+            raw_t = torch.rand(B, generator=g) * 400
+            raw_m = torch.randn(B, 13, generator=g) * 30
+            normed = dict(r=DL.norm_vec(raw_r, range_in=[0, 255]), t=DL.norm_vec(raw_t, range_in=[0, 400]), m=DL.norm_vec(raw_m))
+        torch.save(dict(sd=net.state_dict(), r=r, d=d, t=t, m=m, fused=fused, rgb_only=rgb_only, depth_only=depth_only,
+                        raw_r=raw_r, raw_t=raw_t, raw_m=raw_m, normed=normed), os.path.join(HERE, name))
+        print(name, tuple(fused.shape))
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = tcuda, mcuda
+
+
 def metric_cases(name):
     rng = np.random.default_rng(7)
     cases = []
@@ -190,4 +228,5 @@ if __name__ == "__main__":
     train_case("train_D64.pt", 64, 100, 5, 41, B=32, steps=3, full_state=True)
     train_case("train_D1728.pt", 1728, 100, 5, 51, B=256, steps=2, full_state=False)
     vib_case("vib_D64.pt")
+    feature_case("features.pt")
     metric_cases("metrics_golden.json")

@@ -154,3 +154,17 @@ def test_widths():
     assert RO.decoder_widths(1728, 100, 5) == [100, 425, 751, 1076, 1402, 1728]
     assert RO.encoder_widths(1728, 10, 3) == [1728, 1155, 582, 10]
     assert RO.encoder_widths(64, 100, 5) == [64, 71, 78, 85, 92, 100]
+
+
+def test_feature_extractor_oracle_matches_reference():
+    """oracle/feature_oracle.py against the unmodified reference classes (tests/golden/features.pt)."""
+    from oracle import feature_oracle as FO
+    g = load_golden("features.pt")
+    sd = g["sd"]
+    with torch.no_grad():
+        assert _rel(FO.multisensory_forward(sd, g["r"], g["d"], g["t"], g["m"]), g["fused"]) < 1e-6
+        assert _rel(FO.multisensory_forward(sd, r=g["r"]), g["rgb_only"]) < 1e-6
+        assert _rel(FO.multisensory_forward(sd, d=g["d"]), g["depth_only"]) < 1e-6
+    assert tuple(g["fused"].shape) == (5, 27, 8, 8)
+    assert _rel(FO.norm_vec(g["raw_r"], [0, 255]), g["normed"]["r"]) < 1e-6
+    assert _rel(FO.norm_vec(g["raw_m"]), g["normed"]["m"]) < 1e-6
