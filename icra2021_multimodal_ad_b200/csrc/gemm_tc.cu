@@ -291,10 +291,15 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int num_kb = (K + BK - 1) / BK;
     p.splits = 1;
     p.tri = e.b_upper_tri ? 1 : 0;
-    if (!p.tri && e.plain && e.split_k_ok && tiles * 2 <= g_num_sms) {
-        p.splits = g_num_sms / tiles;
-        if (p.splits > num_kb) p.splits = num_kb;
-        if (p.splits < 1) p.splits = 1;
+    if (!p.tri && e.plain && e.split_k_ok) {
+        // split-K when it fills the machine better: cost ~ waves x k-blocks per item; ties go to fewer splits
+        // (every split adds one atomic pass over the output)
+        long best = (long)((tiles + g_num_sms - 1) / g_num_sms) * num_kb;
+        for (int sp = 2; sp <= 16 && sp <= num_kb; ++sp) {
+            const long waves = ((long)tiles * sp + g_num_sms - 1) / g_num_sms;
+            const long cost = waves * ((num_kb + sp - 1) / sp) + waves;       // + per-item fill/epilogue overhead
+            if (cost * 10 < best * 9) { best = cost; p.splits = sp; }          // require >= 10 % gain
+        }
     }
     if (p.splits > 1)    // partial sums are accumulated atomically: the output starts at zero
         MMAD_CUDA_OK(cudaMemset2DAsync(e.Y, (size_t)e.ldy * 4, 0, (size_t)N * 4, M, s));

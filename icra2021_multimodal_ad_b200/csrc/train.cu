@@ -490,6 +490,14 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                        bool b_mn, int M, int N, int K, const Epilogue& e) -> int {
         TcOperand A, Bo;
         int rc;
+        if (!a_mn && !b_mn && !e.plain && M >= 2048 && tc2_available()) {      // tall K-major GEMM: CTA pairs
+            rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128);
+            if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128);
+            if (!rc) rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, 128);
+            if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, 128);
+            if (rc) return rc;
+            return gemm_tc2(A, Bo, M, N, K, passes, e, s);
+        }
         const int bn = gemm_tc_pick_bn(M, N);
         if (a_mn) { rc = tc_make_operand_map(&A.hi, Ah, K, M, lda, 64); if (!rc) rc = tc_make_operand_map(&A.lo, Al, K, M, lda, 64); }
         else { rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128); if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128); }
@@ -559,7 +567,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             if (tc) {
                 const LayerView lv = handle_layer(h, m, i);
                 e.acc_scale = 1.f / lv.wscale;
-                if (bn) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
+                if (bn && !(B >= 2048 && tc2_available())) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
                     e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1;
                 }
                 rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e);
