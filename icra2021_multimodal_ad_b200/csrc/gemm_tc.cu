@@ -68,7 +68,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
-        if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
+        if (PASSES >= 2) tma_prefetch_desc(&mapAl);
+        if (PASSES == 3) tma_prefetch_desc(&mapBl);
     }
     if (warp == 1) {   // TMEM allocation is a warp-wide operation; the same warp frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
@@ -110,10 +111,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     };
                     load_a(st, &mapAh);
                     load_b(st + A_TILE_BYTES, &mapBh);
-                    if (PASSES == 3) {
-                        load_a(st + A_TILE_BYTES + B_TILE_BYTES, &mapAl);
-                        load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
-                    }
+                    if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_TILE_BYTES, &mapAl);
+                    if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -149,6 +148,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         if (PASSES == 3) {
                             umma_f16(d_tmem, dAh + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16(d_tmem, dAl + advA, dBh + advB, idesc, 1);
+                            umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, 1);
+                        } else if (PASSES == 2) {
+                            umma_f16(d_tmem, dAl + advA, dBh + advB, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, 1);
                         } else {
                             umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, ((kb - kb_lo) | k) != 0);
@@ -231,7 +233,7 @@ int init_tc() {
 #define MMAD_TC_ATTR(P, AM, BMN)                                             \
     attr(gemm_tc_kernel<P, AM, BMN, 256>, Cfg<P, 256>::kSmemBytes);           \
     attr(gemm_tc_kernel<P, AM, BMN, 128>, Cfg<P, 128>::kSmemBytes)
-    MMAD_TC_ATTR(3, false, false); MMAD_TC_ATTR(1, false, false);
+    MMAD_TC_ATTR(3, false, false); MMAD_TC_ATTR(1, false, false); MMAD_TC_ATTR(2, false, false);
     MMAD_TC_ATTR(3, false, true);  MMAD_TC_ATTR(1, false, true);
     MMAD_TC_ATTR(3, true, true);   MMAD_TC_ATTR(1, true, true);
 #undef MMAD_TC_ATTR
@@ -307,14 +309,17 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (A.mn && !B.mn) { set_error("gemm_tc: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
 #define MMAD_TC_LAUNCH2(P, AM, BMN, BNV)                                                                              \
-    gemm_tc_kernel<P, AM, BMN, BNV><<<grid, NTHREADS, Cfg<P, BNV>::kSmemBytes, s>>>(A.hi, P == 3 ? A.lo : A.hi, B.hi, \
+    gemm_tc_kernel<P, AM, BMN, BNV><<<grid, NTHREADS, Cfg<P, BNV>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, \
                                                                                    P == 3 ? B.lo : B.hi, p, e)
 #define MMAD_TC_LAUNCH(P, AM, BMN)                  \
     do {                                            \
         if (bn == 256) MMAD_TC_LAUNCH2(P, AM, BMN, 256); \
         else MMAD_TC_LAUNCH2(P, AM, BMN, 128);      \
     } while (0)
-    if (passes == 3) {
+    if (passes == 2) {
+        if (A.mn || B.mn) { set_error("gemm_tc: the 2-pass mode is instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
+        MMAD_TC_LAUNCH(2, false, false);
+    } else if (passes == 3) {
         if (A.mn) MMAD_TC_LAUNCH(3, true, true);
         else if (B.mn) MMAD_TC_LAUNCH(3, false, true);
         else MMAD_TC_LAUNCH(3, false, false);

@@ -31,10 +31,11 @@ constexpr int BN2 = 256;                       // tile width; each CTA holds BN2
 constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;   // 16 KB
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
+// PASSES: 3 = hi*lo + lo*hi + hi*hi (fp32-equivalent products); 2 = lo*hi + hi*hi (A exact, B rounded to fp16:
+// the NAP rotation, whose B rows are unit-max whitening vectors); 1 = hi*hi
 template <int PASSES> struct Cfg2 {
-    static constexpr int kOperands = PASSES == 3 ? 2 : 1;
-    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + B_HALF_BYTES);        // 64 KB / 32 KB per CTA
-    static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 3 / 6
+    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES == 3 ? 2 : 1) * B_HALF_BYTES;   // 64 / 48 / 32 KB per CTA
+    static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 3 / 4 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;
     static constexpr int kSmemBytes = kSmemTiles + 4 * BN2 * 4 + EPI_WARPS * STG_FLOAT4 * 16 + 256 + 1024;
 };
@@ -110,7 +111,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 2 * EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
-        if (PASSES == 3) { tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBl); }
+        if (PASSES >= 2) tma_prefetch_desc(&mapAl);
+        if (PASSES == 3) tma_prefetch_desc(&mapBl);
     }
     if (warp == 1) {   // the same logical warp of both CTAs allocates (and later frees) the pair's TMEM
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
@@ -140,10 +142,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                     uint8_t* st = smem + stage * C::kStageBytes;
                     tma_load_2d_pair(smem_u32(st), &mapAh, fb, kb * BK, m0);
                     tma_load_2d_pair(smem_u32(st + A_TILE_BYTES), &mapBh, fb, kb * BK, nb0);
-                    if (PASSES == 3) {
-                        tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * BK, m0);
-                        tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * BK, nb0);
-                    }
+                    if (PASSES >= 2) tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * BK, m0);
+                    if (PASSES == 3) tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * BK, nb0);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -176,6 +176,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                         if (PASSES == 3) {
                             umma_f16_pair(d_tmem, dAh + adv, dBl + adv, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16_pair(d_tmem, dAl + adv, dBh + adv, idesc, 1);
+                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                        } else if (PASSES == 2) {
+                            umma_f16_pair(d_tmem, dAl + adv, dBh + adv, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, 1);
                         } else {
                             umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, ((kb - kb_lo) | k) != 0);
@@ -238,6 +241,7 @@ int init_tc2() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
     g_sms = prop.multiProcessorCount;
     if (cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<3>::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -271,6 +275,8 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
     if (passes == 3)
         gemm_tc2_kernel<3><<<grid, NTHREADS, Cfg2<3>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.lo, p, e);
+    else if (passes == 2)
+        gemm_tc2_kernel<2><<<grid, NTHREADS, Cfg2<2>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.hi, p, e);
     else
         gemm_tc2_kernel<1><<<grid, NTHREADS, Cfg2<1>::kSmemBytes, s>>>(A.hi, A.hi, B.hi, B.hi, p, e);
     MMAD_LAUNCHED();

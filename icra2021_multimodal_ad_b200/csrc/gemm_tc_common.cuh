@@ -18,9 +18,9 @@ constexpr int NTHREADS = 64 + 256;          // TMA warp, MMA warp, eight epilogu
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 
 template <int PASSES, int BN> struct Cfg {
-    static constexpr int kOperands = PASSES == 3 ? 2 : 1;      // hi (+ lo)
     static constexpr int kBTileBytes = BN * BK * 2;            // 32 KB / 16 KB
-    static constexpr int kStageBytes = kOperands * (A_TILE_BYTES + kBTileBytes);
+    // PASSES 3: A hi+lo, B hi+lo;  2: A hi+lo, B hi (lo*hi + hi*hi);  1: hi only
+    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES == 3 ? 2 : 1) * kBTileBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 2 / 3 / 4 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;   // <= 192 KB
     static constexpr int kTmemCols = 2 * BN;                   // two fp32 accumulators
