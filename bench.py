@@ -345,10 +345,32 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
+    # what the tensor pipe actually executes per window in this mode: 3 (f16x3) or 1 MMA per chain product, and the
+    # triangular NAP factor's half of the rotation products
+    mma_passes = 3 if precision == "f16x3" else 1
+    executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT / 2 if want_nap else 0))
+    executed_tf = value / world * executed_per_window / 1e12 if precision != "fp32" else None
+    pipe_pct = None
+    try:   # time-weighted tensor-pipe activity of the fused GEMM launches from the committed ncu launch list
+        import csv
+        rows = [r for r in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r1_launches_scoring_f16x3.csv")) if not l.startswith("=="))]
+        t, a = {}, {}
+        for r in rows:
+            if "gemm_tc" in r["Kernel Name"]:
+                v = float(r["Metric Value"].replace(",", ""))
+                (t if r["Metric Name"].startswith("gpu__time") else a)[r["ID"]] = v
+        if t and precision == "f16x3":
+            pipe_pct = sum(t[k] * a.get(k, 0.0) for k in t) / sum(t.values())
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                 "kernel": "fused layer GEMM (%s)" % precision, "peak_source": pk_kind + " bf16 sustained",
-                "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / args.steps)}
+                "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / args.steps),
+                "executed_mma_tflops": executed_tf, "executed_frac_of_peak": executed_tf / peak_tf if executed_tf and peak_tf else None,
+                "ncu_tensor_pipe_active_pct": pipe_pct,
+                "note": "achieved counts ONE product per MAC of the reference's dense algorithm; f16x3 issues 3 MMAs per product "
+                        "(cap = peak/3 for dense work) and the triangular NAP factor executes half of the rotation"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host input, scores back on host) ----
     xh_np = x_host.numpy()
