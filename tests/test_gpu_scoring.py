@@ -233,3 +233,35 @@ def test_streaming_batches_take_the_fp32_weight_streaming_path(n, precision):
     np.testing.assert_allclose(h["sap"], o["sap"].cpu().numpy(), rtol=1e-6)
     h2 = eng.score_host(x.numpy(), 0, nl + 1, base=True, sap=True, nap=False)      # graph replay
     np.testing.assert_array_equal(h2["sap"], h["sap"])
+
+
+def test_bulk_size_properties():
+    """Bulk size (300 000 windows of the headline model: several device chunks, partial last chunk): properties that
+    do not need an oracle at that size -- rows are scored independently of their neighbours and of the chunking
+    (bit-identical under permutation and under splitting the call) -- plus the oracle on a random subset."""
+    from oracle import rapp_oracle as RO
+    D, btl, nl, seed = 1728, 100, 5, 31
+    sd = synth_state_dict(D, btl, nl, seed)
+    m = _model(D, btl, nl, seed, "f16x3")
+    eng = m.engine()
+    xtr, _ = synth_windows(2000, D, seed + 1, anomaly_rate=0.0)
+    eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+    n = 300_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(n, D, device="cuda", generator=g)
+    full = eng.score(x, 0, 1, nap=True)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    shuffled = eng.score(x[perm], 0, 1, nap=True)
+    for k in ("base", "sap", "nap"):
+        assert torch.equal(shuffled[k], full[k][perm]), k
+    cut = 123_457
+    a, b = eng.score(x[:cut], 0, 1, nap=True), eng.score(x[cut:], 0, 1, nap=True)
+    for k in ("base", "sap", "nap"):
+        assert torch.equal(torch.cat([a[k], b[k]]), full[k]), k
+    idx = torch.randint(0, n, (48,), device="cuda", generator=g)
+    ref = RO.get_diffs(x[idx].cpu(), sd)
+    np.testing.assert_allclose(full["base"][idx].cpu().numpy(), RO.recon_score(ref[0]), rtol=1e-4)
+    sap_all = eng.score(x[idx.sort().values], 0, nl + 1)["sap"]           # 48 rows: weight-streaming path
+    big = eng.score(x, 0, nl + 1)["sap"][idx.sort().values]
+    np.testing.assert_allclose(big.cpu().numpy(), sap_all.cpu().numpy(), rtol=1e-4)
+    assert torch.isfinite(full["nap"]).all()
