@@ -77,6 +77,35 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, 
     }
 }
 
+// the same for up to 2 * MMAD_MAX_LAYERS matrices in ONE launch (train step: every layer's twins are refreshed)
+struct SplitMulti {
+    const float* W[2 * MMAD_MAX_LAYERS];
+    __half* Wh[2 * MMAD_MAX_LAYERS];
+    __half* Wl[2 * MMAD_MAX_LAYERS];
+    int N[2 * MMAD_MAX_LAYERS], K[2 * MMAD_MAX_LAYERS], Kp[2 * MMAD_MAX_LAYERS];
+    int block_start[2 * MMAD_MAX_LAYERS + 1];
+    int n;
+    float scale;
+};
+__global__ void __launch_bounds__(256) split_weights_multi_kernel(const __grid_constant__ SplitMulti a) {
+    int t = 0;
+    while (t + 1 < a.n && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
+    const int Kp = a.Kp[t], K = a.K[t];
+    const size_t total = (size_t)a.N[t] * Kp;
+    const size_t base = (size_t)(blockIdx.x - a.block_start[t]) * 4096;
+    const float* __restrict__ W = a.W[t];
+    __half* __restrict__ Wh = a.Wh[t];
+    __half* __restrict__ Wl = a.Wl[t];
+    for (size_t i = base + threadIdx.x; i < base + 4096 && i < total; i += 256) {
+        const int r = (int)(i / Kp), c = (int)(i % Kp);
+        const float v = c < K ? W[(size_t)r * K + c] * a.scale : 0.f;
+        __half h, l;
+        split_half(v, h, l);
+        Wh[i] = h;
+        Wl[i] = l;
+    }
+}
+
 __global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                                int N, int Np, float* scale, float* shift) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +340,25 @@ int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half*
 
 int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s) {
     split_weights_kernel<<<grid_for((size_t)N * Kp), 256, 0, s>>>(W, N, K, Kp, scale, Wh, Wl);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int split_weights_multi(int n, const float* const* W, const int* N, const int* K, const int* Kp, float scale, __half* const* Wh,
+                        __half* const* Wl, cudaStream_t s) {
+    if (n <= 0) return MMAD_OK;
+    if (n > 2 * MMAD_MAX_LAYERS) { set_error("split_weights_multi: too many tensors"); return MMAD_E_ARG; }
+    SplitMulti a;
+    a.n = n; a.scale = scale;
+    int blocks = 0;
+    for (int t = 0; t < n; ++t) {
+        a.W[t] = W[t]; a.Wh[t] = Wh[t]; a.Wl[t] = Wl[t]; a.N[t] = N[t]; a.K[t] = K[t]; a.Kp[t] = Kp[t];
+        a.block_start[t] = blocks;
+        blocks += (int)(((size_t)N[t] * Kp[t] + 4095) / 4096);
+    }
+    a.block_start[n] = blocks;
+    split_weights_multi_kernel<<<blocks, 256, 0, s>>>(a);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

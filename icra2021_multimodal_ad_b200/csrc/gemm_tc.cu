@@ -303,7 +303,7 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
             if (cost * 10 < best * 9) { best = cost; p.splits = sp; }          // require >= 10 % gain
         }
     }
-    if (p.splits > 1)    // partial sums are accumulated atomically: the output starts at zero
+    if (p.splits > 1 && !e.pre_zeroed)    // partial sums are accumulated atomically: the output starts at zero
         MMAD_CUDA_OK(cudaMemset2DAsync(e.Y, (size_t)e.ldy * 4, 0, (size_t)N * 4, M, s));
     const int items = tiles * p.splits;
     const int grid = items < g_num_sms ? items : g_num_sms;

@@ -62,6 +62,7 @@ struct Epilogue {
     float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
     int plain = 0;                                      // Y = acc * acc_scale + bias only, rows of Y may be unaligned
     int b_upper_tri = 0;                                // B[n, k] == 0 for k < n (tensor-core kernel skips those k-blocks)
+    int pre_zeroed = 0;                                 // split-K: the caller already zeroed Y (no memset inside gemm_tc)
     int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
     float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)
 };
@@ -131,6 +132,8 @@ void handle_graph_clear(mmad_t h);
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,
               cudaStream_t s);
 int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s);
+int split_weights_multi(int n, const float* const* W, const int* N, const int* K, const int* Kp, float scale, __half* const* Wh,
+                        __half* const* Wl, cudaStream_t s);
 int finalize_scores(const float* rowpart, int stride, int n, int slot_lo_base, int slot_hi_base,
                     int sap_slot_lo, int sap_slot_hi, float inv_base, float inv_sap,
                     float* base, float* sap, cudaStream_t s);

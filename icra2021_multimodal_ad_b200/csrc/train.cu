@@ -379,6 +379,7 @@ struct TrainPlan {
     size_t inv[2][MMAD_MAX_LAYERS] = {{0}};
     size_t st[2][MMAD_MAX_LAYERS] = {{0}};    // [4][Np] doubles per layer: forward sum / sum sq, backward sum g / sum g xhat
     size_t st_all = 0, st_bytes = 0;
+    size_t pre_all = 0, pre_bytes = 0;
     size_t g[2] = {0, 0};                      // gradient ping-pong [B, maxNp]
     size_t z = 0, genc = 0, eps = 0;           // VIB: sampled code, gradient wrt the encoder output, staged noise
     size_t rowpart = 0;
@@ -410,12 +411,18 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
     }
     p.kl = take(8);
     p.st_bytes = off - p.st_all;
+    p.pre_all = off;                    // every layer's pre-activation buffer, contiguous: one memset zeroes them
+    for (int m = 0; m < 2; ++m) {
+        const int n = m == 0 ? d.n_enc : d.n_dec;
+        const int* w = m == 0 ? d.enc_widths : d.dec_widths;
+        for (int i = 0; i < n; ++i) p.pre[m][i] = take((size_t)B * np_of(w[i + 1]) * 4);
+    }
+    p.pre_bytes = off - p.pre_all;
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
         for (int i = 0; i < n; ++i) {
             const int Np = np_of(w[i + 1]);
-            p.pre[m][i] = take((size_t)B * Np * 4);
             const bool bn = i < n - 1;
             p.out[m][i] = bn ? take((size_t)B * Np * 4) : p.pre[m][i];
             if (bn) { p.mean[m][i] = take((size_t)Np * 4); p.inv[m][i] = take((size_t)Np * 4); }
@@ -514,15 +521,38 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     const float* xref = (const float*)(ws + p.xp);      // staged input: reference of the loss epilogue
     const int ldxref = Dp;
     Mat cur{xref, tc ? (const __half*)(ws + p.xh) : nullptr, tc ? (const __half*)(ws + p.xl) : nullptr, Dp};
+    bool gw_zeroed = false;
     if (tc) {
-        for (int m = 0; m < 2; ++m) {      // weights changed since the last step: refresh their fp16 twins
+        // weights changed since the last step: refresh every layer's fp16 twins in one launch
+        const float* Wp[2 * MMAD_MAX_LAYERS]; __half* Whp[2 * MMAD_MAX_LAYERS]; __half* Wlp[2 * MMAD_MAX_LAYERS];
+        int Ns[2 * MMAD_MAX_LAYERS], Ks[2 * MMAD_MAX_LAYERS], Kps[2 * MMAD_MAX_LAYERS], nt = 0;
+        float wscale = 256.f;
+        uintptr_t g_lo = ~(uintptr_t)0, g_hi = 0;
+        size_t g_sum = 0;
+        for (int m = 0; m < 2; ++m) {
             const int n = m == 0 ? d.n_enc : d.n_dec;
             const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
-            for (int i = 0; i < n; ++i) {
+            for (int i = 0; i < n; ++i, ++nt) {
                 const LayerView lv = handle_layer(h, m, i);
-                int rc = split_weights(Ls[i].W, lv.N, lv.K, lv.Kp, lv.wscale, lv.Wh, lv.Wl, s);
-                if (rc) return rc;
+                Wp[nt] = Ls[i].W; Whp[nt] = lv.Wh; Wlp[nt] = lv.Wl; Ns[nt] = lv.N; Ks[nt] = lv.K; Kps[nt] = lv.Kp;
+                wscale = lv.wscale;
+                auto span = [&](const float* q, size_t count) {
+                    if (!q) return;
+                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(q);
+                    g_lo = std::min(g_lo, a0); g_hi = std::max(g_hi, a0 + count * 4); g_sum += count * 4;
+                };
+                span(Ls[i].gW, (size_t)lv.N * lv.K); span(Ls[i].gb, lv.N);
+                if (i < n - 1) { span(Ls[i].ggamma, lv.N); span(Ls[i].gbeta, lv.N); }
             }
+        }
+        int rc = split_weights_multi(nt, Wp, Ns, Ks, Kps, wscale, Whp, Wlp, s);
+        if (rc) return rc;
+        // split-K outputs start from zero: the pre-activation buffers (contiguous) and, when ALL gradient tensors
+        // tile one flat buffer exactly (they do in the Python layer), that buffer -- two memsets instead of one per GEMM
+        MMAD_CUDA_OK(cudaMemsetAsync(ws + p.pre_all, 0, p.pre_bytes, s));
+        if (g_hi - g_lo == g_sum) {      // the gradient tensors tile one buffer exactly (no foreign bytes in between)
+            MMAD_CUDA_OK(cudaMemsetAsync(reinterpret_cast<void*>(g_lo), 0, g_hi - g_lo, s));
+            gw_zeroed = true;
         }
     }
     const int loss_tile_n = tc ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
@@ -568,7 +598,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 const LayerView lv = handle_layer(h, m, i);
                 e.acc_scale = 1.f / lv.wscale;
                 if (bn && !(B >= 2048 && tc2_available())) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
-                    e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1;
+                    e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1; e.pre_zeroed = 1;
                 }
                 rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e);
             } else {
@@ -626,6 +656,9 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             const float* pre = (const float*)(ws + p.pre[r.m][r.i]);
             const float* mean = (const float*)(ws + p.mean[r.m][r.i]);
             const float* inv = (const float*)(ws + p.inv[r.m][r.i]);
+            float* go = (float*)(ws + p.g[gi ^ 1]);
+            __half* goh = tc ? (__half*)(ws + p.gh[gi ^ 1]) : nullptr;
+            __half* gol = tc ? (__half*)(ws + p.gl[gi ^ 1]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
             bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
                                                                   L.gb, row_slab(B));
@@ -636,9 +669,6 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 int rc = allreduce(allreduce_ctx, stb, 2LL * r.Np, s);
                 if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
             }
-            float* go = (float*)(ws + p.g[gi ^ 1]);
-            __half* goh = tc ? (__half*)(ws + p.gh[gi ^ 1]) : nullptr;
-            __half* gol = tc ? (__half*)(ws + p.gl[gi ^ 1]) : nullptr;
             bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
                                                                  r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
                                                                  L.gbeta, allreduce ? 0 : 1, row_slab(B));
@@ -656,7 +686,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             e.Y = L.gW; e.ldy = r.K; e.y_cols = r.K;
             int rc;
             if (tc) {
-                e.plain = 1; e.split_k_ok = 1;
+                e.plain = 1; e.split_k_ok = 1; e.pre_zeroed = gw_zeroed ? 1 : 0;
                 e.acc_scale = 1.f / GS;          // twins of g_pre carry GS (the 2 of dL/dxhat is inside the loss twins)
                 rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e);
             } else {
