@@ -77,7 +77,22 @@ struct Tc2Params {
     int M, N, K;
     int tiles_m, tiles_n;     // tiles of 256 x 256
     int tri;
+    int band;                 // n-tiles per band of the tile order (see tile_coords)
 };
+
+// Tile order: bands of `band` n-tiles, all m inside a band, n fastest.  The pairs running at any moment then cover
+// ~74/band row panels of A and `band` row panels of B: with band = 8 that is ~100 MB for the NAP rotation
+// (5.7 MB per 256-row fp16 hi+lo panel) and fits the 126 MB L2, so B (the 122 MB whitening factor) is read from HBM
+// once per band instead of once per few row tiles.  Narrow layers (tiles_n <= band) keep the plain n-fastest order.
+__device__ __forceinline__ void tile_coords(const Tc2Params& p, int t, int& tm, int& tn) {
+    const int full = p.tiles_m * p.band;
+    const int b = t / full;
+    const int rem = t - b * full;
+    int w = p.tiles_n - b * p.band;
+    if (w > p.band) w = p.band;
+    tm = rem / w;
+    tn = b * p.band + rem % w;
+}
 
 template <int PASSES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -129,10 +144,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
-                const int n0 = (t % p.tiles_n) * BN;
+                int tm, tn;
+                tile_coords(p, t, tm, tn);
+                const int n0 = tn * BN;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
-                const int m0 = (t / p.tiles_n) * 256 + (int)rank * BM;       // this CTA's 128 rows of A
+                const int m0 = tm * 256 + (int)rank * BM;                     // this CTA's 128 rows of A
                 const int nb0 = n0 + (int)rank * (n_eff >> 1);                // this CTA's half of the B rows
                 const int kb_lo = p.tri ? n0 / BK : 0;
                 for (int kb = kb_lo; kb < num_kb; ++kb) {
@@ -154,7 +171,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
-                const int n0 = (t % p.tiles_n) * BN;
+                int tm, tn;
+                tile_coords(p, t, tm, tn);
+                const int n0 = tn * BN;
                 const int kb_lo = p.tri ? n0 / BK : 0;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
@@ -200,7 +219,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         const int col_lo = half * 128, col_hi = col_lo + 128;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = pair; t < num_tiles; t += npairs) {
-            const int m0 = (t / p.tiles_n) * 256 + (int)rank * BM, tn = t % p.tiles_n, n0 = tn * BN;
+            int tm, tn;
+            tile_coords(p, t, tm, tn);
+            const int m0 = tm * 256 + (int)rank * BM, n0 = tn * BN;
             asm volatile("bar.sync 1, 256;");
             epi_stage_vectors<BN>(e, p.N, n0, 0, et, s_mul, s_bias, s_sc, s_sh);
             asm volatile("bar.sync 1, 256;");
@@ -270,6 +291,7 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + BN2 - 1) / BN2;
     p.tri = e.b_upper_tri ? 1 : 0;
+    p.band = 8;
     const int tiles = p.tiles_m * p.tiles_n;
     const int max_pairs = g_sms / 2;
     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
