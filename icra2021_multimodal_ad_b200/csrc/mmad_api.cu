@@ -78,6 +78,8 @@ struct mmad_handle {
     struct GraphRec { std::string key; cudaGraphExec_t exec; unsigned long long launches; };
     std::vector<GraphRec> graphs;
     cudaStream_t s_capture = nullptr;
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // set for the duration of a call of <= 64 rows: exact-fp32 weight-streaming kernels (gemm_skinny.cu) instead
     // of 128-row tensor-core tiles, whatever the handle's precision mode
     bool skinny = false;
@@ -404,6 +406,19 @@ void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsig
     h->graphs.push_back({key, g, launches});
 }
 
+int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+    if (!h->s_aux) {
+        if (cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+    }
+    *s2 = h->s_aux; *ev_fork = h->ev_fork; *ev_join = h->ev_join;
+    return 0;
+}
+
 void handle_graph_clear(mmad_t h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
@@ -509,6 +524,9 @@ int mmad_destroy(mmad_t h) {
     }
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->s_capture) cudaStreamDestroy(h->s_capture);
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     delete h;

@@ -127,6 +127,8 @@ cudaGraphExec_t handle_graph_find(mmad_t h, const std::string& key, unsigned lon
 void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsigned long long launches);
 cudaStream_t handle_capture_stream(mmad_t h);
 void handle_graph_clear(mmad_t h);
+// second stream + fork/join events of a handle (independent branches of a launch sequence); 0 on success
+int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

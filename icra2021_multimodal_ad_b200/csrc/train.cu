@@ -388,7 +388,8 @@ struct TrainPlan {
     // tensor-core modes: fp16 hi/lo twins
     size_t xh = 0, xl = 0, xp = 0;
     size_t outh[2][MMAD_MAX_LAYERS] = {{0}}, outl[2][MMAD_MAX_LAYERS] = {{0}};
-    size_t gh[2] = {0, 0}, gl[2] = {0, 0};
+    size_t gth[2 * MMAD_MAX_LAYERS] = {0}, gtl[2 * MMAD_MAX_LAYERS] = {0};   // g_pre twins of every layer (forward order index):
+                                                                              // own buffers, so dW can run on a second stream
     size_t zh = 0, zl = 0, gench = 0, gencl = 0;   // VIB twins: sampled code, gradient wrt the encoder output
 };
 
@@ -446,7 +447,7 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
                 p.outl[m][i] = take((size_t)B * np_of(w[i + 1]) * 2);
             }
         }
-        for (int i = 0; i < 2; ++i) { p.gh[i] = take((size_t)B * maxNp * 2); p.gl[i] = take((size_t)B * maxNp * 2); }
+        for (int i = 0; i < d.n_enc + d.n_dec; ++i) { p.gth[i] = take((size_t)B * maxNp * 2); p.gtl[i] = take((size_t)B * maxNp * 2); }
         p.zh = take((size_t)B * np_of(d.dec_widths[0]) * 2);
         p.zl = take((size_t)B * np_of(d.dec_widths[0]) * 2);
         p.gench = take((size_t)B * np_of(d.enc_widths[d.n_enc]) * 2);
@@ -475,7 +476,9 @@ size_t mmad_train_workspace_bytes(mmad_t h, int batch) {
 // sequence can be captured into a CUDA graph.
 static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool tc, bool vib, int batch, long long global_batch,
                       const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, float beta_kl, float bn_momentum,
-                      float* d_loss, char* ws, mmad_allreduce_fn allreduce, void* allreduce_ctx, cudaStream_t s) {
+                      float* d_loss, char* ws, mmad_allreduce_fn allreduce, void* allreduce_ctx, cudaStream_t s,
+                      cudaStream_t s2, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    bool forked = false;
     const int D = d.enc_widths[0];
     const int enc_out = d.enc_widths[d.n_enc], dec_in = d.dec_widths[0];
     const int passes = d.precision == MMAD_PREC_F16X3 ? 3 : 1;
@@ -494,7 +497,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
 
     // C[M,N] = A B^T-like product on the tensor cores.  a_mn / b_mn: operand stored [contraction, M|N].
     auto tc_gemm = [&](const __half* Ah, const __half* Al, int lda, bool a_mn, const __half* Bh, const __half* Bl, int ldb,
-                       bool b_mn, int M, int N, int K, const Epilogue& e) -> int {
+                       bool b_mn, int M, int N, int K, const Epilogue& e, cudaStream_t s) -> int {
         TcOperand A, Bo;
         int rc;
         if (!a_mn && !b_mn && !e.plain && M >= 2048 && tc2_available()) {      // tall K-major GEMM: CTA pairs
@@ -589,7 +592,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 if (last) {   // loss epilogue: d = xhat - x, row sums of d^2; g = 2 d enters the backward pass
                     e.ref = xref; e.ldref = ldxref;
                     e.dout = (float*)(ws + p.g[0]); e.lddout = p.maxNp; e.d_cols = tc ? Np : N;
-                    if (tc) { e.Dh = (__half*)(ws + p.gh[0]); e.Dl = (__half*)(ws + p.gl[0]); e.lddh = p.maxNp; e.d_scale = 2.f * GS; e.Y = nullptr; }
+                    if (tc) { const int li = d.n_enc + d.n_dec - 1; e.Dh = (__half*)(ws + p.gth[li]); e.Dl = (__half*)(ws + p.gtl[li]); e.lddh = p.maxNp; e.d_scale = 2.f * GS; e.Y = nullptr; }
                     e.rowpart = (float*)(ws + p.rowpart); e.rowpart_stride = B;
                 }
             }
@@ -600,7 +603,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 if (bn && !(B >= 2048 && tc2_available())) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
                     e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1; e.pre_zeroed = 1;
                 }
-                rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e);
+                rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e, s);
             } else {
                 GemmShape g;
                 g.M = B; g.N = N; g.K = K; g.A = cur.f; g.lda = cur.ld; g.B = L.W; g.ldb = K;
@@ -645,8 +648,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         const Ref& r = order[idx];
         const mmad_train_layer_t& L = *r.L;
         double* st = (double*)(ws + p.st[r.m][r.i]);
-        Mat gin{(const float*)(ws + p.g[gi]), tc ? (const __half*)(ws + p.gh[gi]) : nullptr,
-                tc ? (const __half*)(ws + p.gl[gi]) : nullptr, p.maxNp};
+        Mat gin{(const float*)(ws + p.g[gi]), tc ? (const __half*)(ws + p.gth[idx]) : nullptr,
+                tc ? (const __half*)(ws + p.gtl[idx]) : nullptr, p.maxNp};
         if (vib && r.m == 0 && r.i == d.n_enc - 1)
             gin = Mat{(const float*)(ws + p.genc), tc ? (const __half*)(ws + p.gench) : nullptr,
                       tc ? (const __half*)(ws + p.gencl) : nullptr, np_of(enc_out)};
@@ -657,8 +660,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             const float* mean = (const float*)(ws + p.mean[r.m][r.i]);
             const float* inv = (const float*)(ws + p.inv[r.m][r.i]);
             float* go = (float*)(ws + p.g[gi ^ 1]);
-            __half* goh = tc ? (__half*)(ws + p.gh[gi ^ 1]) : nullptr;
-            __half* gol = tc ? (__half*)(ws + p.gl[gi ^ 1]) : nullptr;
+            __half* goh = tc ? (__half*)(ws + p.gth[idx]) : nullptr;
+            __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
             bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
                                                                   L.gb, row_slab(B));
@@ -688,7 +691,15 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             if (tc) {
                 e.plain = 1; e.split_k_ok = 1; e.pre_zeroed = gw_zeroed ? 1 : 0;
                 e.acc_scale = 1.f / GS;          // twins of g_pre carry GS (the 2 of dL/dxhat is inside the loss twins)
-                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e);
+                // dW is off the critical path (nothing downstream reads it): second stream, joined at the end
+                cudaStream_t sw = s;
+                if (s2) {
+                    MMAD_CUDA_OK(cudaEventRecord(ev_fork, s));
+                    MMAD_CUDA_OK(cudaStreamWaitEvent(s2, ev_fork, 0));
+                    sw = s2;
+                    forked = true;
+                }
+                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e, sw);
             } else {
                 GemmShape g;
                 g.M = r.N; g.N = r.K; g.K = B;
@@ -711,11 +722,11 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 e.y_cols = np_of(r.K);
                 e.acc_scale = 1.f / (GS * lv.wscale);
                 if (!prev.bn) {   // the consumer is a bare Linear: it needs the twins of g_pre = g_in directly
-                    e.Yh = (__half*)(ws + p.gh[gi ^ 1]); e.Yl = (__half*)(ws + p.gl[gi ^ 1]); e.ldh = p.maxNp; e.y_split_scale = GS;
+                    e.Yh = (__half*)(ws + p.gth[idx - 1]); e.Yl = (__half*)(ws + p.gtl[idx - 1]); e.ldh = p.maxNp; e.y_split_scale = GS;
                 } else {
                     e.plain = 1; e.split_k_ok = 1; e.y_cols = r.K;
                 }
-                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, false, lv.Wh, lv.Wl, lv.Kp, true, B, r.K, r.N, e);
+                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, false, lv.Wh, lv.Wl, lv.Kp, true, B, r.K, r.N, e, s);
             } else {
                 GemmShape g;
                 g.M = B; g.N = r.K; g.K = r.N;
@@ -736,6 +747,10 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             }
         }
         gscale = 1.f;
+    }
+    if (forked) {
+        MMAD_CUDA_OK(cudaEventRecord(ev_join, s2));
+        MMAD_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
     }
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
@@ -783,8 +798,12 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
     const bool use_graph = !allreduce && graphs_enabled() && cap == cudaStreamCaptureStatusNone;
-    if (!use_graph)
-        return train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, allreduce, allreduce_ctx, s);
+    {
+        cudaStream_t s2 = nullptr; cudaEvent_t ef = nullptr, ej = nullptr;
+        if (tc && handle_aux(h, &s2, &ef, &ej)) s2 = nullptr;
+        if (!use_graph)
+            return train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, allreduce, allreduce_ctx, s, s2, ef, ej);
+    }
 
     // ---- CUDA graph of the step, keyed by everything the launch sequence depends on ----
     std::string key("train");
@@ -800,7 +819,9 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         if (!cs) return MMAD_E_CUDA;
         const unsigned long long l0 = g_launches;
         MMAD_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-        rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, nullptr, nullptr, cs);
+        cudaStream_t s2 = nullptr; cudaEvent_t ef = nullptr, ej = nullptr;
+        if (tc && handle_aux(h, &s2, &ef, &ej)) s2 = nullptr;
+        rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, nullptr, nullptr, cs, s2, ef, ej);
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         n_launch = g_launches - l0;
