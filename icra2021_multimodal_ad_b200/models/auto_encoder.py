@@ -30,7 +30,7 @@ class AutoEncoder(AbstractModel):
 
     def handle_engine(self) -> Engine:
         """The device engine (library handle) without (re)packing the eval-mode weights."""
-        p = next(self.parameters())
+        p = self.encoder.layer_list[0].layer.weight
         if not p.is_cuda:
             raise _lib.MmadError("model is on the CPU; the B200 path has no CPU fallback (use gpu_id >= 0)")
         if self._eng is None or self._eng.device != p.device:

@@ -53,7 +53,14 @@ class Adam(torch.optim.Optimizer):
                 continue
             st = self._group_state(gi, group)
             ps = st["params"]
-            G = (C.c_void_p * len(ps))(*[p.grad.data_ptr() for p in ps])
+            # gradient pointer table: reused while the gradients keep living where they did (views of one flat buffer)
+            ga, gb = ps[0].grad, ps[-1].grad
+            flat = ga.untyped_storage().data_ptr() == gb.untyped_storage().data_ptr()
+            gkey = (ga.data_ptr(), gb.data_ptr()) if flat else None
+            if gkey is None or st.get("Gkey") != gkey:
+                st["G"] = (C.c_void_p * len(ps))(*[p.grad.data_ptr() for p in ps])
+                st["Gkey"] = gkey
+            G = st["G"]
             st["step"] += 1
             b1, b2 = group["betas"]
             with torch.cuda.device(ps[0].device):

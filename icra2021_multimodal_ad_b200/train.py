@@ -44,6 +44,7 @@ class TrainState:
         self.anchor = torch.zeros((), dtype=torch.float32, device=dev, requires_grad=True)   # ties the loss to autograd
         self._tables = None
         self._tables_key = None
+        self.momentum = next((fc.bn.momentum for fc in _module_layers(model.encoder) if fc.bn is not None), 0.1)
         self.group = None            # torch.distributed group for BatchNorm statistics (SyncBN semantics)
         self.world = 1
         self._cb = None
@@ -81,9 +82,14 @@ class TrainState:
         """C callback handed to mmad_train_fwd_bwd: SUM-all-reduce of a BatchNorm statistics slice of
         the workspace over ``self.group`` (NCCL, enqueued on the current stream)."""
         if self.world <= 1:
-            return _lib.ALLREDUCE_FN(0), None
+            if self._cb is None:
+                self._cb = _lib.ALLREDUCE_FN(0)
+            return self._cb, None
         import torch.distributed as dist
         state = self
+
+        if self._cb is not None and getattr(self, "_cb_world", 1) == self.world:
+            return self._cb, None
 
         def cb(ctx, d_buf, count, stream):
             try:
@@ -94,15 +100,20 @@ class TrainState:
             except Exception:      # never let an exception cross the C boundary
                 return -1
         self._cb = _lib.ALLREDUCE_FN(cb)
+        self._cb_world = self.world
         return self._cb, None
 
 
 def train_state(model) -> TrainState:
     st = getattr(model, "_train_state", None)
-    if st is None or any(a is not b for a, b in zip(st.params, model.parameters())) \
-            or st.flat_grad.device != next(model.parameters()).device:
-        st = TrainState(model)
-        model._train_state = st
+    if st is not None:       # cheap validity check on the hot path: same first/last Parameter objects, same device
+        first, last = st.params[0], st.params[-1]
+        enc0 = model.encoder.layer_list[0].layer.weight
+        dec_last = model.decoder.layer_list[-1].layer.bias
+        if first is enc0 and last is dec_last and st.flat_grad.device == enc0.device:
+            return st
+    st = TrainState(model)
+    model._train_state = st
     return st
 
 
@@ -133,11 +144,7 @@ class _FusedStep(torch.autograd.Function):
         ws = st.workspace(eng._h, B)
         enc_t, dec_t = st.tables(model)
         cb, _ = st.allreduce_callback()
-        momentum = 0.1
-        for fc in _module_layers(model.encoder):
-            if fc.bn is not None:
-                momentum = fc.bn.momentum
-                break
+        momentum = st.momentum
         with torch.cuda.device(x.device):
             check(lib().mmad_train_fwd_bwd(eng._h, x.data_ptr(), x.stride(0) if B > 1 else x.shape[1], B, B * st.world,
                                            enc_t, dec_t, eps.data_ptr() if eps is not None else None, float(beta_kl),
@@ -170,9 +177,10 @@ def fused_train_loss(model, x: torch.Tensor, eps: Optional[torch.Tensor] = None,
     if eps is not None:
         eps = eps.detach().to(x.device, torch.float32).reshape(x.shape[0], -1).contiguous()
     st = train_state(model)
-    for p, v in zip(st.params, st.views):
-        # a .grad left over from the previous step aliases the flat buffer this step overwrites: give it its
-        # own storage so autograd's accumulation (zero_grad(set_to_none=False) callers) stays correct
-        if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
-            p.grad = p.grad.clone()
+    if any(p.grad is not None for p in st.params):
+        for p, v in zip(st.params, st.views):
+            # a .grad left over from the previous step aliases the flat buffer this step overwrites: give it its
+            # own storage so autograd's accumulation (zero_grad(set_to_none=False) callers) stays correct
+            if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+                p.grad = p.grad.clone()
     return _FusedStep.apply(model, x, eps, beta_kl, st.anchor)
