@@ -358,15 +358,39 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
     const float* __restrict__ g = a.g[t];
     float* __restrict__ m = a.m[t];
     float* __restrict__ v = a.v[t];
-    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-        const float gv = g[i] * gscale;
-        float mv = m[i], vv = v[i];
+    auto upd = [&](float pv, float gr, float& mv, float& vv) -> float {
+        const float gv = gr * gscale;
         mv = mv + w1 * (gv - mv);
-        vv = vv * b2 + omb2 * gv * gv;      // mul_ then addcmul_ (two roundings like torch; FMA contraction is off below)
-        m[i] = mv;
-        v[i] = vv;
+        vv = vv * b2 + omb2 * gv * gv;
         const float denom = sqrtf(vv) / bc2_sqrt + eps;
-        p[i] = p[i] + neg_step * (mv / denom);
+        return pv + neg_step * (mv / denom);
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec) {      // 16-byte accesses: four independent element updates per thread per iteration
+        const long long end4 = base + ((end - base) & ~3LL);
+        for (long long i = base + threadIdx.x * 4LL; i < end4; i += blockDim.x * 4LL) {
+            float4 pv = *reinterpret_cast<const float4*>(p + i);
+            const float4 gr = *reinterpret_cast<const float4*>(g + i);
+            float4 mv = *reinterpret_cast<const float4*>(m + i);
+            float4 vv = *reinterpret_cast<const float4*>(v + i);
+            pv.x = upd(pv.x, gr.x, mv.x, vv.x); pv.y = upd(pv.y, gr.y, mv.y, vv.y);
+            pv.z = upd(pv.z, gr.z, mv.z, vv.z); pv.w = upd(pv.w, gr.w, mv.w, vv.w);
+            *reinterpret_cast<float4*>(m + i) = mv;
+            *reinterpret_cast<float4*>(v + i) = vv;
+            *reinterpret_cast<float4*>(p + i) = pv;
+        }
+        for (long long i = end4 + threadIdx.x; i < end; i += blockDim.x) {
+            float mv = m[i], vv = v[i];
+            p[i] = upd(p[i], g[i], mv, vv);
+            m[i] = mv; v[i] = vv;
+        }
+        return;
+    }
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+        float mv = m[i], vv = v[i];
+        p[i] = upd(p[i], g[i], mv, vv);
+        m[i] = mv; v[i] = vv;
     }
 }
 
@@ -532,6 +556,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         float wscale = 256.f;
         uintptr_t g_lo = ~(uintptr_t)0, g_hi = 0;
         size_t g_sum = 0;
+        int g_cnt = 0;
         for (int m = 0; m < 2; ++m) {
             const int n = m == 0 ? d.n_enc : d.n_dec;
             const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
@@ -542,7 +567,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 auto span = [&](const float* q, size_t count) {
                     if (!q) return;
                     const uintptr_t a0 = reinterpret_cast<uintptr_t>(q);
-                    g_lo = std::min(g_lo, a0); g_hi = std::max(g_hi, a0 + count * 4); g_sum += count * 4;
+                    g_lo = std::min(g_lo, a0); g_hi = std::max(g_hi, a0 + count * 4); g_sum += count * 4; ++g_cnt;
                 };
                 span(Ls[i].gW, (size_t)lv.N * lv.K); span(Ls[i].gb, lv.N);
                 if (i < n - 1) { span(Ls[i].ggamma, lv.N); span(Ls[i].gbeta, lv.N); }
@@ -553,7 +578,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         // split-K outputs start from zero: the pre-activation buffers (contiguous) and, when ALL gradient tensors
         // tile one flat buffer exactly (they do in the Python layer), that buffer -- two memsets instead of one per GEMM
         MMAD_CUDA_OK(cudaMemsetAsync(ws + p.pre_all, 0, p.pre_bytes, s));
-        if (g_hi - g_lo == g_sum) {      // the gradient tensors tile one buffer exactly (no foreign bytes in between)
+        if (g_hi - g_lo <= g_sum + 12 * (size_t)g_cnt) {      // the gradient tensors tile one buffer (gaps < 16 B are alignment padding)
             MMAD_CUDA_OK(cudaMemsetAsync(reinterpret_cast<void*>(g_lo), 0, g_hi - g_lo, s));
             gw_zeroed = true;
         }

@@ -25,7 +25,8 @@ class Adam(torch.optim.Optimizer):
             for p in ps:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise _lib.MmadError("mmad Adam needs contiguous fp32 CUDA parameters (no CPU path)")
-            n = sum(p.numel() for p in ps)
+            pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731   16-byte aligned slots (vector loads in the kernel)
+            n = sum(pad4(p.numel()) for p in ps)
             dev = ps[0].device
             prev = st
             m = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -36,7 +37,7 @@ class Adam(torch.optim.Optimizer):
                 mp.append(m[off:off + p.numel()])
                 vp.append(v[off:off + p.numel()])
                 self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"] = mp[-1].view_as(p), vp[-1].view_as(p)
-                off += p.numel()
+                off += pad4(p.numel())
             arr = lambda ptrs: (C.c_void_p * len(ptrs))(*ptrs)  # noqa: E731
             st["P"] = arr([p.data_ptr() for p in ps])
             st["M"] = arr([t.data_ptr() for t in mp])

@@ -30,13 +30,14 @@ class TrainState:
     def __init__(self, model):
         self.params = list(model.parameters())
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731   every view starts 16-byte aligned (vector loads in Adam)
+        n = sum(pad4(p.numel()) for p in self.params)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views = []
         off = 0
         for p in self.params:
             self.views.append(self.flat_grad[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += pad4(p.numel())
         self.view_of = {id(p): v for p, v in zip(self.params, self.views)}
         self.ws: Optional[torch.Tensor] = None
         self.ws_batch = 0
