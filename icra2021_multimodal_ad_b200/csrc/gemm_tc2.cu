@@ -78,6 +78,7 @@ struct Tc2Params {
     int tiles_m, tiles_n;     // tiles of 256 x 256
     int tri;
     int band;                 // n-tiles per band of the tile order (see tile_coords)
+    int splits;               // split-K factor (plain epilogue): work item = (tile, split), atomically accumulated
 };
 
 // Tile order: bands of `band` n-tiles, all m inside a band, n fastest.  The pairs running at any moment then cover
@@ -94,7 +95,9 @@ __device__ __forceinline__ void tile_coords(const Tc2Params& p, int t, int& tm, 
     tn = b * p.band + rem % w;
 }
 
-template <int PASSES>
+// A_MN / B_MN: the operand is stored [contraction, M or N] (MN-major smem descriptors, TMA boxes of 64 x 64) -- the
+// training GEMMs dW = g_pre^T . in (both) and dX = g_pre . W (B) on the same row-major tensors as the forward pass.
+template <int PASSES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -119,7 +122,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.tiles_m * p.tiles_n * p.splits;      // work items: tile-major, split fastest
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -143,7 +146,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = pair; t < num_tiles; t += npairs) {
+            for (int w = pair; w < num_tiles; w += npairs) {
+                const int t = w / p.splits, sp = w % p.splits;
                 int tm, tn;
                 tile_coords(p, t, tm, tn);
                 const int n0 = tn * BN;
@@ -151,16 +155,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                 n_eff = (n_eff + 15) & ~15;
                 const int m0 = tm * 256 + (int)rank * BM;                     // this CTA's 128 rows of A
                 const int nb0 = n0 + (int)rank * (n_eff >> 1);                // this CTA's half of the B rows
-                const int kb_lo = p.tri ? n0 / BK : 0;
-                for (int kb = kb_lo; kb < num_kb; ++kb) {
+                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     if (rank == 0) mbar_expect_tx(smem_u32(&full[stage]), 2 * C::kStageBytes);
                     const uint32_t fb = smem_u32(&full[stage]) & kPeerBitMask;
                     uint8_t* st = smem + stage * C::kStageBytes;
-                    tma_load_2d_pair(smem_u32(st), &mapAh, fb, kb * BK, m0);
-                    tma_load_2d_pair(smem_u32(st + A_TILE_BYTES), &mapBh, fb, kb * BK, nb0);
-                    if (PASSES >= 2) tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * BK, m0);
-                    if (PASSES == 3) tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * BK, nb0);
+                    auto load_a = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if (A_MN) {   // [k rows, m contiguous]: two boxes of 64 m x 64 k
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, m0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, m0);
+                        }
+                    };
+                    auto load_b = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, nb0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, nb0);
+                        }
+                    };
+                    load_a(st, &mapAh);
+                    load_b(st + A_TILE_BYTES, &mapBh);
+                    if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_HALF_BYTES, &mapAl);
+                    if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_HALF_BYTES, &mapBl);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -170,41 +190,43 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = pair; t < num_tiles; t += npairs) {
+            for (int w = pair; w < num_tiles; w += npairs) {
+                const int t = w / p.splits, sp = w % p.splits;
                 int tm, tn;
                 tile_coords(p, t, tm, tn);
                 const int n0 = tn * BN;
-                const int kb_lo = p.tri ? n0 / BK : 0;
+                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
-                const uint32_t idesc = make_idesc_pair(n_eff);
+                const uint32_t idesc = make_idesc_pair(n_eff) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16);
                 mbar_wait(smem_u32(&acc_empty[acc]), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = kb_lo; kb < num_kb; ++kb) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&full[stage]), phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t dAh = make_smem_desc<false>(st);
-                    const uint64_t dBh = make_smem_desc<false>(st + A_TILE_BYTES);
-                    const uint64_t dAl = make_smem_desc<false>(st + A_TILE_BYTES + B_HALF_BYTES);
-                    const uint64_t dBl = make_smem_desc<false>(st + 2 * A_TILE_BYTES + B_HALF_BYTES);
+                    const uint64_t dAh = make_smem_desc<A_MN>(st);
+                    const uint64_t dBh = make_smem_desc<B_MN>(st + A_TILE_BYTES);
+                    const uint64_t dAl = make_smem_desc<A_MN>(st + A_TILE_BYTES + B_HALF_BYTES);
+                    const uint64_t dBl = make_smem_desc<B_MN>(st + 2 * A_TILE_BYTES + B_HALF_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        const uint64_t advA = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+                        const uint64_t advB = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
                         if (PASSES == 3) {
-                            umma_f16_pair(d_tmem, dAh + adv, dBl + adv, idesc, ((kb - kb_lo) | k) != 0);
-                            umma_f16_pair(d_tmem, dAl + adv, dBh + adv, idesc, 1);
-                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                            umma_f16_pair(d_tmem, dAh + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16_pair(d_tmem, dAl + advA, dBh + advB, idesc, 1);
+                            umma_f16_pair(d_tmem, dAh + advA, dBh + advB, idesc, 1);
                         } else if (PASSES == 2) {
-                            umma_f16_pair(d_tmem, dAl + adv, dBh + adv, idesc, ((kb - kb_lo) | k) != 0);
-                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+                            umma_f16_pair(d_tmem, dAl + advA, dBh + advB, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16_pair(d_tmem, dAh + advA, dBh + advB, idesc, 1);
                         } else {
-                            umma_f16_pair(d_tmem, dAh + adv, dBh + adv, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16_pair(d_tmem, dAh + advA, dBh + advB, idesc, ((kb - kb_lo) | k) != 0);
                         }
                     }
                     umma_commit_pair(smem_u32(&empty[stage]));
-                    if (kb == num_kb - 1) umma_commit_pair(smem_u32(&acc_full[acc]));
+                    if (kb == kb_hi - 1) umma_commit_pair(smem_u32(&acc_full[acc]));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -218,19 +240,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         float4* stg = s_stage + (warp - 2) * STG_FLOAT4;
         const int col_lo = half * 128, col_hi = col_lo + 128;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = pair; t < num_tiles; t += npairs) {
+        for (int w = pair; w < num_tiles; w += npairs) {
+            const int t = w / p.splits, sp = w % p.splits;
             int tm, tn;
             tile_coords(p, t, tm, tn);
             const int m0 = tm * 256 + (int)rank * BM, n0 = tn * BN;
             asm volatile("bar.sync 1, 256;");
-            epi_stage_vectors<BN>(e, p.N, n0, 0, et, s_mul, s_bias, s_sc, s_sh);
+            epi_stage_vectors<BN>(e, p.N, n0, sp, et, s_mul, s_bias, s_sc, s_sh);
             asm volatile("bar.sync 1, 256;");
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             float sq[4];
-            epi_tile<BN>(e, p.M, p.N, 1, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
+            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even(smem_u32(&acc_empty[acc]));
@@ -261,12 +284,18 @@ int init_tc2() {
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
     g_sms = prop.multiProcessorCount;
-    if (cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<3>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<2>::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::kSmemBytes) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
+    bool ok = true;
+    auto attr = [&](auto kern, int bytes) {
+        ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+    };
+    attr(gemm_tc2_kernel<3, false, false>, Cfg2<3>::kSmemBytes);
+    attr(gemm_tc2_kernel<2, false, false>, Cfg2<2>::kSmemBytes);
+    attr(gemm_tc2_kernel<1, false, false>, Cfg2<1>::kSmemBytes);
+    attr(gemm_tc2_kernel<3, false, true>, Cfg2<3>::kSmemBytes);
+    attr(gemm_tc2_kernel<1, false, true>, Cfg2<1>::kSmemBytes);
+    attr(gemm_tc2_kernel<3, true, true>, Cfg2<3>::kSmemBytes);
+    attr(gemm_tc2_kernel<1, true, true>, Cfg2<1>::kSmemBytes);
+    if (!ok) { cudaGetLastError(); return 0; }
     g_tc2_state = 1;
     return 1;
 }
@@ -279,10 +308,11 @@ int tc2_available() { return init_tc2(); }
 int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s) {
     if (!init_tc2()) { set_error("cta_group::2 GEMM unavailable"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
-    if (A.mn || B.mn || e.plain) { set_error("gemm_tc2: K-major operands and the fused epilogue only"); return MMAD_E_ARG; }
+    if (A.mn && !B.mn) { set_error("gemm_tc2: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
+    if ((A.mn || B.mn) && passes == 2) { set_error("gemm_tc2: the 2-pass mode is instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
     auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
-    if (!al(e.Y, e.ldy, 4) || !al(e.pre, e.ldpre, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) ||
-        !al(e.dout, e.lddout, 4) || !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (e.y_cols % 4) || (e.d_cols % 4)) {
+    if (!(e.plain || al(e.Y, e.ldy, 4)) || !al(e.pre, e.ldpre, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) ||
+        !al(e.dout, e.lddout, 4) || !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (!e.plain && (e.y_cols % 4)) || (e.d_cols % 4)) {
         set_error("gemm_tc2: epilogue buffers must be 16-byte aligned with padded leading dimensions");
         return MMAD_E_ARG;
     }
@@ -294,13 +324,28 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     p.band = 8;
     const int tiles = p.tiles_m * p.tiles_n;
     const int max_pairs = g_sms / 2;
-    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-    if (passes == 3)
-        gemm_tc2_kernel<3><<<grid, NTHREADS, Cfg2<3>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.lo, p, e);
-    else if (passes == 2)
-        gemm_tc2_kernel<2><<<grid, NTHREADS, Cfg2<2>::kSmemBytes, s>>>(A.hi, A.lo, B.hi, B.hi, p, e);
-    else
-        gemm_tc2_kernel<1><<<grid, NTHREADS, Cfg2<1>::kSmemBytes, s>>>(A.hi, A.hi, B.hi, B.hi, p, e);
+    const int num_kb = (K + BK - 1) / BK;
+    p.splits = 1;
+    if (!p.tri && e.plain && e.split_k_ok) {   // split-K when it fills the pairs better (see gemm_tc)
+        long best = (long)((tiles + max_pairs - 1) / max_pairs) * num_kb;
+        for (int sp = 2; sp <= 16 && sp <= num_kb; ++sp) {
+            const long waves = ((long)tiles * sp + max_pairs - 1) / max_pairs;
+            const long cost = waves * ((num_kb + sp - 1) / sp) + waves;
+            if (cost * 10 < best * 9) { best = cost; p.splits = sp; }
+        }
+    }
+    if (p.splits > 1 && !e.pre_zeroed)
+        MMAD_CUDA_OK(cudaMemset2DAsync(e.Y, (size_t)e.ldy * 4, 0, (size_t)N * 4, M, s));
+    const int items = tiles * p.splits;
+    const int grid = 2 * (items < max_pairs ? items : max_pairs);
+#define MMAD_TC2_LAUNCH(P, AM, BMN) \
+    gemm_tc2_kernel<P, AM, BMN><<<grid, NTHREADS, Cfg2<P>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, P == 3 ? B.lo : B.hi, p, e)
+    if (A.mn) { if (passes == 3) MMAD_TC2_LAUNCH(3, true, true); else MMAD_TC2_LAUNCH(1, true, true); }
+    else if (B.mn) { if (passes == 3) MMAD_TC2_LAUNCH(3, false, true); else MMAD_TC2_LAUNCH(1, false, true); }
+    else if (passes == 3) MMAD_TC2_LAUNCH(3, false, false);
+    else if (passes == 2) MMAD_TC2_LAUNCH(2, false, false);
+    else MMAD_TC2_LAUNCH(1, false, false);
+#undef MMAD_TC2_LAUNCH
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

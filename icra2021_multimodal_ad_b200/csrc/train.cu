@@ -524,12 +524,14 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                        bool b_mn, int M, int N, int K, const Epilogue& e, cudaStream_t s) -> int {
         TcOperand A, Bo;
         int rc;
-        if (!a_mn && !b_mn && !e.plain && M >= 2048 && tc2_available()) {      // tall K-major GEMM: CTA pairs
-            rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128);
-            if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128);
-            if (!rc) rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, 128);
-            if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, 128);
+        if (B >= 2048 && tc2_available() && (a_mn ? b_mn : true)) {      // large batch: CTA pairs (3-stage pipeline)
+            if (a_mn) { rc = tc_make_operand_map(&A.hi, Ah, K, M, lda, 64); if (!rc) rc = tc_make_operand_map(&A.lo, Al, K, M, lda, 64); }
+            else { rc = tc_make_operand_map(&A.hi, Ah, M, K, lda, 128); if (!rc) rc = tc_make_operand_map(&A.lo, Al, M, K, lda, 128); }
             if (rc) return rc;
+            if (b_mn) { rc = tc_make_operand_map(&Bo.hi, Bh, K, N, ldb, 64); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, K, N, ldb, 64); }
+            else { rc = tc_make_operand_map(&Bo.hi, Bh, N, K, ldb, 128); if (!rc) rc = tc_make_operand_map(&Bo.lo, Bl, N, K, ldb, 128); }
+            if (rc) return rc;
+            A.mn = a_mn; Bo.mn = b_mn;
             return gemm_tc2(A, Bo, M, N, K, passes, e, s);
         }
         const int bn = gemm_tc_pick_bn(M, N);
