@@ -227,7 +227,8 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
             "ms_per_step": ms_dev, "unit": "samples/s", "algorithmic_tflops": flop / (ms_dev / 1e3) / 1e12,
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
                     "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16"}[precision],
-            "graph": world == 1}
+            "graph": True, "collectives": None if world == 1 else
+            "library-owned NCCL communicator: BatchNorm statistics all-reduced inside the captured step, flat gradient once per step"}
 
 
 def bench_stream(eng, batches=(1, 8, 10, 64), calls=300, warm=50):

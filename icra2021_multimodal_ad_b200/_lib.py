@@ -73,6 +73,12 @@ SIGNATURES = {
     "mmad_auc_prc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "mmad_quantile": (_i, [_vp, _ll, _f, C.POINTER(C.c_float), _vp, _sz, _vp]),
     "mmad_confusion": (_i, [_vp, _vp, _ll, _f, _i, C.POINTER(C.c_longlong), _vp, _sz, _vp]),
+    "mmad_comm_unique_id": (_i, [_vp]),
+    "mmad_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "mmad_comm_destroy": (_i, [_vp]),
+    "mmad_comm_world": (_i, [_vp]),
+    "mmad_comm_allreduce_f32": (_i, [_vp, _vp, _ll, _vp]),
+    "mmad_comm_allreduce_f64": (_i, [_vp, _vp, _ll, _vp]),
     "mmad_multisensory_width": (_i, [_i, _i, _i, _i]),
     "mmad_multisensory_forward": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(FeatureWeights), C.POINTER(C.c_float), _vp, _i, _vp]),
     "mmad_profile_begin": (_i, [_vp]),

@@ -80,6 +80,8 @@ struct mmad_handle {
     cudaStream_t s_capture = nullptr;
     cudaStream_t s_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    void* comm = nullptr;          // ncclComm_t (comm.cu)
+    int comm_world = 1, comm_rank = 0;
     // set for the duration of a call of <= 64 rows: exact-fp32 weight-streaming kernels (gemm_skinny.cu) instead
     // of 128-row tensor-core tiles, whatever the handle's precision mode
     bool skinny = false;
@@ -406,6 +408,9 @@ void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsig
     h->graphs.push_back({key, g, launches});
 }
 
+void handle_comm(mmad_t h, void** comm, int* world) { *comm = h->comm; *world = h->comm_world; }
+void handle_set_comm(mmad_t h, void* comm, int world, int rank) { h->comm = comm; h->comm_world = world; h->comm_rank = rank; }
+
 int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
     if (!h->s_aux) {
         if (cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
@@ -510,6 +515,7 @@ int mmad_create(const mmad_desc_t* d, mmad_t* out) {
 
 int mmad_destroy(mmad_t h) {
     if (!h) return MMAD_OK;
+    mmad_comm_destroy(h);
     for (auto& L : h->enc) free_layer(L);
     for (auto& L : h->dec) free_layer(L);
     cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);

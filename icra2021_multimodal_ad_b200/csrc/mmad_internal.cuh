@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -129,6 +130,11 @@ cudaStream_t handle_capture_stream(mmad_t h);
 void handle_graph_clear(mmad_t h);
 // second stream + fork/join events of a handle (independent branches of a launch sequence); 0 on success
 int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
+
+// NCCL communicator of a handle (comm.cu)
+void handle_comm(mmad_t h, void** comm, int* world);
+void handle_set_comm(mmad_t h, void* comm, int world, int rank);
+int comm_allreduce(mmad_t h, void* d_buf, long long count, bool f64, cudaStream_t s);
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

@@ -503,6 +503,18 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                       float* d_loss, char* ws, mmad_allreduce_fn allreduce, void* allreduce_ctx, cudaStream_t s,
                       cudaStream_t s2, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     bool forked = false;
+    // cross-rank combination of the BatchNorm statistics: caller's hook, or the handle's own NCCL communicator
+    void* comm_p = nullptr; int comm_world = 1;
+    handle_comm(h, &comm_p, &comm_world);
+    const bool dist = allreduce != nullptr || (comm_p && comm_world > 1);
+    auto stats_allreduce = [&](double* buf, long long cnt) -> int {
+        if (allreduce) {
+            const int rc = allreduce(allreduce_ctx, buf, cnt, s);
+            if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
+            return MMAD_OK;
+        }
+        return comm_allreduce(h, buf, cnt, true, s);
+    };
     const int D = d.enc_widths[0];
     const int enc_out = d.enc_widths[d.n_enc], dec_in = d.dec_widths[0];
     const int passes = d.precision == MMAD_PREC_F16X3 ? 3 : 1;
@@ -644,9 +656,9 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* out = (float*)(ws + p.out[m][i]);
                 bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
                 MMAD_LAUNCHED();
-                if (allreduce) {
-                    rc = allreduce(allreduce_ctx, st, 2LL * Np, s);
-                    if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
+                if (dist) {
+                    rc = stats_allreduce(st, 2LL * Np);
+                    if (rc) return rc;
                 }
                 bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
                                                                    L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
@@ -693,15 +705,15 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
                                                                   L.gb, row_slab(B));
             MMAD_LAUNCHED();
-            if (allreduce) {    // parameter gradients from the LOCAL sums, then the statistics are combined
+            if (dist) {    // parameter gradients from the LOCAL sums, then the statistics are combined
                 bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
                 MMAD_LAUNCHED();
-                int rc = allreduce(allreduce_ctx, stb, 2LL * r.Np, s);
-                if (rc) { set_error("allreduce hook failed (%d)", rc); return MMAD_E_STATE; }
+                int rc = stats_allreduce(stb, 2LL * r.Np);
+                if (rc) return rc;
             }
             bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
                                                                  r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
-                                                                 L.gbeta, allreduce ? 0 : 1, row_slab(B));
+                                                                 L.gbeta, dist ? 0 : 1, row_slab(B));
             MMAD_LAUNCHED();
             gpre = Mat{go, goh, gol, p.maxNp};
             gi ^= 1;

@@ -82,7 +82,10 @@ class TrainState:
     def allreduce_callback(self):
         """C callback handed to mmad_train_fwd_bwd: SUM-all-reduce of a BatchNorm statistics slice of
         the workspace over ``self.group`` (NCCL, enqueued on the current stream)."""
-        if self.world <= 1:
+        if self.world <= 1 or getattr(self, "native", False):     # native: the library's own communicator does it
+            if self._cb is None or getattr(self, "_cb_world", 1) != 1:
+                self._cb_world = 1
+                self._cb = None
             if self._cb is None:
                 self._cb = _lib.ALLREDUCE_FN(0)
             return self._cb, None
@@ -118,13 +121,36 @@ def train_state(model) -> TrainState:
     return st
 
 
-def set_data_parallel(model, group=None):
+def set_data_parallel(model, group=None, native: Optional[bool] = None):
     """Make BatchNorm batch statistics global over ``group`` (N-GPU data parallel == 1 GPU on the
-    concatenated batch); gradients are combined by ``allreduce_gradients``."""
+    concatenated batch); gradients are combined by ``allreduce_gradients``.
+
+    native (default: env MMAD_PY_ALLREDUCE != 1): the library opens its own NCCL communicator
+    (``mmad_comm_init``; the unique id travels through ``torch.distributed``) and enqueues the collectives
+    itself, so the data-parallel step is one CUDA-graph replay.  Otherwise ``torch.distributed.all_reduce`` is
+    called back from inside the step (works with any backend)."""
+    import os
     import torch.distributed as dist
     st = train_state(model)
     st.group = group
     st.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    st.native = False
+    if native is None:
+        native = os.environ.get("MMAD_PY_ALLREDUCE", "0") != "1"
+    if st.world > 1 and native and dist.get_backend(group) == "nccl":
+        eng = model.handle_engine()
+        dev = eng.device
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if dist.get_rank(group) == 0:
+            buf = (C.c_ubyte * 128)()
+            check(lib().mmad_comm_unique_id(buf))
+            uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(uid, src=src, group=group)
+        raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        with torch.cuda.device(dev):
+            check(lib().mmad_comm_init(eng._h, raw, dist.get_rank(group), st.world))
+        st.native = True
     return st
 
 
@@ -133,7 +159,13 @@ def allreduce_gradients(model):
     import torch.distributed as dist
     st = train_state(model)
     if st.world > 1:
-        dist.all_reduce(st.flat_grad, group=st.group)
+        if getattr(st, "native", False):
+            eng = model.handle_engine()
+            with torch.cuda.device(eng.device):
+                check(lib().mmad_comm_allreduce_f32(eng._h, st.flat_grad.data_ptr(), st.flat_grad.numel(),
+                                                    torch.cuda.current_stream().cuda_stream))
+        else:
+            dist.all_reduce(st.flat_grad, group=st.group)
 
 
 class _FusedStep(torch.autograd.Function):

@@ -223,6 +223,21 @@ int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads,
                    float* const* h_v, const long long* h_numel, int step, float lr, float beta1,
                    float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- communicator: the exchange steps of the path enqueued by the library itself ----
+ * The reference has no distributed code; these back the data-parallel train step and the sharded NAP fit.
+ * One rank calls mmad_comm_unique_id (ncclGetUniqueId), the 128-byte id is distributed by the host layer's own
+ * rendezvous, every rank calls mmad_comm_init (ncclCommInitRank; collective).  With a communicator of world > 1
+ * installed and allreduce == NULL, mmad_train_fwd_bwd all-reduces the BatchNorm statistics itself (and the step is
+ * still captured into a CUDA graph); mmad_comm_allreduce_* are in-place SUM all-reduces on the given stream
+ * (flat gradient buffer, NAP sums / Gram).  libnccl.so.2 is resolved from the process at run time. */
+#define MMAD_UNIQUE_ID_BYTES 128
+int mmad_comm_unique_id(unsigned char* h_id);
+int mmad_comm_init(mmad_t h, const unsigned char* h_id, int rank, int world);
+int mmad_comm_destroy(mmad_t h);
+int mmad_comm_world(mmad_t h);
+int mmad_comm_allreduce_f32(mmad_t h, float* d_buf, long long count, void* stream);
+int mmad_comm_allreduce_f64(mmad_t h, double* d_buf, long long count, void* stream);
+
 /* ---- multimodal feature extractor in front of the autoencoder ----
  * utils/data_loaders.py:152-229 (HSR_Net.forward) / 601-674 (Multisensory_module.forward): per sample
  * conv stacks on the 32x32 RGB and depth images, broadcast force-torque scalar, two 1-d convolutions on the 13
