@@ -77,6 +77,7 @@ SIGNATURES = {
     "mmad_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mmad_comm_destroy": (_i, [_vp]),
     "mmad_comm_world": (_i, [_vp]),
+    "mmad_comm_set_grad_allreduce": (_i, [_vp, _i]),
     "mmad_comm_allreduce_f32": (_i, [_vp, _vp, _ll, _vp]),
     "mmad_comm_allreduce_f64": (_i, [_vp, _vp, _ll, _vp]),
     "mmad_multisensory_width": (_i, [_i, _i, _i, _i]),

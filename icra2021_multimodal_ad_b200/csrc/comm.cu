@@ -69,6 +69,8 @@ int nccl_ok(int r, const char* what) {
 
 namespace mmad {
 
+void handle_set_grad_allreduce(mmad_t h, bool on);
+
 int comm_allreduce(mmad_t h, void* d_buf, long long count, bool f64, cudaStream_t s) {
     void* comm = nullptr; int world = 1;
     handle_comm(h, &comm, &world);
@@ -118,6 +120,13 @@ int mmad_comm_destroy(mmad_t h) {
         g_nccl.comm_destroy(comm);
     }
     handle_set_comm(h, nullptr, 1, 0);
+    return MMAD_OK;
+}
+
+int mmad_comm_set_grad_allreduce(mmad_t h, int on) {
+    if (!h) { set_error("null handle"); return MMAD_E_ARG; }
+    handle_set_grad_allreduce(h, on != 0);
+    handle_graph_clear(h);
     return MMAD_OK;
 }
 

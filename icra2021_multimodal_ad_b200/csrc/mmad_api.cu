@@ -82,6 +82,7 @@ struct mmad_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void* comm = nullptr;          // ncclComm_t (comm.cu)
     int comm_world = 1, comm_rank = 0;
+    bool grad_allreduce = false;   // mmad_comm_set_grad_allreduce
     // set for the duration of a call of <= 64 rows: exact-fp32 weight-streaming kernels (gemm_skinny.cu) instead
     // of 128-row tensor-core tiles, whatever the handle's precision mode
     bool skinny = false;
@@ -409,6 +410,8 @@ void handle_graph_put(mmad_t h, const std::string& key, cudaGraphExec_t g, unsig
 }
 
 void handle_comm(mmad_t h, void** comm, int* world) { *comm = h->comm; *world = h->comm_world; }
+bool handle_grad_allreduce(mmad_t h) { return h->grad_allreduce; }
+void handle_set_grad_allreduce(mmad_t h, bool on) { h->grad_allreduce = on; }
 void handle_set_comm(mmad_t h, void* comm, int world, int rank) { h->comm = comm; h->comm_world = world; h->comm_rank = rank; }
 
 int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {

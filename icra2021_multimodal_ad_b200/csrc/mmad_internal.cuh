@@ -135,6 +135,7 @@ int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev
 void handle_comm(mmad_t h, void** comm, int* world);
 void handle_set_comm(mmad_t h, void* comm, int world, int rank);
 int comm_allreduce(mmad_t h, void* d_buf, long long count, bool f64, cudaStream_t s);
+bool handle_grad_allreduce(mmad_t h);     // all-reduce every layer's gradients inside the train step
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,

@@ -679,6 +679,25 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             MMAD_LAUNCHED();
         }
     }
+    // Data parallel with the handle's communicator: every layer's gradients (W, b, gamma, beta -- contiguous in a flat
+    // gradient buffer) are all-reduced right behind its dW GEMM on the second stream, overlapping the rest of backward.
+    const bool grad_ar = !allreduce && comm_p && comm_world > 1 && handle_grad_allreduce(h);
+    auto layer_grad_allreduce = [&](const mmad_train_layer_t& L, const Ref& r, cudaStream_t st) -> int {
+        const float* ptrs[4] = {L.gW, L.gb, r.bn ? L.ggamma : nullptr, r.bn ? L.gbeta : nullptr};
+        const size_t cnts[4] = {(size_t)r.N * r.K, (size_t)r.N, (size_t)r.N, (size_t)r.N};
+        uintptr_t lo = ~(uintptr_t)0, hi = 0; size_t sum = 0; int n = 0;
+        for (int i = 0; i < 4; ++i) if (ptrs[i]) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptrs[i]);
+            lo = std::min(lo, a0); hi = std::max(hi, a0 + cnts[i] * 4); sum += cnts[i] * 4; ++n;
+        }
+        if (hi - lo <= sum + 12 * (size_t)n)      // one contiguous block (alignment padding only)
+            return comm_allreduce(h, reinterpret_cast<void*>(lo), (long long)((hi - lo) / 4), false, st);
+        for (int i = 0; i < 4; ++i) if (ptrs[i]) {
+            const int rc = comm_allreduce(h, const_cast<float*>(ptrs[i]), (long long)cnts[i], false, st);
+            if (rc) return rc;
+        }
+        return MMAD_OK;
+    };
     // ------------------------------- backward -------------------------------
     // g (ping) holds d = xhat - x in fp32 (and 2 d GS as twins); dL/dxhat = 2 d enters through gscale
     int gi = 0;
@@ -739,6 +758,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                     forked = true;
                 }
                 rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e, sw);
+                if (!rc && grad_ar) rc = layer_grad_allreduce(L, r, sw);
             } else {
                 GemmShape g;
                 g.M = r.N; g.N = r.K; g.K = B;
@@ -746,6 +766,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 g.B = r.in.f; g.ldb = r.in.ld; g.transB = true;
                 e.acc_scale = gemm_scale;
                 rc = gemm_simt(g, e, s);
+                if (!rc && grad_ar) rc = layer_grad_allreduce(L, r, s);
             }
             if (rc) return rc;
         }

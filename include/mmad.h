@@ -235,6 +235,9 @@ int mmad_comm_unique_id(unsigned char* h_id);
 int mmad_comm_init(mmad_t h, const unsigned char* h_id, int rank, int world);
 int mmad_comm_destroy(mmad_t h);
 int mmad_comm_world(mmad_t h);
+/* on: mmad_train_fwd_bwd also SUM-all-reduces every layer's gradients (W, b, gamma, beta) right behind that layer's
+ * weight-gradient GEMM on its second stream, overlapping the rest of the backward pass (needs a communicator). */
+int mmad_comm_set_grad_allreduce(mmad_t h, int on);
 int mmad_comm_allreduce_f32(mmad_t h, float* d_buf, long long count, void* stream);
 int mmad_comm_allreduce_f64(mmad_t h, double* d_buf, long long count, void* stream);
 
