@@ -88,3 +88,16 @@ def test_layer_range_clamp_matches_reference():
                 exp = list(range(n))[a:b]
                 l2, h2 = clamp_layer_range(n, lo, hi)
                 assert list(range(l2, h2)) == exp or (exp == [] and h2 <= l2)
+
+
+def test_communicator_entry_points_without_gpu():
+    """The library resolves libnccl from the process (torch ships it): a unique id can be produced on a CPU-only
+    machine; argument errors are reported without touching a device."""
+    L = _lib.lib()
+    buf = (ctypes.c_ubyte * 128)()
+    assert L.mmad_comm_unique_id(buf) == 0
+    assert any(bytes(buf))
+    assert L.mmad_comm_unique_id(None) == -1
+    assert L.mmad_comm_world(None) == 1
+    assert L.mmad_comm_init(None, buf, 0, 1) == -1
+    assert L.mmad_comm_allreduce_f32(None, None, 4, None) == -1
