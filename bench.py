@@ -30,6 +30,8 @@ MAC_ENC = sum(a * b for a, b in zip(W_ENC[:-1], W_ENC[1:]))
 FLOP_SAP = 2 * 3 * MAC_ENC         # enc(x) + dec + enc(xhat): 30 605 754 per window
 FLOP_NAP_ROT = 2 * DPRIME * DPRIME  # rotation (d-mu) V: 60 104 648 per window
 N_FIT = 8192                       # NAP fit set (>= D' so K = D')
+DTYPE_NAME = {"fp32": "f32", "f16x3": "f16x3 split (fp32-equivalent)", "f16": "f16",
+              "f16f8": "f16 + fp8(e4m3) cross terms (fp32 accumulate; scores within 1e-4 of fp32)"}
 
 
 def parse():
@@ -226,7 +228,7 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
     return {"metric": "VIB-AE train samples/sec" if vib else "AE train samples/sec", "batch_per_gpu": batch, "value": world * batch / (ms_dev / 1e3),
             "ms_per_step": ms_dev, "unit": "samples/s", "algorithmic_tflops": flop / (ms_dev / 1e3) / 1e12,
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
-                    "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16"}[precision],
+                    "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16", "f16f8": "tcgen05 f16x3 split"}[precision],
             "graph": True, "collectives": None if world == 1 else
             "library-owned NCCL communicator: BatchNorm statistics all-reduced inside the captured step, flat gradient once per step"}
 
@@ -348,7 +350,9 @@ def main():
         pass
     # what the tensor pipe actually executes per window in this mode: 3 (f16x3) or 1 MMA per chain product, and the
     # triangular NAP factor's half of the rotation products
-    mma_passes = 3 if precision == "f16x3" else 1
+    # tensor work per product in fp16-pass units: f16x3 three fp16 MMAs; f16f8 one fp16 MMA + one fp8 MMA over twice the
+    # contraction length at twice the rate (= one more unit)
+    mma_passes = {"f16x3": 3, "f16f8": 2}.get(precision, 1)
     executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT / 2 if want_nap else 0))
     executed_tf = value / world * executed_per_window / 1e12 if precision != "fp32" else None
     pipe_pct = None
@@ -370,8 +374,9 @@ def main():
                 "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / args.steps),
                 "executed_mma_tflops": executed_tf, "executed_frac_of_peak": executed_tf / peak_tf if executed_tf and peak_tf else None,
                 "ncu_tensor_pipe_active_pct": pipe_pct,
-                "note": "achieved counts ONE product per MAC of the reference's dense algorithm; f16x3 issues 3 MMAs per product "
-                        "(cap = peak/3 for dense work) and the triangular NAP factor executes half of the rotation"}
+                "note": "achieved counts ONE product per MAC of the reference's dense algorithm; f16x3 issues 3 fp16 MMAs per product "
+                        "(cap = peak/3 for dense work), f16f8 one fp16 + one double-length fp8 MMA (= 2 fp16-pass units, cap = peak/2); "
+                        "the triangular NAP factor executes half of the rotation"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host input, scores back on host) ----
     xh_np = x_host.numpy()
@@ -404,8 +409,7 @@ def main():
         flop_per_window = FLOP_SAP + (FLOP_NAP_ROT if want_nap else 0)
         line = {"metric": "anomaly-scored samples/sec (SAP+NAP)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "f16x3": "f16x3 split (fp32-equivalent)",
-                                                                  "f16": "f16"}[precision],
+                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[precision],
                 "data": "synthetic", "config": workload_config(args, precision), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "clocks": clocks,
                 "algorithmic_tflops": value * flop_per_window / 1e12, "nap_fit_s": fit_s}

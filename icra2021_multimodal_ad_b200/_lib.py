@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmad.so")
 
 MMAD_MAX_LAYERS = 16
-PREC = {"fp32": 0, "f16x3": 1, "f16": 2}
+PREC = {"fp32": 0, "f16x3": 1, "f16": 2, "f16f8": 3}
 
 
 class MmadError(RuntimeError):

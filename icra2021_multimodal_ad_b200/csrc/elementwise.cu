@@ -1,5 +1,7 @@
 // Small HBM-bound helpers around the GEMM chain: operand packing, score finalisation,
 // NAP statistics.  All are grid-stride / coalesced; none is on the critical path.
+#include <cuda_fp8.h>
+
 #include "mmad_internal.cuh"
 
 namespace mmad {
@@ -11,9 +13,17 @@ __device__ __forceinline__ void split_half(float v, __half& h, __half& l) {
     l = __float2half_rn(v - __half2float(h));
 }
 
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+// fp8 twin bytes of column c of a row (layout: Epilogue::lo_f8)
+__device__ __forceinline__ void store_f8_twin1(uint8_t* row, int c, float v, float residual) {
+    uint8_t* q = row + (c >> 2) * 8 + (c & 3);
+    q[0] = to_e4m3(residual * kF8LoScale);
+    q[4] = to_e4m3(v);
+}
+
 // x [n, D] (row stride ldx) -> zero-padded fp32 [n, ldp] and/or fp16 hi/lo [n, ldh]
 __global__ void pad_split_kernel(const float* __restrict__ x, int ldx, int n, int D, float* __restrict__ xp, int ldp,
-                                 __half* __restrict__ xh, __half* __restrict__ xl, int ldh) {
+                                 __half* __restrict__ xh, __half* __restrict__ xl, int ldh, int lo_f8) {
     const int cols = xp ? ldp : ldh;
     const size_t total = (size_t)n * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -24,7 +34,8 @@ __global__ void pad_split_kernel(const float* __restrict__ x, int ldx, int n, in
             __half h, l;
             split_half(v, h, l);
             xh[(size_t)r * ldh + c] = h;
-            if (xl) xl[(size_t)r * ldh + c] = l;
+            if (xl && lo_f8) store_f8_twin1(reinterpret_cast<uint8_t*>(xl) + (size_t)r * ldh * 2, c, v, v - __half2float(h));
+            else if (xl) xl[(size_t)r * ldh + c] = l;
         }
     }
 }
@@ -32,7 +43,7 @@ __global__ void pad_split_kernel(const float* __restrict__ x, int ldx, int n, in
 // same, four columns per thread (16-byte loads, 8-byte fp16 stores): needs ldx % 4 == 0, x 16-byte aligned,
 // padded widths multiples of 4
 __global__ void pad_split_vec4_kernel(const float* __restrict__ x, int ldx, int n, int D, float* __restrict__ xp, int ldp,
-                                      __half* __restrict__ xh, __half* __restrict__ xl, int ldh) {
+                                      __half* __restrict__ xh, __half* __restrict__ xl, int ldh, int lo_f8) {
     const int cols4 = (xp ? ldp : ldh) >> 2;
     const size_t total = (size_t)n * cols4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -52,7 +63,16 @@ __global__ void pad_split_vec4_kernel(const float* __restrict__ x, int ldx, int 
             uint2 hv;
             hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
             *reinterpret_cast<uint2*>(xh + (size_t)r * ldh + c) = hv;
-            if (xl) {
+            if (xl && lo_f8) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                uint8_t* q = reinterpret_cast<uint8_t*>(xl) + (size_t)r * ldh * 2 + 2 * c;
+                const float ls = kF8LoScale;
+                const uint32_t r01 = __nv_cvt_float2_to_fp8x2(make_float2((v.x - f01.x) * ls, (v.y - f01.y) * ls), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t r23 = __nv_cvt_float2_to_fp8x2(make_float2((v.z - f23.x) * ls, (v.w - f23.y) * ls), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t a01 = __nv_cvt_float2_to_fp8x2(make_float2(v.x, v.y), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t a23 = __nv_cvt_float2_to_fp8x2(make_float2(v.z, v.w), __NV_SATFINITE, __NV_E4M3);
+                *reinterpret_cast<uint2*>(q) = make_uint2(r01 | (r23 << 16), a01 | (a23 << 16));
+            } else if (xl) {
                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                 const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
                 uint2 lv;
@@ -74,6 +94,41 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, 
         split_half(v, h, l);
         Wh[i] = h;
         Wl[i] = l;
+    }
+}
+
+// MMAD_PREC_F16F8 weight twins ------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ W, int N, int K, int ldw, unsigned int* __restrict__ out) {
+    const size_t total = (size_t)N * K;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(W[(i / K) * ldw + (i % K)]);
+        if (v < 3.0e38f) m = fmaxf(m, v);      // NaN / inf do not set the scale
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bits
+}
+// scale = the power of two that puts max|W| * scale in [2^13, 2^14): fp16 hi parts below 16384, residuals |Wl| <= 4,
+// Wh / 2^11 <= 8 -- all inside e4m3's normal range for the weights that matter
+__global__ void pick_pow2_scale_kernel(const unsigned int* amax, float* scale) {
+    const float m = __uint_as_float(*amax);
+    int ex = 0;
+    if (m > 0.f) frexpf(m, &ex);             // m = f * 2^ex, f in [0.5, 1)
+    *scale = m > 0.f ? exp2f((float)(14 - ex)) : 1.f;
+}
+__global__ void split_weights_f8_kernel(const float* __restrict__ W, int N, int K, int ldw, int Kp, const float* __restrict__ scale,
+                                        __half* __restrict__ Wh, uint8_t* __restrict__ W8) {
+    const size_t total = (size_t)N * Kp;
+    const float sc = *scale;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Kp), c = (int)(i % Kp);
+        const float v = c < K ? W[(size_t)r * ldw + c] * sc : 0.f;
+        const __half h = __float2half_rn(v);
+        const float hf = __half2float(h);
+        Wh[i] = h;
+        uint8_t* q = W8 + (size_t)r * Kp * 2 + (c >> 2) * 8 + (c & 3);
+        q[0] = to_e4m3(hf * (1.f / kF8LoScale));
+        q[4] = to_e4m3(v - hf);
     }
 }
 
@@ -326,13 +381,13 @@ inline int grid_for(size_t total, int block = 256) {
 }  // namespace
 
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,
-              cudaStream_t s) {
+              cudaStream_t s, int lo_f8) {
     if (n <= 0) return MMAD_OK;
     size_t total = (size_t)n * (xp ? ldp : ldh);
     const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldp % 4 == 0) && (ldh % 4 == 0) &&
                      (!xp || !xh || ldp == ldh);
-    if (vec) pad_split_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh);
-    else pad_split_kernel<<<grid_for(total), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh);
+    if (vec) pad_split_vec4_kernel<<<grid_for(total / 4), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh, lo_f8);
+    else pad_split_kernel<<<grid_for(total), 256, 0, s>>>(x, ldx, n, D, xp, ldp, xh, xl, ldh, lo_f8);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
@@ -340,6 +395,20 @@ int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half*
 
 int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s) {
     split_weights_kernel<<<grid_for((size_t)N * Kp), 256, 0, s>>>(W, N, K, Kp, scale, Wh, Wl);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int split_weights_f8(const float* W, int N, int K, int ldw, int Kp, __half* Wh, uint8_t* W8, float* d_scale, cudaStream_t s) {
+    // d_scale doubles as the atomicMax cell of the first pass (two floats: [scale, amax bits])
+    unsigned int* amax = reinterpret_cast<unsigned int*>(d_scale) + 1;
+    MMAD_CUDA_OK(cudaMemsetAsync(amax, 0, 4, s));
+    absmax_kernel<<<grid_for((size_t)N * K), 256, 0, s>>>(W, N, K, ldw, amax);
+    MMAD_LAUNCHED();
+    pick_pow2_scale_kernel<<<1, 1, 0, s>>>(amax, d_scale);
+    MMAD_LAUNCHED();
+    split_weights_f8_kernel<<<grid_for((size_t)N * Kp), 256, 0, s>>>(W, N, K, ldw, Kp, d_scale, Wh, W8);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

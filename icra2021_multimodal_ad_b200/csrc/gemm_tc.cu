@@ -69,7 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
         if (PASSES >= 2) tma_prefetch_desc(&mapAl);
-        if (PASSES == 3) tma_prefetch_desc(&mapBl);
+        if (PASSES >= 3) tma_prefetch_desc(&mapBl);
     }
     if (warp == 1) {   // TMEM allocation is a warp-wide operation; the same warp frees it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
@@ -111,8 +111,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                     };
                     load_a(st, &mapAh);
                     load_b(st + A_TILE_BYTES, &mapBh);
-                    if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_TILE_BYTES, &mapAl);
-                    if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
+                    if (PASSES == 4) {   // fp8 twins: byte maps, one 128-byte block per k-block
+                        tma_load_2d(smem_u32(st + A_TILE_BYTES + B_TILE_BYTES), &mapAl, fb, kb * 128, m0);
+                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + B_TILE_BYTES), &mapBl, fb, kb * 128, n0);
+                    } else {
+                        if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_TILE_BYTES, &mapAl);
+                        if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,7 +150,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         // K step of 16: 32 B inside the swizzle row (K-major) or 16 rows of 128 B (MN-major), 16-byte units
                         const uint64_t advA = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
                         const uint64_t advB = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-                        if (PASSES == 3) {
+                        if (PASSES == 4) {   // the fp8 pass covers 32 bytes of the twin per instruction too
+                            umma_f8(d_tmem, dAl + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, 1);
+                        } else if (PASSES == 3) {
                             umma_f16(d_tmem, dAh + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16(d_tmem, dAl + advA, dBh + advB, idesc, 1);
                             umma_f16(d_tmem, dAh + advA, dBh + advB, idesc, 1);
@@ -183,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            float sq[4];
+            float sq[8];
             epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
@@ -233,7 +241,7 @@ int init_tc() {
 #define MMAD_TC_ATTR(P, AM, BMN)                                             \
     attr(gemm_tc_kernel<P, AM, BMN, 256>, Cfg<P, 256>::kSmemBytes);           \
     attr(gemm_tc_kernel<P, AM, BMN, 128>, Cfg<P, 128>::kSmemBytes)
-    MMAD_TC_ATTR(3, false, false); MMAD_TC_ATTR(1, false, false); MMAD_TC_ATTR(2, false, false);
+    MMAD_TC_ATTR(3, false, false); MMAD_TC_ATTR(1, false, false); MMAD_TC_ATTR(2, false, false); MMAD_TC_ATTR(4, false, false);
     MMAD_TC_ATTR(3, false, true);  MMAD_TC_ATTR(1, false, true);
     MMAD_TC_ATTR(3, true, true);   MMAD_TC_ATTR(1, true, true);
 #undef MMAD_TC_ATTR
@@ -275,6 +283,20 @@ int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int k, i
     return MMAD_OK;
 }
 
+int tc_make_operand_map_f8(CUtensorMap* map, const void* base, int rows, int k, int ld_bytes, int box_rows) {
+    if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_bytes % 16)) { set_error("TMA operand must be 16-byte aligned (ld=%d bytes)", ld_bytes); return MMAD_E_ARG; }
+    cuuint64_t dims[2] = {(cuuint64_t)2 * ((k + BK - 1) / BK * BK), (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_bytes};
+    cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp8 twin) failed (%d) rows=%d k=%d ld=%d", (int)r, rows, k, ld_bytes); return MMAD_E_CUDA; }
+    return MMAD_OK;
+}
+
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s, int bn) {
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
@@ -310,15 +332,16 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     if (A.mn && !B.mn) { set_error("gemm_tc: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
 #define MMAD_TC_LAUNCH2(P, AM, BMN, BNV)                                                                              \
     gemm_tc_kernel<P, AM, BMN, BNV><<<grid, NTHREADS, Cfg<P, BNV>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, \
-                                                                                   P == 3 ? B.lo : B.hi, p, e)
+                                                                                   P >= 3 ? B.lo : B.hi, p, e)
 #define MMAD_TC_LAUNCH(P, AM, BMN)                  \
     do {                                            \
         if (bn == 256) MMAD_TC_LAUNCH2(P, AM, BMN, 256); \
         else MMAD_TC_LAUNCH2(P, AM, BMN, 128);      \
     } while (0)
-    if (passes == 2) {
-        if (A.mn || B.mn) { set_error("gemm_tc: the 2-pass mode is instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
-        MMAD_TC_LAUNCH(2, false, false);
+    if (passes == 2 || passes == 4) {
+        if (A.mn || B.mn) { set_error("gemm_tc: the 2-pass and fp8-assisted modes are instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
+        if (passes == 4) MMAD_TC_LAUNCH(4, false, false);
+        else MMAD_TC_LAUNCH(2, false, false);
     } else if (passes == 3) {
         if (A.mn) MMAD_TC_LAUNCH(3, true, true);
         else if (B.mn) MMAD_TC_LAUNCH(3, false, true);

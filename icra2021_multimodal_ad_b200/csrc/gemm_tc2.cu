@@ -32,9 +32,11 @@ constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;   // 16 KB
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
 // PASSES: 3 = hi*lo + lo*hi + hi*hi (fp32-equivalent products); 2 = lo*hi + hi*hi (A exact, B rounded to fp16:
-// the NAP rotation, whose B rows are unit-max whitening vectors); 1 = hi*hi
+// the NAP rotation, whose B rows are unit-max whitening vectors); 1 = hi*hi;
+// 4 = hi*hi in fp16 + one fp8 pass over the twins [lo8 | a8] . [Wh8 ; Wl8] (MMAD_PREC_F16F8): per k-block four
+// kind::f16 and four kind::f8f6f4 instructions into the same fp32 accumulator, against twelve kind::f16 in mode 3
 template <int PASSES> struct Cfg2 {
-    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES == 3 ? 2 : 1) * B_HALF_BYTES;   // 64 / 48 / 32 KB per CTA
+    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES >= 3 ? 2 : 1) * B_HALF_BYTES;   // 64 / 48 / 32 KB per CTA
     static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 3 / 4 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;
     static constexpr int kSmemBytes = kSmemTiles + 4 * BN2 * 4 + EPI_WARPS * STG_FLOAT4 * 16 + 256 + 1024;
@@ -58,6 +60,13 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
@@ -130,7 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         fence_barrier_init();
         tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapBh);
         if (PASSES >= 2) tma_prefetch_desc(&mapAl);
-        if (PASSES == 3) tma_prefetch_desc(&mapBl);
+        if (PASSES >= 3) tma_prefetch_desc(&mapBl);
     }
     if (warp == 1) {   // the same logical warp of both CTAs allocates (and later frees) the pair's TMEM
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
@@ -179,8 +188,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                     };
                     load_a(st, &mapAh);
                     load_b(st + A_TILE_BYTES, &mapBh);
-                    if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_HALF_BYTES, &mapAl);
-                    if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_HALF_BYTES, &mapBl);
+                    if (PASSES == 4) {   // fp8 twins: byte maps, one 128-byte block per k-block
+                        tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * 128, m0);
+                        tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * 128, nb0);
+                    } else {
+                        if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_HALF_BYTES, &mapAl);
+                        if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_HALF_BYTES, &mapBl);
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -214,7 +228,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t advA = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
                         const uint64_t advB = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-                        if (PASSES == 3) {
+                        if (PASSES == 4) {
+                            umma_f8_pair(d_tmem, dAl + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
+                            umma_f16_pair(d_tmem, dAh + advA, dBh + advB, idesc, 1);
+                        } else if (PASSES == 3) {
                             umma_f16_pair(d_tmem, dAh + advA, dBl + advB, idesc, ((kb - kb_lo) | k) != 0);
                             umma_f16_pair(d_tmem, dAl + advA, dBh + advB, idesc, 1);
                             umma_f16_pair(d_tmem, dAh + advA, dBh + advB, idesc, 1);
@@ -252,7 +269,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             tc_fence_after();
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            float sq[4];
+            float sq[8];
             epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             tc_fence_before();
             __syncwarp();
@@ -289,6 +306,7 @@ int init_tc2() {
         ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
     };
     attr(gemm_tc2_kernel<3, false, false>, Cfg2<3>::kSmemBytes);
+    attr(gemm_tc2_kernel<4, false, false>, Cfg2<4>::kSmemBytes);
     attr(gemm_tc2_kernel<2, false, false>, Cfg2<2>::kSmemBytes);
     attr(gemm_tc2_kernel<1, false, false>, Cfg2<1>::kSmemBytes);
     attr(gemm_tc2_kernel<3, false, true>, Cfg2<3>::kSmemBytes);
@@ -309,7 +327,7 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     if (!init_tc2()) { set_error("cta_group::2 GEMM unavailable"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
     if (A.mn && !B.mn) { set_error("gemm_tc2: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
-    if ((A.mn || B.mn) && passes == 2) { set_error("gemm_tc2: the 2-pass mode is instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
+    if ((A.mn || B.mn) && (passes == 2 || passes == 4)) { set_error("gemm_tc2: the 2-pass and fp8-assisted modes are instantiated for K-major operands only"); return MMAD_E_UNSUPPORTED; }
     auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
     if (!(e.plain || al(e.Y, e.ldy, 4)) || !al(e.pre, e.ldpre, 4) || !al(e.Yh, e.ldh, 8) || !al(e.Yl, e.ldh, 8) || !al(e.ref, e.ldref, 4) ||
         !al(e.dout, e.lddout, 4) || !al(e.Dh, e.lddh, 8) || !al(e.Dl, e.lddh, 8) || (!e.plain && (e.y_cols % 4)) || (e.d_cols % 4)) {
@@ -339,9 +357,10 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     const int items = tiles * p.splits;
     const int grid = 2 * (items < max_pairs ? items : max_pairs);
 #define MMAD_TC2_LAUNCH(P, AM, BMN) \
-    gemm_tc2_kernel<P, AM, BMN><<<grid, NTHREADS, Cfg2<P>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, P == 3 ? B.lo : B.hi, p, e)
+    gemm_tc2_kernel<P, AM, BMN><<<grid, NTHREADS, Cfg2<P>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, P >= 3 ? B.lo : B.hi, p, e)
     if (A.mn) { if (passes == 3) MMAD_TC2_LAUNCH(3, true, true); else MMAD_TC2_LAUNCH(1, true, true); }
     else if (B.mn) { if (passes == 3) MMAD_TC2_LAUNCH(3, false, true); else MMAD_TC2_LAUNCH(1, false, true); }
+    else if (passes == 4) MMAD_TC2_LAUNCH(4, false, false);
     else if (passes == 3) MMAD_TC2_LAUNCH(3, false, false);
     else if (passes == 2) MMAD_TC2_LAUNCH(2, false, false);
     else MMAD_TC2_LAUNCH(1, false, false);

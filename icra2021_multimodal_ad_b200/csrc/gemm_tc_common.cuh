@@ -1,6 +1,8 @@
 // Shared pieces of the tcgen05 GEMM kernels (gemm_tc.cu: one CTA per tile; gemm_tc2.cu: CTA pairs, cta_group::2):
 // tile constants, PTX wrappers, and the fused epilogue applied to one 32-row x BN-column accumulator slice.
 #pragma once
+#include <cuda_fp8.h>
+
 #include "mmad_internal.cuh"
 
 namespace mmad {
@@ -19,8 +21,9 @@ constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 
 template <int PASSES, int BN> struct Cfg {
     static constexpr int kBTileBytes = BN * BK * 2;            // 32 KB / 16 KB
-    // PASSES 3: A hi+lo, B hi+lo;  2: A hi+lo, B hi (lo*hi + hi*hi);  1: hi only
-    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES == 3 ? 2 : 1) * kBTileBytes;
+    // PASSES 3: A hi+lo, B hi+lo;  2: A hi+lo, B hi (lo*hi + hi*hi);  1: hi only;
+    // 4: fp16 hi*hi + fp8 [lo8 | a8] . [Wh8 ; Wl8] (the fp8 twins take the place of the lo tiles, same bytes)
+    static constexpr int kStageBytes = (PASSES >= 2 ? 2 : 1) * A_TILE_BYTES + (PASSES >= 3 ? 2 : 1) * kBTileBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;   // 2 / 3 / 4 / 6
     static constexpr int kSmemTiles = kStages * kStageBytes;   // <= 192 KB
     static constexpr int kTmemCols = 2 * BN;                   // two fp32 accumulators
@@ -96,6 +99,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// e4m3 x e4m3 -> fp32 (K = 32 per instruction; the instruction descriptor's format fields are 0 = E4M3, so the
+// descriptor value is the one of the fp16 kind)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -148,33 +160,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// four e4m3 values, first in the low byte
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+// fp8 twin of four consecutive columns starting at col (multiple of 4) of a row whose fp16 twin starts at `row`:
+// 8 bytes at byte offset 2 * col = [4 x e4m3(residual * 2^11) | 4 x e4m3(value)]  (one 8-byte store, like the fp16 lo)
+__device__ __forceinline__ void store_f8_twin(uint8_t* row, int col, float v0, float v1, float v2, float v3,
+                                              float r0, float r1, float r2, float r3) {
+    uint2 t;
+    t.x = pack_e4m3x4(r0 * kF8LoScale, r1 * kF8LoScale, r2 * kF8LoScale, r3 * kF8LoScale);
+    t.y = pack_e4m3x4(v0, v1, v2, v3);
+    *reinterpret_cast<uint2*>(row + 2 * col) = t;
+}
+
+// plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]): 16-column pieces,
+// half-warp <-> one row, lane <-> column: two coalesced 64-byte row segments per instruction
 template <int BN>
-__device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
-                                         float4* stg, const float* s_mul, const float* s_bias, const float* s_sc,
-                                         const float* s_sh, int lane, int col_lo, int col_hi, float (&sq)[4]) {
-    const int rsub = lane >> 2;             // 0..7  row inside a group of 8
-    const int cg = lane & 3;                // float4 column group inside the 16-column piece
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sq[i] = 0.f;
-    int n_cols = N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
-    int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
-    int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
-    int c_end = (max(max(n_cols, w_cols), dw_cols) + 15) & ~15;
+__device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
+                                               float4* stg, const float* s_mul, const float* s_bias, int lane, int col_lo,
+                                               int col_hi) {
+    int n_cols = N - n0; if (n_cols > BN) n_cols = BN;
+    int c_end = (n_cols + 15) & ~15;
     if (c_end > col_hi) c_end = col_hi;
     for (int c0 = col_lo; c0 < c_end; c0 += 16) {
-        const int cc = c0 + cg * 4;             // tile-local column of this lane's float4
-        // issue this piece's reference loads first: 4 independent 16-byte loads per lane in flight while the
-        // accumulator piece is fetched from TMEM and transposed
-        float4 rf[4];
-        if (e.ref) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int r = row_base + it * 8 + rsub;
-                rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < M && cc + 3 < n_cols)
-                    rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + cc));
-            }
-        }
         {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
@@ -184,29 +195,56 @@ __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int sp
                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
         __syncwarp();
-        if (e.plain) {
-            // plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]):
-            // half-warp <-> one row, lane <-> column: two coalesced 64-byte row segments per instruction
-            const int c = c0 + (lane & 15);
-            const int gc = n0 + c;
-            const int rpar = lane >> 4;
-            if (gc < N) {
-                const float mulc = s_mul[c], biac = s_bias[c];
-                const float* stf = reinterpret_cast<const float*>(stg);
+        const int c = c0 + (lane & 15);
+        const int gc = n0 + c;
+        const int rpar = lane >> 4;
+        if (gc < N) {
+            const float mulc = s_mul[c], biac = s_bias[c];
+            const float* stf = reinterpret_cast<const float*>(stg);
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int rl = i * 2 + rpar;
-                    const int r = row_base + rl;
-                    const float val = fmaf(stf[stg_slot(rl, (lane & 15) >> 2) * 4 + (lane & 3)], mulc, biac);
-                    if (r < M) {
-                        if (splits > 1) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);   // split-K partial sums
-                        else e.Y[(size_t)r * e.ldy + gc] = val;
-                    }
+            for (int i = 0; i < 16; ++i) {
+                const int rl = i * 2 + rpar;
+                const int r = row_base + rl;
+                const float val = fmaf(stf[stg_slot(rl, (lane & 15) >> 2) * 4 + (lane & 3)], mulc, biac);
+                if (r < M) {
+                    if (splits > 1) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);   // split-K partial sums
+                    else e.Y[(size_t)r * e.ldy + gc] = val;
                 }
             }
-            __syncwarp();
-            continue;
         }
+        __syncwarp();
+    }
+}
+
+// Fused epilogue of one warp's 32 rows x [col_lo, col_hi) slice.  The warp works in 32-column blocks: one tcgen05.ld
+// hands each thread its accumulator ROW (32 columns); the block goes through a 2 KB XOR-swizzled shared tile in two
+// phases of 16 rows and is re-read as (4 rows x 8 float4 columns), so every global access of the warp covers whole
+// 128-byte (fp32) / 64-byte (fp16, fp8 twin) row segments -- half the LSU wavefronts of 16-column pieces, which is what
+// the chain layers are bound by once the MMA work drops to two passes.
+// sq[ph * 4 + it] returns this lane's partial row sum of squares for row row_base + ph*16 + it*4 + lane/8.
+__device__ __forceinline__ int stg_slot32(int row16, int j8) { return row16 * 8 + (j8 ^ (row16 & 7)); }
+
+template <int BN>
+__device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
+                                         float4* stg, const float* s_mul, const float* s_bias, const float* s_sc,
+                                         const float* s_sh, int lane, int col_lo, int col_hi, float (&sq)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq[i] = 0.f;
+    if (e.plain) {
+        epi_tile_plain<BN>(e, M, N, splits, row_base, n0, taddr, stg, s_mul, s_bias, lane, col_lo, col_hi);
+        return;
+    }
+    const int rsub = lane >> 3;             // 0..3  row inside a group of 4
+    const int cg = lane & 7;                // float4 column group inside the 32-column block
+    int n_cols = N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
+    int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
+    int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
+    int c_end = (max(max(n_cols, w_cols), dw_cols) + 31) & ~31;
+    if (c_end > col_hi) c_end = col_hi;
+    for (int c0 = col_lo; c0 < c_end; c0 += 32) {
+        const int cc = c0 + cg * 4;             // tile-local column of this lane's float4
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
         const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
         const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
         const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc);
@@ -215,83 +253,117 @@ __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int sp
         const bool wy = cc < w_cols, wd = cc < dw_cols;   // widths are multiples of 4 (padded to 64)
         const size_t gcol = (size_t)n0 + cc;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int rl = it * 8 + rsub;
-            const int r = row_base + rl;
-            const float4 a = stg[stg_slot(rl, cg)];
-            float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
-            float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
-            if (r < M) {
-                if (e.pre && cc < e.ldpre - n0)     // train: pre-activation, zero padded to ldpre columns
-                    *reinterpret_cast<float4*>(e.pre + (size_t)r * e.ldpre + gcol) =
-                        make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
-                if (e.bn_scale) {
-                    x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
-                    x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
-                    x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
-                    x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
-                }
-                x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
-                if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
-                if (e.Yh && wy) {
-                    const float ys = e.y_split_scale;
-                    const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
-                    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                    uint2 hv;
-                    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                    *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
-                    if (e.Yl) {
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
-                        const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
-                        uint2 lv;
-                        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                        *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
-                    }
-                }
-                if (e.ref) {
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-                    if (k3) {
-                        const float4 f = rf[it];
-                        d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
-                    } else if (k0) {
-                        const float* rp = e.ref + (size_t)r * e.ldref + gcol;
-                        d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
-                    }
-                    sq[it] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq[it]))));
-                    if (e.dout && wd) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + gcol) = make_float4(d0, d1, d2, d3);
-                    if (e.Dh && wd) {
-                        const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
-                        const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
-                        const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
-                        uint2 hv, lv;
-                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                        *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + gcol) = hv;
-                        *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + gcol) = lv;
-                    }
-                } else if (e.sq_self) {
-                    sq[it] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, sq[it]))));
+        for (int ph = 0; ph < 2; ++ph) {
+            // this phase's reference loads first: 4 independent 16-byte loads per lane in flight during the transpose
+            float4 rf[4];
+            if (e.ref) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = row_base + ph * 16 + it * 4 + rsub;
+                    rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < M && cc + 3 < n_cols)
+                        rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + cc));
                 }
             }
+            if ((lane >> 4) == ph) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    stg[stg_slot32(lane & 15, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rl = it * 4 + rsub;
+                const int r = row_base + ph * 16 + rl;
+                const float4 a = stg[stg_slot32(rl, cg)];
+                float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
+                float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
+                if (r < M) {
+                    if (e.pre && cc < e.ldpre - n0)     // train: pre-activation, zero padded to ldpre columns
+                        *reinterpret_cast<float4*>(e.pre + (size_t)r * e.ldpre + gcol) =
+                            make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
+                    if (e.bn_scale) {
+                        x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
+                        x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
+                        x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
+                        x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
+                    }
+                    x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
+                    if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
+                    if (e.Yh && wy) {
+                        const float ys = e.y_split_scale;
+                        const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
+                        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                        uint2 hv;
+                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
+                        if (e.Yl && e.lo_f8) {
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            store_f8_twin(reinterpret_cast<uint8_t*>(e.Yl) + (size_t)r * e.ldh * 2, (int)gcol, y0, y1, y2, y3,
+                                          y0 - f01.x, y1 - f01.y, y2 - f23.x, y3 - f23.y);
+                        } else if (e.Yl) {
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
+                            const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
+                            uint2 lv;
+                            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
+                        }
+                    }
+                    if (e.ref) {
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                        if (k3) {
+                            const float4 f = rf[it];
+                            d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
+                        } else if (k0) {
+                            const float* rp = e.ref + (size_t)r * e.ldref + gcol;
+                            d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
+                        }
+                        float& acc = sq[ph * 4 + it];
+                        acc = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, acc))));
+                        if (e.dout && wd) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + gcol) = make_float4(d0, d1, d2, d3);
+                        if (e.Dh && wd) {
+                            const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
+                            const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            uint2 hv;
+                            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + gcol) = hv;
+                            if (e.lo_f8) {
+                                store_f8_twin(reinterpret_cast<uint8_t*>(e.Dl) + (size_t)r * e.lddh * 2, (int)gcol, s0, s1, s2, s3,
+                                              s0 - f01.x, s1 - f01.y, s2 - f23.x, s3 - f23.y);
+                            } else {
+                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
+                                const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                                uint2 lv;
+                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                                *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + gcol) = lv;
+                            }
+                        }
+                    } else if (e.sq_self) {
+                        float& acc = sq[ph * 4 + it];
+                        acc = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, acc))));
+                    }
+                }
+            }
+            __syncwarp();     // the staging tile is rewritten by the next phase
         }
-        __syncwarp();     // the staging tile is rewritten by the next piece
     }
 }
 
 // row partial sums of squares of this warp's column half: slot = 128-column block index
-__device__ __forceinline__ void epi_rowpart(const Epilogue& e, int M, int row_base, int slot, int lane, const float (&sq)[4]) {
+__device__ __forceinline__ void epi_rowpart(const Epilogue& e, int M, int row_base, int slot, int lane, const float (&sq)[8]) {
     if (!e.rowpart) return;
-    const int rsub = lane >> 2;
+    const int rsub = lane >> 3;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        float v = sq[it];
+    for (int i = 0; i < 8; ++i) {
+        float v = sq[i];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        const int r = row_base + it * 8 + rsub;
-        if ((lane & 3) == 0 && r < M) e.rowpart[(size_t)slot * e.rowpart_stride + r] = v;
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const int r = row_base + (i >> 2) * 16 + (i & 3) * 4 + rsub;
+        if ((lane & 7) == 0 && r < M) e.rowpart[(size_t)slot * e.rowpart_stride + r] = v;
     }
 }
 

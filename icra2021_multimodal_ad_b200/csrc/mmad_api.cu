@@ -35,6 +35,12 @@ struct Layer {
     TcOperand tcB;            // box 64 x 256: one CTA per 128 x 256 tile
     TcOperand tcB2;           // box 64 x 128: CTA pairs, each CTA stages half of the tile's weight rows
     bool tc_ready = false;
+    // MMAD_PREC_F16F8 twins: fp16 hi of W * wscale8 and the fp8 block twin [Wh8 | Wl8] (elementwise.cu:split_weights_f8)
+    __half* Wh8 = nullptr;    // [N, Kp]
+    uint8_t* W8 = nullptr;    // [N, 2 * Kp] bytes
+    float* d_wscale8 = nullptr;   // device: [scale, amax bits]
+    float wscale8 = 1.f;
+    TcOperand tcB_f8, tcB2_f8;    // .hi over Wh8, .lo (byte map) over W8
 };
 
 struct NapFit {
@@ -50,6 +56,11 @@ struct NapFit {
     __half* Bl = nullptr;
     TcOperand tcB, tcB2;
     bool tc_ready = false;
+    __half* Bh8 = nullptr;      // MMAD_PREC_F16F8 twins of B (see Layer)
+    uint8_t* B8 = nullptr;
+    float* d_wscale8 = nullptr;
+    float wscale8 = 1.f;
+    TcOperand tcB_f8, tcB2_f8;
 };
 
 }  // namespace mmad
@@ -107,6 +118,7 @@ static int host_chunk() { return wave_rows(); }        // rows per pipelined hos
 constexpr int kPairMinRows = 2048;    // chunks at least this tall run on CTA pairs (gemm_tc2.cu)
 constexpr int kStreamRows = 2048;     // host calls up to this many rows take the graph-replay latency path
 constexpr float kDiffScale = 1024.f;   // diffs are scaled by 2^10 before the fp16 hi/lo split
+constexpr float kDiffScaleF8 = 16.f;   // MMAD_PREC_F16F8: e4m3(d * scale) must stay below 448
 
 static int D_of(mmad_t h) { return h->desc.enc_widths[0]; }
 static int width_of_diff(mmad_t h, int l) { return h->desc.enc_widths[l]; }   // d_0 has width D, d_l width w_l
@@ -132,6 +144,7 @@ static SegMap make_segmap(mmad_t h, int lo, int hi) {
 
 static void free_layer(Layer& L) {
     cudaFree(L.W); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); cudaFree(L.Wh); cudaFree(L.Wl);
+    cudaFree(L.Wh8); cudaFree(L.W8); cudaFree(L.d_wscale8);
     L = Layer();
 }
 
@@ -177,6 +190,29 @@ static int nap_passes() {
 }
 
 static bool use_tc(mmad_t h) { return h->desc.precision != MMAD_PREC_FP32 && !h->skinny; }
+static bool f8_mode(mmad_t h) { return h->desc.precision == MMAD_PREC_F16F8 && !h->skinny; }
+static float diff_scale(mmad_t h) { return f8_mode(h) ? kDiffScaleF8 : kDiffScale; }
+static int tc_passes(mmad_t h) {
+    return h->desc.precision == MMAD_PREC_F16X3 ? 3 : h->desc.precision == MMAD_PREC_F16F8 ? 4 : 1;
+}
+
+// fp8-assisted twins of a weight matrix W [N, K] (row stride ldw): allocation, packing, TMA maps
+static int make_f8_twins(const float* W, int N, int K, int ldw, int Kp, __half** Wh8, uint8_t** W8, float** d_scale, float* scale,
+                         TcOperand* tcB, TcOperand* tcB2, cudaStream_t s) {
+    if (!*Wh8) MMAD_CUDA_OK(cudaMalloc(Wh8, (size_t)N * Kp * 2));
+    if (!*W8) MMAD_CUDA_OK(cudaMalloc(W8, (size_t)N * Kp * 2));
+    if (!*d_scale) MMAD_CUDA_OK(cudaMalloc(d_scale, 8));
+    int rc = split_weights_f8(W, N, K, ldw, Kp, *Wh8, *W8, *d_scale, s);
+    if (rc) return rc;
+    MMAD_CUDA_OK(cudaMemcpyAsync(scale, *d_scale, 4, cudaMemcpyDeviceToHost, s));
+    MMAD_CUDA_OK(cudaStreamSynchronize(s));
+    rc = tc_make_operand_map(&tcB->hi, *Wh8, N, K, Kp, gemm_tc_tile_n());
+    if (!rc) rc = tc_make_operand_map_f8(&tcB->lo, *W8, N, K, Kp * 2, gemm_tc_tile_n());
+    if (!rc) rc = tc_make_operand_map(&tcB2->hi, *Wh8, N, K, Kp, 128);
+    if (!rc) rc = tc_make_operand_map_f8(&tcB2->lo, *W8, N, K, Kp * 2, 128);
+    tcB->rows = tcB2->rows = N; tcB->k = tcB2->k = K;
+    return rc;
+}
 
 static int tile_n_for(mmad_t h) {
     if (h->skinny) return gemm_skinny_tile_n();
@@ -278,15 +314,18 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     }
     // tensor-core path: TMA descriptors over the fp16 hi/lo twins
     TcOperand A;
+    const bool f8 = f8_mode(h);
     int rc = tc_make_operand_map(&A.hi, in.h, rows, Lr.K, in.ldh, 128);
     if (rc) return rc;
-    rc = tc_make_operand_map(&A.lo, in.l ? in.l : in.h, rows, Lr.K, in.ldh, 128);
+    if (f8) rc = tc_make_operand_map_f8(&A.lo, in.l, rows, Lr.K, in.ldh * 2, 128);
+    else rc = tc_make_operand_map(&A.lo, in.l ? in.l : in.h, rows, Lr.K, in.ldh, 128);
     if (rc) return rc;
     A.rows = rows; A.k = Lr.K;
-    e.acc_scale = 1.f / Lr.wscale;
-    const int passes = h->desc.precision == MMAD_PREC_F16X3 ? 3 : 1;
-    if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
-    return gemm_tc(A, Lr.tcB, rows, Lr.N, Lr.K, passes, e, s);
+    e.acc_scale = 1.f / (f8 ? Lr.wscale8 : Lr.wscale);
+    e.lo_f8 = f8 ? 1 : 0;
+    const int passes = tc_passes(h);
+    if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, f8 ? Lr.tcB2_f8 : Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
+    return gemm_tc(A, f8 ? Lr.tcB_f8 : Lr.tcB, rows, Lr.N, Lr.K, passes, e, s);
 }
 
 // What a chain invocation should produce for one chunk.
@@ -312,7 +351,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         a0.f = x; a0.ld = ldx;
     } else {
         int rc = pad_split(x, ldx, rows, D, (tc && x_aligned) ? nullptr : (float*)(ws + p.xp), Dp, tc ? (__half*)(ws + p.xh) : nullptr,
-                           tc ? (__half*)(ws + p.xl) : nullptr, Dp, s);
+                           tc ? (__half*)(ws + p.xl) : nullptr, Dp, s, f8_mode(h) ? 1 : 0);
         if (rc) return rc;
         a0.f = (const float*)(ws + p.xp); a0.ld = Dp;
         a0.h = (const __half*)(ws + p.xh); a0.l = (const __half*)(ws + p.xl); a0.ldh = Dp;
@@ -351,7 +390,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
             if (co.lo == 0 && co.hi > 0) {
                 e.d_cols = Lr.Np;
                 if (co.dout) { e.dout = co.dout; e.lddout = co.lddout; }
-                if (co.dh) { e.Dh = co.dh; e.Dl = co.dl; e.lddh = co.lddh; e.d_scale = kDiffScale; }
+                if (co.dh) { e.Dh = co.dh; e.Dl = co.dl; e.lddh = co.lddh; e.d_scale = diff_scale(h); }
             }
         }
         int rc = run_layer(h, Lr, cur, rows, e, s);
@@ -377,7 +416,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
             e.rowpart = (float*)(ws + p.rowpart) + (size_t)p.slot_off[l] * p.R; e.rowpart_stride = p.R;
             e.d_cols = Lr.Np;
             if (co.dout) { e.dout = co.dout + col_off; e.lddout = co.lddout; }
-            if (co.dh) { e.Dh = co.dh + col_off; e.Dl = co.dl + col_off; e.lddh = co.lddh; e.d_scale = kDiffScale; }
+            if (co.dh) { e.Dh = co.dh + col_off; e.Dl = co.dl + col_off; e.lddh = co.lddh; e.d_scale = diff_scale(h); }
             col_off += Lr.Np;
         }
         int rc = run_layer(h, Lr, cur, rows, e, s);
@@ -483,7 +522,7 @@ int mmad_create(const mmad_desc_t* d, mmad_t* out) {
     }
     for (int i = 0; i <= d->n_enc; ++i) if (d->enc_widths[i] < 1) { set_error("bad encoder width"); return MMAD_E_ARG; }
     for (int i = 0; i <= d->n_dec; ++i) if (d->dec_widths[i] < 1) { set_error("bad decoder width"); return MMAD_E_ARG; }
-    if (d->precision < MMAD_PREC_FP32 || d->precision > MMAD_PREC_F16) { set_error("bad precision"); return MMAD_E_ARG; }
+    if (d->precision < MMAD_PREC_FP32 || d->precision > MMAD_PREC_F16F8) { set_error("bad precision"); return MMAD_E_ARG; }
     int dev = 0;
     MMAD_CUDA_OK(cudaGetDevice(&dev));
     if (d->precision != MMAD_PREC_FP32 && !tc_available()) {
@@ -523,6 +562,7 @@ int mmad_destroy(mmad_t h) {
     for (auto& L : h->dec) free_layer(L);
     cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);
     cudaFree(h->nap.Bh); cudaFree(h->nap.Bl);
+    cudaFree(h->nap.Bh8); cudaFree(h->nap.B8); cudaFree(h->nap.d_wscale8);
     cudaFree(h->host_ws);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->host_x[i]); cudaFree(h->host_out[i]);
@@ -544,7 +584,7 @@ int mmad_destroy(mmad_t h) {
 
 int mmad_set_precision(mmad_t h, int precision) {
     if (!h) { set_error("null handle"); return MMAD_E_ARG; }
-    if (precision < MMAD_PREC_FP32 || precision > MMAD_PREC_F16) { set_error("bad precision"); return MMAD_E_ARG; }
+    if (precision < MMAD_PREC_FP32 || precision > MMAD_PREC_F16F8) { set_error("bad precision"); return MMAD_E_ARG; }
     if (precision != MMAD_PREC_FP32 && !tc_available()) {
         set_error("tensor-core precision requested but the device is not sm_100"); return MMAD_E_UNSUPPORTED;
     }
@@ -587,6 +627,8 @@ int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const floa
         if (!rc) rc = tc_make_operand_map(&L.tcB2.lo, L.Wl, L.N, L.K, L.Kp, 128);
         if (rc) return rc;
         L.tcB.rows = L.tcB2.rows = L.N; L.tcB.k = L.tcB2.k = L.K;
+        rc = make_f8_twins(d_W, L.N, L.K, L.K, L.Kp, &L.Wh8, &L.W8, &L.d_wscale8, &L.wscale8, &L.tcB_f8, &L.tcB2_f8, s);
+        if (rc) return rc;
         L.tc_ready = true;
     }
     L.loaded = true;
@@ -696,19 +738,21 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         rc = h->skinny ? gemm_skinny(g, e, s) : gemm_simt(g, e, s);
     } else {
         TcOperand A;
+        const bool f8 = f8_mode(h);
         rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.Dp, p.Dselp, 128);
-        if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.Dp, p.Dselp, 128);
+        if (!rc && f8) rc = tc_make_operand_map_f8(&A.lo, ws + p.dl, rows, f.Dp, p.Dselp * 2, 128);
+        else if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.Dp, p.Dselp, 128);
         if (rc) return rc;
         A.rows = rows; A.k = f.Dp;
-        e.acc_scale = 1.f / (f.wscale * kDiffScale);
+        e.acc_scale = 1.f / ((f8 ? f.wscale8 : f.wscale) * diff_scale(h));
         e.b_upper_tri = f.upper_tri ? 1 : 0;
         // f16x3: full split by default.  MMAD_NAP_PASSES=2 keeps the diffs' hi+lo pair but takes the whitening rows as
         // fp16 (two MMAs per product, +17 % scoring throughput): fine for well-conditioned layer selections (score
         // error ~1e-4), NOT for the rank-deficient all-layers default, whose near-null directions it perturbs beyond
         // the reference's own error (tests/test_gpu_metrics.py::test_nap_all_layers_protocol fails with it)
-        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? nap_passes() : 1;
-        if (rows >= kPairMinRows && tc2_available()) rc = gemm_tc2(A, f.tcB2, rows, f.K, f.Dp, passes, e, s);
-        else rc = gemm_tc(A, f.tcB, rows, f.K, f.Dp, passes, e, s);
+        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? nap_passes() : tc_passes(h);
+        if (rows >= kPairMinRows && tc2_available()) rc = gemm_tc2(A, f8 ? f.tcB2_f8 : f.tcB2, rows, f.K, f.Dp, passes, e, s);
+        else rc = gemm_tc(A, f8 ? f.tcB_f8 : f.tcB, rows, f.K, f.Dp, passes, e, s);
     }
     if (rc || !d_nap) return rc;
     return finalize_sum((const float*)(ws + p.rowpart), p.R, rows, p.slot_off[L + 1], p.slot_off[L + 2], 1.f / f.K,
@@ -724,6 +768,9 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     if (rc) return rc;
     // <= 64 rows (the realtime caller): exact-fp32 weight-streaming kernels on all SMs instead of one 128-row tile
     h->skinny = n > 0 && n <= gemm_skinny_max_rows() && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0);
+    // F16F8 NAP: the fit's variances carry this mode's rounding noise in the near-null directions, so scoring keeps the
+    // same arithmetic at every batch size
+    if (h->desc.precision == MMAD_PREC_F16F8 && d_nap) h->skinny = false;
     rc = score_impl(h, d_x, ldx, n, lo, hi, d_base, d_sap, d_nap, d_diffs, d_ws, ws_bytes, stream);
     h->skinny = false;
     return rc;
@@ -850,6 +897,7 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
     MMAD_CUDA_OK(cudaDeviceSynchronize());
     handle_graph_clear(h);          // cached graphs hold the old fit's pointers
     cudaFree(f.B); cudaFree(f.colscale); cudaFree(f.bias); cudaFree(f.bias_rot); cudaFree(f.Bh); cudaFree(f.Bl);
+    cudaFree(f.Bh8); cudaFree(f.B8); cudaFree(f.d_wscale8);
     f = NapFit();
     const SegMap seg = make_segmap(h, lo, hi);
     f.lo = lo; f.hi = hi; f.K = K; f.D = D; f.Dp = seg.pad_off[seg.n];
@@ -870,6 +918,8 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
         if (!rc) rc = tc_make_operand_map(&f.tcB2.lo, f.Bl, K, f.Dp, f.Dp, 128);
         if (rc) return rc;
         f.tcB.rows = f.tcB2.rows = K; f.tcB.k = f.tcB2.k = f.Dp;
+        rc = make_f8_twins(f.B, K, f.Dp, f.Dp, f.Dp, &f.Bh8, &f.B8, &f.d_wscale8, &f.wscale8, &f.tcB_f8, &f.tcB2_f8, s);
+        if (rc) return rc;
         f.tc_ready = true;
     }
     f.ready = true;

@@ -66,7 +66,13 @@ struct Epilogue {
     int pre_zeroed = 0;                                 // split-K: the caller already zeroed Y (no memset inside gemm_tc)
     int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
     float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)
+    // MMAD_PREC_F16F8: Yl / Dl hold the fp8 twin instead of the fp16 lo part -- per 4 columns 8 bytes:
+    // 4 x e4m3((v - hi) * 2^11) then 4 x e4m3(v)  (v = value * split scale).  Same bytes per row as the fp16 lo; a
+    // 64-column k-block of the fp16 operand corresponds to one 128-byte block of the twin.
+    int lo_f8 = 0;
 };
+
+constexpr float kF8LoScale = 2048.f;   // the residual v - fp16(v) is at most 2^-11 |v|: scaled to |lo8| <= |v|
 
 struct GemmShape {
     int M, N, K;
@@ -107,6 +113,8 @@ struct TcOperand {
 };
 int tc_available();
 int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, int ld, int box_rows);
+// fp8 twin ([rows, 2 * round_up(k, 64)] bytes, row stride ld_bytes): box = [128 bytes x box_rows]
+int tc_make_operand_map_f8(CUtensorMap* map, const void* base, int rows, int k, int ld_bytes, int box_rows);
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
             const Epilogue& e, cudaStream_t s, int bn = 256);   // bn: CTA tile width; K-major B maps need box_rows == bn
 int gemm_tc_tile_n();                    // the default (256)
@@ -139,7 +147,10 @@ bool handle_grad_allreduce(mmad_t h);     // all-reduce every layer's gradients 
 
 // elementwise helpers (elementwise.cu)
 int pad_split(const float* x, int ldx, int n, int D, float* xp, int ldp, __half* xh, __half* xl, int ldh,
-              cudaStream_t s);
+              cudaStream_t s, int lo_f8 = 0);
+// MMAD_PREC_F16F8 weight twins: Wh = fp16(W * scale), W8 = per 4 columns [4 x e4m3(Wh / 2^11) | 4 x e4m3(W * scale - Wh)];
+// *d_scale (device) receives the power-of-two scale that puts max|W| * scale in [2^13, 2^14)
+int split_weights_f8(const float* W, int N, int K, int ldw, int Kp, __half* Wh, uint8_t* W8, float* d_scale, cudaStream_t s);
 int split_weights(const float* W, int N, int K, int Kp, float scale, __half* Wh, __half* Wl, cudaStream_t s);
 int split_weights_multi(int n, const float* const* W, const int* N, const int* K, const int* Kp, float scale, __half* const* Wh,
                         __half* const* Wl, cudaStream_t s);

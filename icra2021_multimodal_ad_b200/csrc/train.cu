@@ -517,7 +517,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     };
     const int D = d.enc_widths[0];
     const int enc_out = d.enc_widths[d.n_enc], dec_in = d.dec_widths[0];
-    const int passes = d.precision == MMAD_PREC_F16X3 ? 3 : 1;
+    const int passes = d.precision == MMAD_PREC_F16 ? 1 : 3;   // F16F8 is a scoring mode: training keeps the full fp16 split
     const float* d_eps = vib ? (const float*)(ws + p.eps) : nullptr;
     const int B = batch;
     const double Bg = (double)global_batch;

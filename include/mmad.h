@@ -44,10 +44,13 @@ extern "C" {
  * reference mode).  F16X3: tcgen05 tensor cores, every fp32 operand split into an fp16
  * pair (hi + lo), three MMAs per product, fp32 accumulation in TMEM -- meets the 1e-4
  * score tolerance.  F16: one tcgen05 pass on the hi parts only (separately stated
- * tolerance). */
+ * tolerance).  F16F8: the hi*hi pass in fp16 plus ONE fp8 (e4m3) pass of twice the
+ * contraction length carrying both cross terms, [lo8 | a8] . [Wh8 ; Wl8] -- two thirds of the
+ * F16X3 tensor work; score error <= 1e-4 at D = 1728, 3e-4 for the narrow sensors. */
 #define MMAD_PREC_FP32 0
 #define MMAD_PREC_F16X3 1
 #define MMAD_PREC_F16 2
+#define MMAD_PREC_F16F8 3
 
 typedef struct mmad_handle* mmad_t;
 

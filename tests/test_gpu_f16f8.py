@@ -1,0 +1,98 @@
+"""GPU parity of MMAD_PREC_F16F8 (fp16 hi*hi pass + one fp8 e4m3 pass carrying both cross terms).
+
+Stated tolerance (scripts/emulate_split_f8.py): base / SAP scores within 1e-4 relative
+per sample at the headline width D = 1728 (emulation: 5.5e-5 max over 8192 windows); 5e-4 for the narrow
+sensors (D <= 128: few products per dot product to average the fp8 rounding over; emulation 1.5e-4);
+diffs within 3e-4 of the matrix max.  F16X3 stays the strict fp32-equivalent mode."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_max(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _model(D, btl, nl, seed, precision):
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=precision))
+    m.load_state_dict(synth_state_dict(D, btl, nl, seed))
+    return m.eval()
+
+
+@pytest.mark.parametrize("name,tol", [("score_D1728.pt", 1e-4), ("score_D64.pt", 5e-4), ("score_D128_l3.pt", 5e-4)])
+def test_scores_match_reference_golden(name, tol):
+    """Against outputs of the unmodified reference (tests/golden/make_golden.py); small batches: one CTA per tile."""
+    from icra2021_multimodal_ad_b200.reconstruction_aggregation import get_diffs, get_scores
+    g = load_golden(name)
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    m = _model(D, btl, nl, seed, "f16f8")
+    xte, _ = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    r = g["xhat"].shape[0]
+    with torch.no_grad():
+        xhat = m(xte.cuda()).cpu()
+        diffs = get_diffs(xte.numpy(), m, batch_size=g["bs"])
+    assert _rel_max(xhat[:r], g["xhat"]) < 3e-4
+    for d, dg in zip(diffs, g["diffs_te"]):
+        assert _rel_max(d[:r], dg) < 3e-4
+    for sel, ent in g["sap"].items():
+        lo, hi = sel.split(":")
+        lo, hi = int(lo), (None if hi == "None" else int(hi))
+        sc = get_scores(xte, m, lo, hi)
+        np.testing.assert_allclose(sc["sap"].cpu().numpy(), ent["score"].numpy(), rtol=tol)
+        np.testing.assert_allclose(sc["base"].cpu().numpy(), g["base"]["score"].numpy(), rtol=tol)
+
+
+@pytest.mark.parametrize("D,btl,nl,n,tol", [(1728, 100, 5, 4096 + 300, 1e-4), (300, 17, 2, 4096 + 129, 5e-4), (93, 10, 3, 2500, 5e-4)])
+def test_cta_pair_kernel_against_oracle_on_tall_chunks(D, btl, nl, n, tol):
+    """Chunks of >= 2048 rows: cta_group::2 kernel with kind::f16 and kind::f8f6f4 instructions into one accumulator;
+    ragged last pair tile, partial N tiles.  Checked against the CPU oracle (fp32) and the fp32 CUDA-core mode."""
+    from oracle import rapp_oracle as RO
+    sd = synth_state_dict(D, btl, nl, 77)
+    x, _ = synth_windows(n, D, 5)
+    ref = RO.get_diffs(x, sd)
+    m = _model(D, btl, nl, 77, "f16f8")
+    o = m.engine().score(x.cuda(), 0, nl + 1, diffs=True)
+    np.testing.assert_allclose(o["sap"].cpu().numpy(), RO.sap_score(ref), rtol=tol)
+    np.testing.assert_allclose(o["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=tol)
+    assert _rel_max(o["diffs"].cpu().numpy(), RO.concat_diffs(ref)) < 3e-4
+    # chunk-size independence of the arithmetic: the same rows in one tall chunk and in 700-row calls (single-CTA kernel)
+    eng = m.engine()
+    small = torch.cat([eng.score(x[i:i + 700].cuda(), 0, nl + 1)["sap"] for i in range(0, 2100, 700)]).cpu().numpy()
+    np.testing.assert_allclose(small, o["sap"].cpu().numpy()[:2100], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n", [33, 130, 700])
+def test_single_cta_kernel_tile_edges(n):
+    for D, btl, nl, tol in ((1728, 100, 5, 1e-4), (300, 17, 2, 5e-4), (2048, 100, 5, 1e-4)):
+        x, _ = synth_windows(n, D, 40 + n)
+        a = _model(D, btl, nl, 123, "fp32").engine().score(x.cuda(), 0, nl + 1)
+        b = _model(D, btl, nl, 123, "f16f8").engine().score(x.cuda(), 0, nl + 1)
+        np.testing.assert_allclose(b["sap"].cpu().numpy(), a["sap"].cpu().numpy(), rtol=tol)
+        np.testing.assert_allclose(b["base"].cpu().numpy(), a["base"].cpu().numpy(), rtol=tol)
+
+
+@pytest.mark.parametrize("factor", ["eigen", "triangular"])
+def test_nap_well_conditioned_selection(factor):
+    """NAP on d_0 alone (cond ~ 9): fit and scoring both in the fp8-assisted arithmetic, within 1e-3 of
+    the fp32 mode (the bar the F16X3 pair kernel is held to)."""
+    D, btl, nl, n = 1728, 100, 5, 4096
+    x, _ = synth_windows(n, D, 5)
+    xtr, _ = synth_windows(2 * D, D, 6, anomaly_rate=0.0)
+    out = {}
+    for prec in ("fp32", "f16f8"):
+        eng = _model(D, btl, nl, 77, prec).engine()
+        eng.nap_fit(xtr.cuda(), 0, 1, distributed=False, factor=factor)
+        out[prec] = eng.score(x.cuda(), 0, 1, nap=True)["nap"].cpu().numpy()
+        small = eng.score(x[:10].cuda(), 0, 1, nap=True)["nap"].cpu().numpy()      # same arithmetic at batch 10
+        np.testing.assert_allclose(small, out[prec][:10], rtol=1e-3 if prec == "fp32" else 1e-5)
+    np.testing.assert_allclose(out["f16f8"], out["fp32"], rtol=1e-3)

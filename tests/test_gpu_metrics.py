@@ -116,7 +116,7 @@ def test_reference_api_scoring_functions_on_golden_diffs():
 
 
 @pytest.mark.parametrize("factor", ["eigen", "triangular"])
-@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16f8"])
 def test_nap_all_layers_protocol(precision, factor):
     """the default all-layers NAP is rank-deficient by construction (d_5 = W_5 d_4), so the
     reference's own fp32 result is far from the fp64 value of the same formula.  Required: our error
