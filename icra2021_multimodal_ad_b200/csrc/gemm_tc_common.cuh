@@ -219,10 +219,130 @@ __device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, 
 // Fused epilogue of one warp's 32 rows x [col_lo, col_hi) slice.  The warp works in 32-column blocks: one tcgen05.ld
 // hands each thread its accumulator ROW (32 columns); the block goes through a 2 KB XOR-swizzled shared tile in two
 // phases of 16 rows and is re-read as (4 rows x 8 float4 columns), so every global access of the warp covers whole
-// 128-byte (fp32) / 64-byte (fp16, fp8 twin) row segments -- half the LSU wavefronts of 16-column pieces, which is what
-// the chain layers are bound by once the MMA work drops to two passes.
+// 128-byte (fp32) / 64-byte (fp16, fp8 twin) row segments.  Blocks that lie completely inside the matrix (all but the
+// ragged last block of a layer / the last row tile) take the FULL instantiation: no per-element predicates or zero
+// selects, row pointers advanced by constant strides -- the epilogue is issue-bound (two warps per scheduler), so the
+// instruction count of this loop is what paces the chain layers once the MMA work drops to two passes.
 // sq[ph * 4 + it] returns this lane's partial row sum of squares for row row_base + ph*16 + it*4 + lane/8.
-__device__ __forceinline__ int stg_slot32(int row16, int j8) { return row16 * 8 + (j8 ^ (row16 & 7)); }
+__device__ __forceinline__ uint32_t stg_off32(int row16, int j8) { return (uint32_t)(row16 * 8 + (j8 ^ (row16 & 7))) * 16u; }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
+struct EpiPtrs {     // per-lane pointers at (row_base + lane/8, n0 + 4 * (lane%8)); null when the output is absent
+    float* Y; float* pre; float* dout; const float* ref;
+    __half* Yh; uint8_t* Yl; __half* Dh; uint8_t* Dl;
+};
+
+template <bool FULL>
+__device__ __forceinline__ void epi_block(const Epilogue& e, const EpiPtrs& q, int M, int row_base, int c0, int cc, int n_cols,
+                                          int w_cols, int dw_cols, int pre_cols, const uint32_t (&v)[32], uint32_t stg_s,
+                                          const float4& mul, const float4& bia, const float4& sc, const float4& sh, int lane,
+                                          float (&sq)[8]) {
+    const int rsub = lane >> 3, cg = lane & 7;
+    const bool k0 = FULL || cc < n_cols, k1 = FULL || cc + 1 < n_cols, k2 = FULL || cc + 2 < n_cols, k3 = FULL || cc + 3 < n_cols;
+    const bool wy = FULL || cc < w_cols, wd = FULL || cc < dw_cols, wp = FULL || cc < pre_cols;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        // this phase's reference loads first: 4 independent 16-byte loads per lane in flight during the transpose
+        float4 rf[4];
+        if (q.ref) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = ph * 16 + it * 4;
+                rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FULL || (row_base + rr + rsub < M && k3))
+                    rf[it] = __ldg(reinterpret_cast<const float4*>(q.ref + (size_t)rr * e.ldref + c0));
+            }
+        }
+        if ((lane >> 4) == ph) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(stg_s + stg_off32(lane & 15, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rl = it * 4 + rsub;
+            const int rr = ph * 16 + it * 4;            // row offset from this lane's base row
+            const float4 a = lds128(stg_s + stg_off32(rl, cg));
+            float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
+            float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
+            if (FULL || row_base + rr + rsub < M) {
+                if (q.pre && wp)     // train: pre-activation, zero padded to ldpre columns
+                    *reinterpret_cast<float4*>(q.pre + (size_t)rr * e.ldpre + c0) =
+                        make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
+                if (e.bn_scale) {
+                    x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
+                    x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
+                    x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
+                    x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
+                }
+                if (!FULL) { x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f; }
+                if (q.Y && wy) *reinterpret_cast<float4*>(q.Y + (size_t)rr * e.ldy + c0) = make_float4(x0, x1, x2, x3);
+                if (q.Yh && wy) {
+                    const float ys = e.y_split_scale;
+                    const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
+                    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+                    uint2 hv;
+                    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    *reinterpret_cast<uint2*>(q.Yh + (size_t)rr * e.ldh + c0) = hv;
+                    if (q.Yl) {
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        uint2 lv;
+                        if (e.lo_f8) {
+                            lv.x = pack_e4m3x4((y0 - f01.x) * kF8LoScale, (y1 - f01.y) * kF8LoScale, (y2 - f23.x) * kF8LoScale, (y3 - f23.y) * kF8LoScale);
+                            lv.y = pack_e4m3x4(y0, y1, y2, y3);
+                        } else {
+                            const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
+                            const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
+                            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        }
+                        *reinterpret_cast<uint2*>(q.Yl + ((size_t)rr * e.ldh + c0) * 2) = lv;
+                    }
+                }
+                if (q.ref) {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                    if (k3) {
+                        const float4 f = rf[it];
+                        d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
+                    } else if (k0) {
+                        const float* rp = q.ref + (size_t)rr * e.ldref + c0;
+                        d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
+                    }
+                    float& acc = sq[ph * 4 + it];
+                    acc = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, acc))));
+                    if (q.dout && wd) *reinterpret_cast<float4*>(q.dout + (size_t)rr * e.lddout + c0) = make_float4(d0, d1, d2, d3);
+                    if (q.Dh && wd) {
+                        const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
+                        const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(q.Dh + (size_t)rr * e.lddh + c0) = hv;
+                        if (e.lo_f8) {
+                            lv.x = pack_e4m3x4((s0 - f01.x) * kF8LoScale, (s1 - f01.y) * kF8LoScale, (s2 - f23.x) * kF8LoScale, (s3 - f23.y) * kF8LoScale);
+                            lv.y = pack_e4m3x4(s0, s1, s2, s3);
+                        } else {
+                            const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
+                            const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        }
+                        *reinterpret_cast<uint2*>(q.Dl + ((size_t)rr * e.lddh + c0) * 2) = lv;
+                    }
+                } else if (e.sq_self) {
+                    float& acc = sq[ph * 4 + it];
+                    acc = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, acc))));
+                }
+            }
+        }
+        __syncwarp();     // the staging tile is rewritten by the next phase
+    }
+}
 
 template <int BN>
 __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
@@ -239,116 +359,34 @@ __device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int sp
     int n_cols = N - n0; if (n_cols > BN) n_cols = BN;          // valid columns of this tile
     int w_cols = e.y_cols - n0; if (w_cols > BN) w_cols = BN;      // activation columns to write (zero padded)
     int dw_cols = e.ref ? e.d_cols - n0 : 0; if (dw_cols > BN) dw_cols = BN;   // diff columns to write
+    const int pre_cols = e.pre ? e.ldpre - n0 : 0;
     int c_end = (max(max(n_cols, w_cols), dw_cols) + 31) & ~31;
     if (c_end > col_hi) c_end = col_hi;
+    const bool rows_full = row_base + 32 <= M;
+    // per-lane base pointers at (row_base + rsub, n0 + 4 * cg); a block adds c0, a row step adds rr * ld
+    const size_t r0 = (size_t)(row_base + rsub);
+    const int cb = n0 + cg * 4;
+    EpiPtrs q;
+    q.Y = e.Y ? e.Y + r0 * e.ldy + cb : nullptr;
+    q.pre = e.pre ? e.pre + r0 * e.ldpre + cb : nullptr;
+    q.ref = e.ref ? e.ref + r0 * e.ldref + cb : nullptr;
+    q.dout = (e.ref && e.dout) ? e.dout + r0 * e.lddout + cb : nullptr;
+    q.Yh = e.Yh ? e.Yh + r0 * e.ldh + cb : nullptr;
+    q.Yl = (e.Yh && e.Yl) ? reinterpret_cast<uint8_t*>(e.Yl) + (r0 * e.ldh + cb) * 2 : nullptr;
+    q.Dh = (e.ref && e.Dh) ? e.Dh + r0 * e.lddh + cb : nullptr;
+    q.Dl = (e.ref && e.Dh) ? reinterpret_cast<uint8_t*>(e.Dl) + (r0 * e.lddh + cb) * 2 : nullptr;
+    const uint32_t stg_s = smem_u32(stg);
+    const uint32_t mul_s = smem_u32(s_mul), bias_s = smem_u32(s_bias), sc_s = smem_u32(s_sc), sh_s = smem_u32(s_sh);
     for (int c0 = col_lo; c0 < c_end; c0 += 32) {
         const int cc = c0 + cg * 4;             // tile-local column of this lane's float4
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
-        const float4 mul = *reinterpret_cast<const float4*>(s_mul + cc);
-        const float4 bia = *reinterpret_cast<const float4*>(s_bias + cc);
-        const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc);
-        const float4 sh = *reinterpret_cast<const float4*>(s_sh + cc);
-        const bool k0 = cc < n_cols, k1 = cc + 1 < n_cols, k2 = cc + 2 < n_cols, k3 = cc + 3 < n_cols;
-        const bool wy = cc < w_cols, wd = cc < dw_cols;   // widths are multiples of 4 (padded to 64)
-        const size_t gcol = (size_t)n0 + cc;
-#pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-            // this phase's reference loads first: 4 independent 16-byte loads per lane in flight during the transpose
-            float4 rf[4];
-            if (e.ref) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int r = row_base + ph * 16 + it * 4 + rsub;
-                    rf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < M && cc + 3 < n_cols)
-                        rf[it] = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + n0 + cc));
-                }
-            }
-            if ((lane >> 4) == ph) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    stg[stg_slot32(lane & 15, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int rl = it * 4 + rsub;
-                const int r = row_base + ph * 16 + rl;
-                const float4 a = stg[stg_slot32(rl, cg)];
-                float x0 = fmaf(a.x, mul.x, bia.x), x1 = fmaf(a.y, mul.y, bia.y);
-                float x2 = fmaf(a.z, mul.z, bia.z), x3 = fmaf(a.w, mul.w, bia.w);
-                if (r < M) {
-                    if (e.pre && cc < e.ldpre - n0)     // train: pre-activation, zero padded to ldpre columns
-                        *reinterpret_cast<float4*>(e.pre + (size_t)r * e.ldpre + gcol) =
-                            make_float4(k0 ? x0 : 0.f, k1 ? x1 : 0.f, k2 ? x2 : 0.f, k3 ? x3 : 0.f);
-                    if (e.bn_scale) {
-                        x0 = x0 > 0.f ? x0 : x0 * e.slope; x1 = x1 > 0.f ? x1 : x1 * e.slope;
-                        x2 = x2 > 0.f ? x2 : x2 * e.slope; x3 = x3 > 0.f ? x3 : x3 * e.slope;
-                        x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y);
-                        x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
-                    }
-                    x0 = k0 ? x0 : 0.f; x1 = k1 ? x1 : 0.f; x2 = k2 ? x2 : 0.f; x3 = k3 ? x3 : 0.f;
-                    if (e.Y && wy) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + gcol) = make_float4(x0, x1, x2, x3);
-                    if (e.Yh && wy) {
-                        const float ys = e.y_split_scale;
-                        const float y0 = x0 * ys, y1 = x1 * ys, y2 = x2 * ys, y3 = x3 * ys;
-                        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-                        uint2 hv;
-                        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                        *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + gcol) = hv;
-                        if (e.Yl && e.lo_f8) {
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            store_f8_twin(reinterpret_cast<uint8_t*>(e.Yl) + (size_t)r * e.ldh * 2, (int)gcol, y0, y1, y2, y3,
-                                          y0 - f01.x, y1 - f01.y, y2 - f23.x, y3 - f23.y);
-                        } else if (e.Yl) {
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            const __half2 l01 = __floats2half2_rn(y0 - f01.x, y1 - f01.y);
-                            const __half2 l23 = __floats2half2_rn(y2 - f23.x, y3 - f23.y);
-                            uint2 lv;
-                            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                            *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + gcol) = lv;
-                        }
-                    }
-                    if (e.ref) {
-                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-                        if (k3) {
-                            const float4 f = rf[it];
-                            d0 = x0 - f.x; d1 = x1 - f.y; d2 = x2 - f.z; d3 = x3 - f.w;
-                        } else if (k0) {
-                            const float* rp = e.ref + (size_t)r * e.ldref + gcol;
-                            d0 = x0 - rp[0]; if (k1) d1 = x1 - rp[1]; if (k2) d2 = x2 - rp[2];
-                        }
-                        float& acc = sq[ph * 4 + it];
-                        acc = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, acc))));
-                        if (e.dout && wd) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + gcol) = make_float4(d0, d1, d2, d3);
-                        if (e.Dh && wd) {
-                            const float s0 = d0 * e.d_scale, s1 = d1 * e.d_scale, s2 = d2 * e.d_scale, s3 = d3 * e.d_scale;
-                            const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            uint2 hv;
-                            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                            *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + gcol) = hv;
-                            if (e.lo_f8) {
-                                store_f8_twin(reinterpret_cast<uint8_t*>(e.Dl) + (size_t)r * e.lddh * 2, (int)gcol, s0, s1, s2, s3,
-                                              s0 - f01.x, s1 - f01.y, s2 - f23.x, s3 - f23.y);
-                            } else {
-                                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y);
-                                const __half2 l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
-                                uint2 lv;
-                                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                                *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + gcol) = lv;
-                            }
-                        }
-                    } else if (e.sq_self) {
-                        float& acc = sq[ph * 4 + it];
-                        acc = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, acc))));
-                    }
-                }
-            }
-            __syncwarp();     // the staging tile is rewritten by the next phase
-        }
+        const float4 mul = lds128(mul_s + cc * 4), bia = lds128(bias_s + cc * 4);
+        const float4 sc = lds128(sc_s + cc * 4), sh = lds128(sh_s + cc * 4);
+        if (rows_full && c0 + 32 <= n_cols)
+            epi_block<true>(e, q, M, row_base, c0, cc, n_cols, w_cols, dw_cols, pre_cols, v, stg_s, mul, bia, sc, sh, lane, sq);
+        else
+            epi_block<false>(e, q, M, row_base, c0, cc, n_cols, w_cols, dw_cols, pre_cols, v, stg_s, mul, bia, sc, sh, lane, sq);
     }
 }
 
