@@ -30,6 +30,7 @@ MAC_ENC = sum(a * b for a, b in zip(W_ENC[:-1], W_ENC[1:]))
 FLOP_SAP = 2 * 3 * MAC_ENC         # enc(x) + dec + enc(xhat): 30 605 754 per window
 FLOP_NAP_ROT = 2 * DPRIME * DPRIME  # rotation (d-mu) V: 60 104 648 per window
 N_FIT = 8192                       # NAP fit set (>= D' so K = D')
+DEFAULT_PRECISION = "f16f8"        # MMAD_DEFAULT_PRECISION overrides; f16x3 and fp32 are measured with --precision
 DTYPE_NAME = {"fp32": "f32", "f16x3": "f16x3 split (fp32-equivalent)", "f16": "f16",
               "f16f8": "f16 + fp8(e4m3) cross terms (fp32 accumulate; scores within 1e-4 of fp32)"}
 
@@ -157,7 +158,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "anomaly-scored samples/sec (SAP+NAP)", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, os.environ.get("MMAD_DEFAULT_PRECISION", "f16x3") if args.precision == "auto" else args.precision),
+            "config": workload_config(args, os.environ.get("MMAD_DEFAULT_PRECISION", DEFAULT_PRECISION) if args.precision == "auto" else args.precision),
             "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "arithmetic": "fp32 (torch CPU)",
                              "sample": f"{n} windows per step, get_diffs(batch 256)+base+SAP" + ("" if args.no_nap else "+NAP score (K=5482 fit)")},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -273,7 +274,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("MMAD_DEFAULT_PRECISION", "f16x3")
+        precision = os.environ.get("MMAD_DEFAULT_PRECISION", DEFAULT_PRECISION)
     sd = synth_state_dict(D, BTL, NL, 0)
     cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
     model = get_model(cfg).eval()
@@ -344,6 +345,7 @@ def main():
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused GEMM, from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = tj.get(precision, tj)            # one record per precision mode
         if tj.get("precision") == precision and tj.get("batch") == args.batch:
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
@@ -358,13 +360,13 @@ def main():
     pipe_pct = None
     try:   # time-weighted tensor-pipe activity of the fused GEMM launches from the committed ncu launch list
         import csv
-        rows = [r for r in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r1_launches_scoring_f16x3.csv")) if not l.startswith("=="))]
+        rows = [r for r in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r1_launches_scoring_%s.csv" % precision)) if not l.startswith("=="))]
         t, a = {}, {}
         for r in rows:
             if "gemm_tc" in r["Kernel Name"]:
                 v = float(r["Metric Value"].replace(",", ""))
                 (t if r["Metric Name"].startswith("gpu__time") else a)[r["ID"]] = v
-        if t and precision == "f16x3":
+        if t:
             pipe_pct = sum(t[k] * a.get(k, 0.0) for k in t) / sum(t.values())
     except Exception:
         pass
@@ -404,6 +406,25 @@ def main():
         if world == 1:
             extras["train_b7000"] = bench_train(dev, local, world, 7000, max(3, tsteps // 3), 2, precision)
             extras["stream_latency"] = bench_stream(eng)
+    # ---- the same step in the full fp16 split (three fp16 MMAs per product), for comparison ----
+    if precision == "f16f8" and not args.no_extras:
+        eng.set_precision("f16x3")
+        if want_nap:
+            eng.nap_fit(xtr.to(dev), 0, NL + 1, distributed=world > 1)
+        for _ in range(2):
+            step_dev()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            step_dev()
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extras["f16x3"] = {"value": world * B * args.steps / (float(t.item()) / 1e3), "unit": "samples/s",
+                           "ms_per_step": float(t.item()) / args.steps, "dtype": DTYPE_NAME["f16x3"]}
     if rank == 0:
         cpu_rate, cores = cpu_scoring_rate(args.cpu_sample, sd, fit, want_nap) if world == 1 else (None, None)
         flop_per_window = FLOP_SAP + (FLOP_NAP_ROT if want_nap else 0)

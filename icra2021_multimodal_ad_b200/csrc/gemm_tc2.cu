@@ -50,10 +50,24 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even, int c0, int c1) {
+// L2 eviction priority of the load: the B operand (weights / the NAP whitening factor, re-read by every row tile) is kept,
+// the A operand (activation rows, dead once the band of n-tiles over them is done) is evicted first.  Without the hint the
+// 75 776-row A stream pushes the 122 MB NAP factor out of the 126 MB L2 and it is re-streamed from HBM (12.9 GB per launch,
+// profiles/r1_ncu_full_f16f8.md) -- bandwidth that is free, but power that the capped SM clock pays for.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even, int c0, int c1, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar_even), "r"(c0), "r"(c1) : "memory");
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar_even), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -155,6 +169,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint64_t pol_a = l2_policy_evict_normal(), pol_b = l2_policy_evict_last();
             for (int w = pair; w < num_tiles; w += npairs) {
                 const int t = w / p.splits, sp = w % p.splits;
                 int tm, tn;
@@ -173,24 +188,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                     auto load_a = [&](uint8_t* dst, const CUtensorMap* map) {
                         if (A_MN) {   // [k rows, m contiguous]: two boxes of 64 m x 64 k
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, m0 + j * 64, kb * BK);
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, m0 + j * 64, kb * BK, pol_a);
                         } else {
-                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, m0);
+                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, m0, pol_a);
                         }
                     };
                     auto load_b = [&](uint8_t* dst, const CUtensorMap* map) {
                         if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, nb0 + j * 64, kb * BK);
+                            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(smem_u32(dst + j * 8192), map, fb, nb0 + j * 64, kb * BK, pol_b);
                         } else {
-                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, nb0);
+                            tma_load_2d_pair(smem_u32(dst), map, fb, kb * BK, nb0, pol_b);
                         }
                     };
                     load_a(st, &mapAh);
                     load_b(st + A_TILE_BYTES, &mapBh);
                     if (PASSES == 4) {   // fp8 twins: byte maps, one 128-byte block per k-block
-                        tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * 128, m0);
-                        tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * 128, nb0);
+                        tma_load_2d_pair(smem_u32(st + A_TILE_BYTES + B_HALF_BYTES), &mapAl, fb, kb * 128, m0, pol_a);
+                        tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + B_HALF_BYTES), &mapBl, fb, kb * 128, nb0, pol_b);
                     } else {
                         if (PASSES >= 2) load_a(st + A_TILE_BYTES + B_HALF_BYTES, &mapAl);
                         if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_HALF_BYTES, &mapBl);

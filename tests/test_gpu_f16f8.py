@@ -1,9 +1,9 @@
 """GPU parity of MMAD_PREC_F16F8 (fp16 hi*hi pass + one fp8 e4m3 pass carrying both cross terms).
 
-Stated tolerance (scripts/emulate_split_f8.py): base / SAP scores within 1e-4 relative
-per sample at the headline width D = 1728 (emulation: 5.5e-5 max over 8192 windows); 5e-4 for the narrow
-sensors (D <= 128: few products per dot product to average the fp8 rounding over; emulation 1.5e-4);
-diffs within 3e-4 of the matrix max.  F16X3 stays the strict fp32-equivalent mode."""
+Stated tolerance (scripts/emulate_split_f8.py, scripts/score_error_modes.py): on random-init
+weights base / SAP scores within 1e-4 relative per window at D = 1728 and 5e-4 for the narrow sensors (D <= 128: few
+products per dot product to average the fp8 rounding over), diffs within 3e-4 of the matrix max; on a trained
+model see test_trained_model_tolerance (same error floor as F16X3 at D = 1728).  fp32 is the strict mode."""
 import argparse
 
 import numpy as np
@@ -96,3 +96,38 @@ def test_nap_well_conditioned_selection(factor):
         small = eng.score(x[:10].cuda(), 0, 1, nap=True)["nap"].cpu().numpy()      # same arithmetic at batch 10
         np.testing.assert_allclose(small, out[prec][:10], rtol=1e-3 if prec == "fp32" else 1e-5)
     np.testing.assert_allclose(out["f16f8"], out["fp32"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("D,steps", [(1728, 60), (64, 100)])
+def test_trained_model_tolerance(D, steps):
+    """Random-init weights are the easy case (score error ~2e-6 in every tensor-core mode); what matters is a TRAINED
+    autoencoder, whose reconstructions are close to the inputs so that the diffs are small differences of large
+    activations.  The weights are trained with the oracle's Adam steps (CPU, the reference's algorithm), then every
+    window's base and SAP score is compared with the oracle's fp32 scores.
+
+    Measured on B200 (scripts/score_error_modes.py, 4096 windows): fp32 mode max 9e-6; D = 1728: F16X3 max 9.0e-5 /
+    median 1.4e-5, F16F8 max 9.6e-5 / median 1.1e-5 -- both tensor-core modes sit on the same floor, the truncating
+    fp32 accumulation of the tensor core (one truncation of the accumulator per MMA instruction, biased towards
+    zero), not the operand split.  D = 64 (short dot products): F16X3 1.0e-5, F16F8 1.4e-4.
+    Bars: fp32 1e-5 relative everywhere; tensor-core modes median 3e-5, 99.9 % of the windows within 1e-4, every
+    window within 2e-4 (D = 1728) / 5e-4 (F16F8 at D = 64)."""
+    from oracle import rapp_oracle as RO
+    btl, nl = 100, 5
+    sd = synth_state_dict(D, btl, nl, 0)
+    xtr, _ = synth_windows(256 * 8, D, 7, anomaly_rate=0.0)
+    opt = {}
+    for i in range(steps):
+        RO.train_step(xtr[(i % 8) * 256:(i % 8 + 1) * 256], sd, opt)
+    x, _ = synth_windows(4096, D, 1236)
+    ref = RO.get_diffs(x, sd, batch_size=256)
+    sap_o, base_o = RO.sap_score(ref).astype(np.float64), RO.recon_score(ref[0]).astype(np.float64)
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    bars = {"fp32": (1e-5, 1e-5, 1e-5), "f16x3": (3e-5, 1e-4, 2e-4), "f16f8": (3e-5, 1e-4 if D > 128 else 3e-4, 2e-4 if D > 128 else 5e-4)}
+    for prec, (b_med, b_p999, b_max) in bars.items():
+        m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=prec)).eval()
+        m.load_state_dict(sd)
+        o = m.engine().score(x.cuda(), 0, nl + 1)
+        for name, got, want in (("sap", o["sap"], sap_o), ("base", o["base"], base_o)):
+            err = np.abs(got.cpu().numpy() - want) / want
+            print(f"trained D={D} {prec} {name}: max {err.max():.2e} p99.9 {np.quantile(err, 0.999):.2e} median {np.median(err):.2e}")
+            assert np.median(err) < b_med and np.quantile(err, 0.999) < b_p999 and err.max() < b_max, (prec, name)
