@@ -354,7 +354,10 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + BN2 - 1) / BN2;
     p.tri = e.b_upper_tri ? 1 : 0;
-    p.band = 8;
+    // balanced bands of at most 12 n-tiles: the NAP factor's 22 n-tiles run as 2 x 11 (A is streamed twice, the 61 MB band
+    // of B plus the ~7 row panels in flight stay L2 resident); MMAD_TC2_BAND overrides for experiments
+    p.band = (p.tiles_n + (p.tiles_n + 11) / 12 - 1) / ((p.tiles_n + 11) / 12);
+    { static int b = -1; if (b < 0) { const char* q = getenv("MMAD_TC2_BAND"); b = q ? atoi(q) : 0; } if (b > 0) p.band = b; }
     const int tiles = p.tiles_m * p.tiles_n;
     const int max_pairs = g_sms / 2;
     const int num_kb = (K + BK - 1) / BK;
