@@ -59,7 +59,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons every 100 ms during the timed region (NVML)."""
+    """Samples SM clock and throttle reasons every 5 ms during the timed region (NVML; the region is ~100 ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_ev.wait(0.1)
+            self._stop_ev.wait(0.005)
 
     def stop(self):
         self._stop_ev.set()
