@@ -180,13 +180,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int col_lo = BN == 256 ? half * 128 : 0;
         const int col_hi = BN == 256 ? col_lo + 128 : (half == 0 ? 128 : 0);
         int acc = 0; uint32_t acc_phase = 0;
+        EpiVec vec;
+        if (et < BN && (int)blockIdx.x < num_tiles)
+            vec = epi_vec_load(e, p.N, (((int)blockIdx.x / p.splits) % p.tiles_n) * BN, (int)blockIdx.x % p.splits, et);
         for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
             const int t = w / p.splits, sp = w % p.splits;
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
-            // stage the per-column epilogue vectors of this tile
+            // stage the per-column epilogue vectors of this tile (loaded one tile ahead), load the next tile's
             asm volatile("bar.sync 1, 256;");
-            epi_stage_vectors<BN>(e, p.N, n0, sp, et, s_mul, s_bias, s_sc, s_sh);
+            if (et < BN) epi_vec_store(vec, et, s_mul, s_bias, s_sc, s_sh);
             asm volatile("bar.sync 1, 256;");
+            if (et < BN && w + (int)gridDim.x < num_tiles) {
+                const int w2 = w + (int)gridDim.x;
+                vec = epi_vec_load(e, p.N, ((w2 / p.splits) % p.tiles_n) * BN, w2 % p.splits, et);
+            }
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;

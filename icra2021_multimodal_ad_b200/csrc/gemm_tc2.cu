@@ -272,14 +272,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         float4* stg = s_stage + (warp - 2) * STG_FLOAT4;
         const int col_lo = half * 128, col_hi = col_lo + 128;
         int acc = 0; uint32_t acc_phase = 0;
+        EpiVec vec;
+        if (pair < num_tiles) {      // the first tile's column vectors; later ones are loaded one tile ahead
+            int tm, tn;
+            tile_coords(p, pair / p.splits, tm, tn);
+            vec = epi_vec_load(e, p.N, tn * BN, pair % p.splits, et);
+        }
         for (int w = pair; w < num_tiles; w += npairs) {
             const int t = w / p.splits, sp = w % p.splits;
             int tm, tn;
             tile_coords(p, t, tm, tn);
             const int m0 = tm * 256 + (int)rank * BM, n0 = tn * BN;
+            asm volatile("bar.sync 1, 256;");          // every warp is done with the previous tile's vectors
+            epi_vec_store(vec, et, s_mul, s_bias, s_sc, s_sh);
             asm volatile("bar.sync 1, 256;");
-            epi_stage_vectors<BN>(e, p.N, n0, sp, et, s_mul, s_bias, s_sc, s_sh);
-            asm volatile("bar.sync 1, 256;");
+            if (w + npairs < num_tiles) {
+                int tm2, tn2;
+                tile_coords(p, (w + npairs) / p.splits, tm2, tn2);
+                vec = epi_vec_load(e, p.N, tn2 * BN, (w + npairs) % p.splits, et);
+            }
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
             const int row_base = m0 + q * 32;

@@ -126,18 +126,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 
 // ---- fused epilogue --------------------------------------------------------------------------------
-// per-column vectors of the tile (called by the 128 epilogue threads between two named barriers)
-template <int BN>
-__device__ __forceinline__ void epi_stage_vectors(const Epilogue& e, int N, int n0, int sp, int et, float* s_mul, float* s_bias,
-                                                  float* s_sc, float* s_sh) {
-    for (int c = et; c < BN; c += EPI_THREADS) {
-        const int gc = n0 + c;
-        const bool ok = gc < N;
-        s_mul[c] = e.acc_scale * ((e.col_scale && ok) ? e.col_scale[gc] : 1.f);
-        s_bias[c] = (e.bias && ok && sp == 0) ? e.bias[gc] : 0.f;
-        s_sc[c] = (e.bn_scale && ok) ? e.bn_scale[gc] : 1.f;
-        s_sh[c] = (e.bn_scale && ok) ? e.bn_shift[gc] : 0.f;
-    }
+// Per-column vectors of a tile (multiplier, bias, BatchNorm scale / shift).  Epilogue thread et owns column et of the
+// tile (EPI_THREADS >= BN): it LOADS the four values of the next tile's column into registers while the current tile is
+// drained (epi_vec_load), and STORES them to shared memory between the two named barriers at the top of the next
+// iteration (epi_vec_store).  Loading inside the barriers put ~40 % of the epilogue warps' time on the global-load
+// latency of four scalars (profiles/r1_ncu_full_gemm_tc2_f16f8.md, source page).
+struct EpiVec { float mul, bias, sc, sh; };
+
+__device__ __forceinline__ EpiVec epi_vec_load(const Epilogue& e, int N, int n0, int sp, int c) {
+    const int gc = n0 + c;
+    const bool ok = gc < N;
+    EpiVec v;
+    v.mul = e.acc_scale * ((e.col_scale && ok) ? __ldg(e.col_scale + gc) : 1.f);
+    v.bias = (e.bias && ok && sp == 0) ? __ldg(e.bias + gc) : 0.f;
+    v.sc = (e.bn_scale && ok) ? __ldg(e.bn_scale + gc) : 1.f;
+    v.sh = (e.bn_scale && ok) ? __ldg(e.bn_shift + gc) : 0.f;
+    return v;
+}
+__device__ __forceinline__ void epi_vec_store(const EpiVec& v, int c, float* s_mul, float* s_bias, float* s_sc, float* s_sh) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_mul + c)), "f"(v.mul) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_bias + c)), "f"(v.bias) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_sc + c)), "f"(v.sc) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_sh + c)), "f"(v.sh) : "memory");
 }
 
 // Eight epilogue warps per CTA: warps 2-5 drain columns [0, 128) of a tile, warps 6-9 columns [128, 256); warp w may
