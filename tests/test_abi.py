@@ -101,3 +101,20 @@ def test_communicator_entry_points_without_gpu():
     assert L.mmad_comm_world(None) == 1
     assert L.mmad_comm_init(None, buf, 0, 1) == -1
     assert L.mmad_comm_allreduce_f32(None, None, 4, None) == -1
+
+
+def test_precision_modes_match_the_header():
+    """The host layer's precision names map to the MMAD_PREC_* values of include/mmad.h; a precision outside the
+    enum is rejected by mmad_create before anything touches a GPU."""
+    txt = open(os.path.join(ROOT, "include", "mmad.h")).read()
+    enum = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define MMAD_PREC_([A-Z0-9]+)\s+(\d+)", txt)}
+    assert enum == _lib.PREC == {"fp32": 0, "f16x3": 1, "f16": 2, "f16f8": 3}
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    d = _lib.Desc()
+    d.n_enc = d.n_dec = 1
+    d.enc_widths[0], d.enc_widths[1] = 8, 4
+    d.dec_widths[0], d.dec_widths[1] = 4, 8
+    d.precision = max(enum.values()) + 1
+    assert L.mmad_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"precision" in L.mmad_last_error()
