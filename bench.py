@@ -32,7 +32,7 @@ FLOP_NAP_ROT = 2 * DPRIME * DPRIME  # rotation (d-mu) V: 60 104 648 per window
 N_FIT = 8192                       # NAP fit set (>= D' so K = D')
 DEFAULT_PRECISION = "f16f8"        # MMAD_DEFAULT_PRECISION overrides; f16x3 and fp32 are measured with --precision
 DTYPE_NAME = {"fp32": "f32", "f16x3": "f16x3 split (fp32-equivalent)", "f16": "f16",
-              "f16f8": "f16 + fp8(e4m3) cross terms (fp32 accumulate; scores within 1e-4 of fp32)"}
+              "f16f8": "f16f8 split: fp16 hi*hi + fp8(e4m3) cross terms, fp32 accumulate (DESIGN.md section 3)"}
 
 
 def parse():
