@@ -50,7 +50,8 @@ class AutoEncoder(AbstractModel):
         return self._eng
 
     def set_precision(self, precision):
-        """'fp32' (CUDA-core fp32, default), 'f16x3' (tcgen05 split, 1e-4 parity), 'f16' (one pass)."""
+        """'fp32' (CUDA-core fp32, default), 'f16x3' (tcgen05, fp16 hi/lo split), 'f16f8' (tcgen05, fp16 hi*hi + fp8
+        cross terms: the bulk-scoring mode), 'f16' (one pass).  Error bars: DESIGN.md section 3."""
         self.precision = precision
         return self
 
