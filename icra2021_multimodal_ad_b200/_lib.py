@@ -46,6 +46,7 @@ SIGNATURES = {
     "mmad_create": (_i, [C.POINTER(Desc), C.POINTER(_vp)]),
     "mmad_destroy": (_i, [_vp]),
     "mmad_set_precision": (_i, [_vp, _i]),
+    "mmad_set_option": (_i, [_vp, C.c_char_p, C.c_double]),
     "mmad_set_layer": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmad_workspace_bytes": (_sz, [_vp, _i]),
     "mmad_ae_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "mmad_nap_set_structure": (_i, [_vp, _i]),
     "mmad_fc_layer_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _vp]),
     "mmad_sq_diff_sum": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "mmad_scale_unless_one": (_i, [_vp, _ll, _vp, _vp]),
     "mmad_row_mean_sq": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mmad_vib_reparam": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmad_normalizer_workspace_bytes": (_sz, [_i]),

@@ -42,7 +42,9 @@ def build(force=False, verbose=False):
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static", "-ldl"]
+    # shared CUDA runtime: the process already holds torch's libcudart.so.12 (same soname), so the library shares one runtime
+    # instance with torch instead of embedding a second, static copy; the rpath serves a process that loads it first
+    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "shared", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -62,6 +62,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     const int num_kb = (p.K + BK - 1) / BK;
     const int num_tiles = p.tiles_m * p.tiles_n * p.splits;     // work items: tile-major, split fastest
     // k-block range of split sp: [sp * num_kb / splits, (sp + 1) * num_kb / splits)  (host guarantees splits <= num_kb)
+    auto tile_kb = [&](int n0, int sp) {
+        const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+        return kb_hi - kb_lo;
+    };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -182,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         EpiVec vec;
         if (et < BN && (int)blockIdx.x < num_tiles)
-            vec = epi_vec_load(e, p.N, (((int)blockIdx.x / p.splits) % p.tiles_n) * BN, (int)blockIdx.x % p.splits, et);
+            vec = epi_vec_load(e, p.N, (((int)blockIdx.x / p.splits) % p.tiles_n) * BN, (int)blockIdx.x % p.splits, et,
+                               tile_kb((((int)blockIdx.x / p.splits) % p.tiles_n) * BN, (int)blockIdx.x % p.splits));
         for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
             const int t = w / p.splits, sp = w % p.splits;
             const int m0 = (t / p.tiles_n) * BM, tn = t % p.tiles_n, n0 = tn * BN;
@@ -192,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             asm volatile("bar.sync 1, 256;");
             if (et < BN && w + (int)gridDim.x < num_tiles) {
                 const int w2 = w + (int)gridDim.x;
-                vec = epi_vec_load(e, p.N, ((w2 / p.splits) % p.tiles_n) * BN, w2 % p.splits, et);
+                vec = epi_vec_load(e, p.N, ((w2 / p.splits) % p.tiles_n) * BN, w2 % p.splits, et, tile_kb(((w2 / p.splits) % p.tiles_n) * BN, w2 % p.splits));
             }
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();

@@ -118,6 +118,12 @@ __device__ __forceinline__ void tile_coords(const Tc2Params& p, int t, int& tm, 
     tn = b * p.band + rem % w;
 }
 
+// k-blocks accumulated into the tile at column n0, split sp (the producer's / issuer's kb_lo..kb_hi range)
+__device__ __forceinline__ int tile_kb(const Tc2Params& p, int num_kb, int n0, int sp) {
+    const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+    return kb_hi - kb_lo;
+}
+
 // A_MN / B_MN: the operand is stored [contraction, M or N] (MN-major smem descriptors, TMA boxes of 64 x 64) -- the
 // training GEMMs dW = g_pre^T . in (both) and dX = g_pre . W (B) on the same row-major tensors as the forward pass.
 template <int PASSES, bool A_MN, bool B_MN>
@@ -276,7 +282,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         if (pair < num_tiles) {      // the first tile's column vectors; later ones are loaded one tile ahead
             int tm, tn;
             tile_coords(p, pair / p.splits, tm, tn);
-            vec = epi_vec_load(e, p.N, tn * BN, pair % p.splits, et);
+            vec = epi_vec_load(e, p.N, tn * BN, pair % p.splits, et, tile_kb(p, num_kb, tn * BN, pair % p.splits));
         }
         for (int w = pair; w < num_tiles; w += npairs) {
             const int t = w / p.splits, sp = w % p.splits;
@@ -289,7 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             if (w + npairs < num_tiles) {
                 int tm2, tn2;
                 tile_coords(p, (w + npairs) / p.splits, tm2, tn2);
-                vec = epi_vec_load(e, p.N, tn2 * BN, (w + npairs) % p.splits, et);
+                vec = epi_vec_load(e, p.N, tn2 * BN, (w + npairs) % p.splits, et, tile_kb(p, num_kb, tn2 * BN, (w + npairs) % p.splits));
             }
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();

@@ -133,11 +133,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // latency of four scalars (profiles/r1_ncu_full_gemm_tc2_f16f8.md, source page).
 struct EpiVec { float mul, bias, sc, sh; };
 
-__device__ __forceinline__ EpiVec epi_vec_load(const Epilogue& e, int N, int n0, int sp, int c) {
+__device__ __forceinline__ EpiVec epi_vec_load(const Epilogue& e, int N, int n0, int sp, int c, int n_kb) {
     const int gc = n0 + c;
     const bool ok = gc < N;
     EpiVec v;
-    v.mul = e.acc_scale * ((e.col_scale && ok) ? __ldg(e.col_scale + gc) : 1.f);
+    v.mul = e.acc_scale * fmaf(e.acc_comp, (float)n_kb, 1.f) * ((e.col_scale && ok) ? __ldg(e.col_scale + gc) : 1.f);
     v.bias = (e.bias && ok && sp == 0) ? __ldg(e.bias + gc) : 0.f;
     v.sc = (e.bn_scale && ok) ? __ldg(e.bn_scale + gc) : 1.f;
     v.sh = (e.bn_scale && ok) ? __ldg(e.bn_shift + gc) : 0.f;

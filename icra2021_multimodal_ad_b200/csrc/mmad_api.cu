@@ -67,6 +67,9 @@ struct NapFit {
 
 using namespace mmad;
 
+// Measured on B200 (scripts/calibrate_acc_comp.py): the value that centres the score error of a trained D = 1728 model.
+constexpr double kAccCompDefault = 0.0;
+
 struct mmad_handle {
     mmad_desc_t desc;
     int device = 0;
@@ -97,6 +100,14 @@ struct mmad_handle {
     // set for the duration of a call of <= 64 rows: exact-fp32 weight-streaming kernels (gemm_skinny.cu) instead
     // of 128-row tensor-core tiles, whatever the handle's precision mode
     bool skinny = false;
+    // first-order compensation of the tensor core's truncating accumulation: relative shrink per MMA instruction
+    // (mmad_set_option "acc_comp")
+    double acc_comp = kAccCompDefault;
+    int nap_passes = 0;            // 0 = env MMAD_NAP_PASSES / default 3 (mmad_set_option "nap_passes")
+    bool require_pinned = false;   // mmad_score_host rejects pageable bulk input (mmad_set_option "require_pinned")
+    // TMA descriptors of workspace operands, keyed by (base, rows, k, ld, kind): encoded once, not per layer per call
+    struct MapRec { const void* base; int rows, k, ld, kind; CUtensorMap map; };
+    std::vector<MapRec> maps;
 };
 
 namespace mmad {
@@ -298,6 +309,21 @@ struct ProfScope {   // records a CUDA-event pair around one GEMM launch when pr
     ~ProfScope() { if (b) cudaEventRecord(b, s); }
 };
 
+// cached TMA descriptor of an activation operand in the workspace (kind 0: fp16 [rows, k] with row stride ld halfs;
+// kind 1: fp8 twin, ld in bytes)
+static int operand_map(mmad_t h, CUtensorMap* out, const void* base, int rows, int k, int ld, int kind) {
+    for (auto& m : h->maps)
+        if (m.base == base && m.rows == rows && m.k == k && m.ld == ld && m.kind == kind) { *out = m.map; return MMAD_OK; }
+    int rc = kind ? tc_make_operand_map_f8(out, base, rows, k, ld, 128) : tc_make_operand_map(out, (const __half*)base, rows, k, ld, 128);
+    if (rc) return rc;
+    if (h->maps.size() >= 256) h->maps.erase(h->maps.begin(), h->maps.begin() + 64);
+    h->maps.push_back({base, rows, k, ld, kind, *out});
+    return MMAD_OK;
+}
+
+// MMA instructions per 64-wide k-block and accumulator in each tensor-core mode (the unit of acc_comp)
+static float instr_per_kb(int passes) { return passes == 3 ? 12.f : passes == 1 ? 4.f : 8.f; }
+
 static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogue e, cudaStream_t s) {
     ProfScope prof(h, s, 2.0 * rows * (double)Lr.N * (double)Lr.K);
     e.bias = Lr.bias;
@@ -315,15 +341,16 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     // tensor-core path: TMA descriptors over the fp16 hi/lo twins
     TcOperand A;
     const bool f8 = f8_mode(h);
-    int rc = tc_make_operand_map(&A.hi, in.h, rows, Lr.K, in.ldh, 128);
+    int rc = operand_map(h, &A.hi, in.h, rows, Lr.K, in.ldh, 0);
     if (rc) return rc;
-    if (f8) rc = tc_make_operand_map_f8(&A.lo, in.l, rows, Lr.K, in.ldh * 2, 128);
-    else rc = tc_make_operand_map(&A.lo, in.l ? in.l : in.h, rows, Lr.K, in.ldh, 128);
+    if (f8) rc = operand_map(h, &A.lo, in.l, rows, Lr.K, in.ldh * 2, 1);
+    else rc = operand_map(h, &A.lo, in.l ? in.l : in.h, rows, Lr.K, in.ldh, 0);
     if (rc) return rc;
     A.rows = rows; A.k = Lr.K;
     e.acc_scale = 1.f / (f8 ? Lr.wscale8 : Lr.wscale);
     e.lo_f8 = f8 ? 1 : 0;
     const int passes = tc_passes(h);
+    e.acc_comp = (float)(h->acc_comp * instr_per_kb(passes));
     if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, f8 ? Lr.tcB2_f8 : Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
     return gemm_tc(A, f8 ? Lr.tcB_f8 : Lr.tcB, rows, Lr.N, Lr.K, passes, e, s);
 }
@@ -588,8 +615,27 @@ int mmad_set_precision(mmad_t h, int precision) {
     if (precision != MMAD_PREC_FP32 && !tc_available()) {
         set_error("tensor-core precision requested but the device is not sm_100"); return MMAD_E_UNSUPPORTED;
     }
+    if (h->desc.precision != precision) h->nap.ready = false;   // the fit's variances carry the old mode's rounding noise
     h->desc.precision = precision;
     handle_graph_clear(h);
+    return MMAD_OK;
+}
+
+int mmad_set_option(mmad_t h, const char* name, double value) {
+    if (!h || !name) { set_error("null argument"); return MMAD_E_ARG; }
+    if (!strcmp(name, "acc_comp")) {
+        if (!(value >= 0.0 && value < 1e-6)) { set_error("acc_comp out of range [0, 1e-6)"); return MMAD_E_ARG; }
+        h->acc_comp = value;
+    } else if (!strcmp(name, "nap_passes")) {
+        if (value != 0 && value != 2 && value != 3) { set_error("nap_passes must be 0 (default), 2 or 3"); return MMAD_E_ARG; }
+        h->nap_passes = (int)value;
+    } else if (!strcmp(name, "require_pinned")) {
+        h->require_pinned = value != 0;
+    } else {
+        set_error("unknown option '%s'", name);
+        return MMAD_E_ARG;
+    }
+    handle_graph_clear(h);       // cached graphs hold kernel arguments derived from the options
     return MMAD_OK;
 }
 
@@ -604,6 +650,10 @@ int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const floa
         return MMAD_E_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // new weights: cached score graphs hold kernel arguments derived from the old ones (the f16f8 weight scale), and an
+    // installed NAP fit belongs to the old model (the reference refits on every test() call, novelty_detection.py:56-73)
+    handle_graph_clear(h);
+    h->nap.ready = false;
     MMAD_CUDA_OK(cudaMemsetAsync(L.W, 0, (size_t)L.N * L.Kp * 4, s));
     MMAD_CUDA_OK(cudaMemcpy2DAsync(L.W, (size_t)L.Kp * 4, d_W, (size_t)L.K * 4, (size_t)L.K * 4, L.N,
                                    cudaMemcpyDeviceToDevice, s));
@@ -739,9 +789,9 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
     } else {
         TcOperand A;
         const bool f8 = f8_mode(h);
-        rc = tc_make_operand_map(&A.hi, (const __half*)(ws + p.dh), rows, f.Dp, p.Dselp, 128);
-        if (!rc && f8) rc = tc_make_operand_map_f8(&A.lo, ws + p.dl, rows, f.Dp, p.Dselp * 2, 128);
-        else if (!rc) rc = tc_make_operand_map(&A.lo, (const __half*)(ws + p.dl), rows, f.Dp, p.Dselp, 128);
+        rc = operand_map(h, &A.hi, ws + p.dh, rows, f.Dp, p.Dselp, 0);
+        if (!rc && f8) rc = operand_map(h, &A.lo, ws + p.dl, rows, f.Dp, p.Dselp * 2, 1);
+        else if (!rc) rc = operand_map(h, &A.lo, ws + p.dl, rows, f.Dp, p.Dselp, 0);
         if (rc) return rc;
         A.rows = rows; A.k = f.Dp;
         e.acc_scale = 1.f / ((f8 ? f.wscale8 : f.wscale) * diff_scale(h));
@@ -750,7 +800,8 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         // fp16 (two MMAs per product, +17 % scoring throughput): fine for well-conditioned layer selections (score
         // error ~1e-4), NOT for the rank-deficient all-layers default, whose near-null directions it perturbs beyond
         // the reference's own error (tests/test_gpu_metrics.py::test_nap_all_layers_protocol fails with it)
-        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? nap_passes() : tc_passes(h);
+        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? (h->nap_passes ? h->nap_passes : nap_passes()) : tc_passes(h);
+        e.acc_comp = (float)(h->acc_comp * instr_per_kb(passes));
         if (rows >= kPairMinRows && tc2_available()) rc = gemm_tc2(A, f8 ? f.tcB2_f8 : f.tcB2, rows, f.K, f.Dp, passes, e, s);
         else rc = gemm_tc(A, f8 ? f.tcB_f8 : f.tcB, rows, f.K, f.Dp, passes, e, s);
     }
@@ -988,6 +1039,18 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         return MMAD_E_STATE;
     }
     const int D = D_of(h);
+    if (n > kStreamRows) {
+        // bulk path: cudaMemcpyAsync from PAGEABLE memory stages through the driver and blocks the issuing thread, so the
+        // H2D / compute overlap degrades to what the staging copy allows.  Accepted (documented in mmad.h) unless the
+        // caller asked for strictness with mmad_set_option("require_pinned", 1).
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, h_x) == cudaSuccess && pa.type != cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (!pinned && h->require_pinned) {
+            set_error("mmad_score_host: input is pageable host memory (require_pinned is set): allocate it with cudaMallocHost / cudaHostRegister");
+            return MMAD_E_ARG;
+        }
+    }
     const int chunk = (int)std::min<long long>(host_chunk(), std::max<long long>(128, (n + 127) / 128 * 128));
     if (!h->s_copy) {
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));

@@ -50,6 +50,9 @@ struct Epilogue {
     float bn_eps = 1e-5f;
     float slope = 0.2f;
     float acc_scale = 1.0f;
+    // tensor-core kernels: first-order compensation of the truncating fp32 accumulation -- the accumulator of a tile that
+    // went through n k-blocks is multiplied by (1 + acc_comp * n) on top of acc_scale; 0 = off
+    float acc_comp = 0.0f;
     const float* col_scale = nullptr;  // optional per-column multiplier applied with acc_scale
     float* Y = nullptr;  int ldy = 0;  int y_cols = 0;   // writes cols [0,y_cols); cols >= N are zero-filled
     __half* Yh = nullptr; __half* Yl = nullptr; int ldh = 0;

@@ -52,9 +52,34 @@ __global__ void vib_kernel(const float* __restrict__ o, int ld, int B, int h, in
     }
 }
 
+// buf *= *scale unless *scale == 1 (the autograd seed of a plain loss.backward()): every thread reads the scalar
+// first, so the common case is a launch that touches 4 bytes
+__global__ void scale_unless_one_kernel(float* __restrict__ buf, long long n4, const float* __restrict__ scale) {
+    const float s = __ldg(scale);
+    if (s == 1.f) return;
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = b4[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        b4[i] = v;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int mmad_scale_unless_one(float* d_buf, long long n, const float* d_scale, void* stream) {
+    if (!d_buf || !d_scale || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(d_buf) & 15)) {
+        set_error("mmad_scale_unless_one: buffer must be 16-byte aligned with a multiple of 4 elements");
+        return MMAD_E_ARG;
+    }
+    if (n == 0) return MMAD_OK;
+    scale_unless_one_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(d_buf, n / 4, d_scale);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
 
 int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_out, void* stream) {
     if (!d_a || !d_b || !d_out || n < 0) { set_error("bad argument"); return MMAD_E_ARG; }

@@ -1,7 +1,9 @@
 """Device engine: one ``mmad_t`` handle (packed weights + NAP fit) bound to a CUDA device.
 
 Thin host-side plumbing over the C ABI: torch owns device memory and streams, libmmad
-does the arithmetic.  Nothing here computes on the CPU or through torch ops.
+does the arithmetic.  Nothing on the scoring path computes on the CPU or through torch ops; the NAP FIT (off the
+timed path) calls two library factorizations, ``torch.linalg.eigh`` and ``torch.linalg.qr`` (cuSOLVER), on the
+D' x D' Gram matrix.
 """
 from __future__ import annotations
 
@@ -76,12 +78,20 @@ class Engine:
 
     def set_precision(self, precision: str):
         check(lib().mmad_set_precision(self._h, PREC[precision]))
+        if precision != self.precision:
+            self.nap_range = None        # the library dropped the fit: its variances belong to the old arithmetic
         self.precision = precision
         self._ws = None
         self._ws_rows = 0
 
+    def set_option(self, name: str, value: float):
+        """``mmad_set_option``: 'acc_comp', 'nap_passes', 'require_pinned' (include/mmad.h)."""
+        check(lib().mmad_set_option(self._h, name.encode(), float(value)))
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
-        """Pack a reference-format state dict (keys ``encoder.net.{i}.layer.weight`` ...)."""
+        """Pack a reference-format state dict (keys ``encoder.net.{i}.layer.weight`` ...).  An installed NAP fit
+        belongs to the old weights and is dropped (the reference refits on every test() call)."""
+        self.nap_range = None
         with torch.cuda.device(self.device):
             for m, prefix, widths in ((0, "encoder", self.enc_widths), (1, "decoder", self.dec_widths)):
                 for i in range(len(widths) - 1):

@@ -155,8 +155,33 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
             # (ten medium collectives cost more latency than they hide for a 41 MB model), hence off by default.
             check(lib().mmad_comm_set_grad_allreduce(eng._h, 1 if overlap_grads else 0))
         st.native = True
+        st.native_handle = eng._h.value      # the communicator lives in THIS library handle
         st.grads_in_step = bool(overlap_grads)
+    st.batch_checked = None
     return st
+
+
+def _check_native_comm(st, eng):
+    """The library-owned communicator dies with its handle: if the Engine was recreated (device move) after
+    set_data_parallel, the collectives would silently become no-ops while the statistics are still divided by the
+    global batch."""
+    if getattr(st, "native", False) and st.world > 1 and getattr(st, "native_handle", None) != eng._h.value:
+        raise _lib.MmadError("the model's device engine was recreated after set_data_parallel(): call "
+                             "set_data_parallel(model, group) again")
+
+
+def _check_equal_batches(st, B: int):
+    """BatchNorm statistics and the unbiased running variance are divided by B * world: every rank must hold the same
+    number of rows.  Checked once per batch size (one tiny all-reduce), not per step."""
+    if st.world <= 1 or getattr(st, "batch_checked", None) == B:
+        return
+    import torch.distributed as dist
+    t = torch.tensor([B, -B], dtype=torch.int64, device=st.flat_grad.device if dist.get_backend(st.group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=st.group)
+    if int(t[0]) != B or int(-t[1]) != B:
+        raise ValueError(f"data-parallel step: local batches differ across ranks (this rank {B}, min {int(-t[1])}, "
+                         f"max {int(t[0])}); pad or drop the last shard so every rank holds the same number of rows")
+    st.batch_checked = B
 
 
 def allreduce_gradients(model):
@@ -168,6 +193,7 @@ def allreduce_gradients(model):
             if getattr(st, "grads_in_step", False):
                 return      # already all-reduced per layer inside the captured step (mmad_comm_set_grad_allreduce)
             eng = model.handle_engine()
+            _check_native_comm(st, eng)
             with torch.cuda.device(eng.device):
                 check(lib().mmad_comm_allreduce_f32(eng._h, st.flat_grad.data_ptr(), st.flat_grad.numel(),
                                                     torch.cuda.current_stream().cuda_stream))
@@ -181,6 +207,9 @@ class _FusedStep(torch.autograd.Function):
         st = train_state(model)
         eng = model.handle_engine()
         B = x.shape[0]
+        if st.world > 1:
+            _check_native_comm(st, eng)
+            _check_equal_batches(st, B)
         ws = st.workspace(eng._h, B)
         enc_t, dec_t = st.tables(model)
         cb, _ = st.allreduce_callback()
@@ -198,7 +227,11 @@ class _FusedStep(torch.autograd.Function):
     def backward(ctx, gout):
         st = train_state(ctx.model)
         flat = st.flat_grad
-        flat.mul_(gout)            # d(loss)/d(loss) scaling: one launch over the flat buffer
+        # d(loss)/d(loss) scaling.  loss.backward() -- the reference's step body -- seeds autograd with ones; only a
+        # caller-supplied seed (loss.backward(g), a scaled loss) needs the multiply.  The kernel reads the seed on the
+        # device and returns at once when it is 1 (this used to rewrite 41 MB per step to multiply by 1.0)
+        g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
+        check(lib().mmad_scale_unless_one(flat.data_ptr(), flat.numel(), g.data_ptr(), torch.cuda.current_stream().cuda_stream))
         # hand the gradients over directly (36 AccumulateGrad nodes cost ~0.7 ms of host time per step)
         for p, v in zip(st.params, st.views):
             if p.grad is None:

@@ -13,7 +13,8 @@
  *    mmad_last_error() returns a thread-local message.  No C++ exception crosses.
  *  - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  The caller owns
  *    every buffer; the library allocates device memory only in mmad_create /
- *    mmad_set_layer / mmad_nap_set_fit (packed weights) -- never on the scoring path.
+ *    mmad_set_layer / mmad_nap_set_fit (packed weights), and lazily in the two host-buffer
+ *    entry points that take no workspace (mmad_score_host, mmad_stream_*) -- never in mmad_score.
  *  - scratch comes from a caller-provided workspace sized by the *_workspace_bytes
  *    queries; work is enqueued on the caller's cudaStream_t (passed as void*),
  *    asynchronously, with no implicit synchronisation unless stated.
@@ -72,12 +73,22 @@ int mmad_version(void);
 /* model_builder.py:6-53 (ae_wrapper/get_model): build the packed device model. */
 int mmad_create(const mmad_desc_t* desc, mmad_t* out);
 int mmad_destroy(mmad_t h);
-int mmad_set_precision(mmad_t h, int precision);
+int mmad_set_precision(mmad_t h, int precision);   /* invalidates an installed NAP fit (refit in the new arithmetic) */
+
+/* Tuning knobs of a handle (none of them has a reference counterpart; they select between implementations of the
+ * same reference arithmetic):
+ *   "acc_comp"        relative shrink of a tensor-core accumulator per MMA instruction that the epilogue compensates
+ *                     (first-order correction of the truncating fp32 accumulation); 0 = off
+ *   "nap_passes"      F16X3 NAP rotation: 3 = full split (default), 2 = whitening rows rounded to fp16, 0 = default
+ *   "require_pinned"  1: mmad_score_host returns MMAD_E_ARG for pageable bulk input instead of accepting it
+ * Unknown names return MMAD_E_ARG. */
+int mmad_set_option(mmad_t h, const char* name, double value);
 
 /* Load one FCLayer (layers/fc_layer.py:23-35) from state_dict tensors.  module 0 =
  * encoder, 1 = decoder.  d_W [N,K] row-major fp32, d_b [N].  BatchNorm pointers are
  * NULL for the bare last layer (modules/fc_module.py:49-54).  Repacks (pads K to the
- * tile multiple, splits fp16 hi/lo, folds eval BatchNorm into scale/shift). */
+ * tile multiple, splits fp16 hi/lo, folds eval BatchNorm into scale/shift).  New weights invalidate the
+ * installed NAP fit and the cached launch graphs: run the NAP fit again before asking for NAP scores. */
 int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const float* d_b,
                    const float* d_gamma, const float* d_beta, const float* d_mean,
                    const float* d_var, void* stream);
@@ -118,15 +129,22 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int lay
                float* d_base, float* d_sap, float* d_nap, float* d_diffs,
                void* d_ws, size_t ws_bytes, void* stream);
 
-/* Same as mmad_score with HOST buffers: rows are staged through pinned memory in
- * chunks, host->device copies overlap compute on internal streams, results are copied
- * back, and the call returns after everything has landed (synchronous).  This is the
- * call the e2e benchmark times. */
+/* Same as mmad_score with HOST buffers: rows go to the device in chunks, host->device copies
+ * overlap compute on internal streams, scores come back through pinned staging, and the call
+ * returns after everything has landed (synchronous).  This is the call the e2e benchmark times.
+ * h_x should be PINNED (cudaMallocHost / cudaHostRegister / torch pin_memory): from pageable memory every
+ * chunk copy blocks the calling thread while the driver stages it, and the copy/compute overlap is lost
+ * (accepted, slower; mmad_set_option("require_pinned", 1) turns it into MMAD_E_ARG).
+ * Exception to "the caller owns every buffer": this entry point has no workspace argument, so the library
+ * allocates its device staging + workspace on the first call (and again only if a later call needs more). */
 int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int layer_lo, int layer_hi,
                     float* h_base, float* h_sap, float* h_nap);
 
 /* modules/loss.py:31-32 nn.MSELoss(reduction='sum'): *d_out += sum_i (a_i - b_i)^2 (zero it first). */
 int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_out, void* stream);
+/* models/auto_encoder.py:73 loss.backward(): the gradients of the fused step are d(loss)/d(param) for a unit seed;
+ * d_buf[n] *= *d_scale for any other autograd seed, nothing is touched when *d_scale == 1 (n % 4 == 0, 16-byte aligned). */
+int mmad_scale_unless_one(float* d_buf, long long n, const float* d_scale, void* stream);
 /* utils/metric.py:133,171 (d**2).mean(axis=1) over a [n, cols] matrix with row stride ld. */
 int mmad_row_mean_sq(const float* d_d, int ld, int n, int cols, float* d_out, void* stream);
 /* decorators/variational_info_bottleneck.py:19-42 ('normal'): d_out [B, 2h] -> mu, logvar [B,h],
