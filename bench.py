@@ -6,11 +6,15 @@ synthetic data of data_config.json dims").
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, libmmad.so)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
-A step = every rank scores ``--batch`` windows (base, SAP and NAP scores for each).  One JSON line
-is printed by rank 0.  ``value`` is device-resident throughput, ``e2e`` goes through the
-host-buffer C-ABI call (pinned host memory -> H2D -> scores -> D2H inside the timed region).
+A step = every rank scores ``--batch`` windows (base, SAP and NAP scores for each).  One JSON line is printed by
+rank 0.  The headline (``value`` / ``e2e`` / ``roofline``) is measured in the fp32-PARITY tensor-core mode ``f16x3``
+(every fp32 operand split into an fp16 pair, three MMAs per product; the mode the 1e-4 parity tests hold).  The
+reduced-operand mode ``f16f8`` and the CUDA-core ``fp32`` mode are reported as named extras with their own ``e2e``.
+``value`` is device-resident throughput, ``e2e`` goes through the host-buffer C-ABI call (pinned host memory -> H2D ->
+scores -> D2H inside the timed region).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -24,15 +28,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, BTL, NL = 1728, 100, 5          # sensor=All (utils/data_loaders.py:16-19), novelty_detection.py:147-148
-W_ENC = [1728, 1402, 1076, 751, 425, 100]
-DPRIME = sum(W_ENC)                # 5482
-MAC_ENC = sum(a * b for a, b in zip(W_ENC[:-1], W_ENC[1:]))
-FLOP_SAP = 2 * 3 * MAC_ENC         # enc(x) + dec + enc(xhat): 30 605 754 per window
-FLOP_NAP_ROT = 2 * DPRIME * DPRIME  # rotation (d-mu) V: 60 104 648 per window
-N_FIT = 8192                       # NAP fit set (>= D' so K = D')
-DEFAULT_PRECISION = "f16f8"        # MMAD_DEFAULT_PRECISION overrides; f16x3 and fp32 are measured with --precision
-DTYPE_NAME = {"fp32": "f32", "f16x3": "f16x3 split (fp32-equivalent)", "f16": "f16",
-              "f16f8": "f16f8 split: fp16 hi*hi + fp8(e4m3) cross terms, fp32 accumulate (DESIGN.md section 3)"}
+N_FIT = 65536                      # NAP fit set of configs[2]: total rows, sharded over the ranks
+TRAIN_WARM_STEPS = 20              # 20 Adam steps (B = 256) before the weights are frozen
+DEFAULT_PRECISION = "f16x3"        # the fp32-parity tensor-core mode; f16f8 / fp32 are extras
+DTYPE_NAME = {"fp32": "f32 (CUDA cores)", "f16x3": "f16x3 split (fp32-equivalent operands, fp32 accumulate)", "f16": "f16",
+              "f16f8": "f16f8 split: fp16 hi*hi + fp8(e4m3) cross terms, fp32 accumulate (reduced operand precision, DESIGN.md section 3)"}
+
+
+def widths(d, btl=BTL, nl=NL):
+    diff = (d - btl) / nl
+    return [d] + [int(d - diff * (i + 1)) for i in range(nl - 1)] + [btl]
+
+
+def flops(d, btl=BTL, nl=NL):
+    """(chain FLOP per window: enc(x) + dec + enc(xhat), NAP rotation FLOP per window: dense D' x D')  -- SURVEY 8d."""
+    w = widths(d, btl, nl)
+    mac = sum(a * b for a, b in zip(w[:-1], w[1:]))
+    return 2 * 3 * mac, 2 * sum(w) * sum(w)
+
+
+FLOP_SAP, FLOP_NAP_ROT = flops(D)   # 30 605 754 and 60 104 648
 
 
 def parse():
@@ -46,8 +61,9 @@ def parse():
     p.add_argument("--precision", default=os.environ.get("MMAD_BENCH_PRECISION", "auto"))
     p.add_argument("--no-nap", action="store_true")
     p.add_argument("--cpu-sample", type=int, default=4096)
-    p.add_argument("--no-extras", action="store_true", help="skip the train-step and streaming-latency sections")
+    p.add_argument("--no-extras", action="store_true", help="headline only")
     p.add_argument("--train-batch", type=int, default=256)
+    p.add_argument("--fit-rows", type=int, default=N_FIT)
     return p.parse_args()
 
 
@@ -133,8 +149,8 @@ def cpu_scoring_rate(n_sample, sd, fit, with_nap, repeats=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
-    reference itself cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference itself cannot
+    travel to the GPU box), all host threads, fp32, a bounded sample per step.  The line describes what THIS arm ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -143,6 +159,10 @@ def run_reference(args):
     sd = synth_state_dict(D, BTL, NL, 0)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    xw, _ = synth_windows(256 * 8, D, 7, anomaly_rate=0.0)
+    opt = {}
+    for i in range(TRAIN_WARM_STEPS):       # same preparation as the CUDA arm: 20 Adam steps of the reference's algorithm
+        RO.train_step(xw[(i % 8) * 256:(i % 8 + 1) * 256], sd, opt)
     n = min(args.cpu_sample, 2048)
     fit = None
     if not args.no_nap:   # CPU fit with K = D' = 5482 like the GPU arm (fit time is not part of the metric)
@@ -155,10 +175,15 @@ def run_reference(args):
     rates = [cpu_scoring_rate(n, sd, fit, not args.no_nap)[0] for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     rate = float(np.mean(rates))
+    cfg = workload_config(args, "fp32", windows=n, fit_rows=0 if args.no_nap else 5632)
+    cfg["precision"] = "fp32 (torch CPU, MKL sgemm)"
+    cfg["parallelism"] = f"rank 0 only, {cores} host threads (the reference has no multi-device path)"
+    cfg["note"] = ("same workload definition as the CUDA arm (configs[1], D = 1728, base+SAP+NAP per window); each step is a bounded sample "
+                   f"of {n} windows (the CUDA arm scores {args.batch} per rank per step); a rate, so directly comparable")
     line = {"impl": "reference", "metric": "anomaly-scored samples/sec (SAP+NAP)", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, os.environ.get("MMAD_DEFAULT_PRECISION", DEFAULT_PRECISION) if args.precision == "auto" else args.precision),
+            "config": cfg,
             "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "arithmetic": "fp32 (torch CPU)",
                              "sample": f"{n} windows per step, get_diffs(batch 256)+base+SAP" + ("" if args.no_nap else "+NAP score (K=5482 fit)")},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -166,12 +191,146 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, precision):
+def workload_config(args, precision, windows=None, fit_rows=None):
     return {"workload": "configs[1]: fused AE + RaPP scoring (base+SAP" + ("" if args.no_nap else "+NAP") +
             ") of synthetic 1728-d windows", "input_size": D, "btl_size": BTL, "n_layers": NL,
-            "windows_per_rank_per_step": args.batch, "nap_fit_rows": 0 if args.no_nap else N_FIT,
-            "precision": precision, "l2": "per-step input (%.0f MB) exceeds the 126 MB L2" % (args.batch * D * 4 / 1e6),
+            "windows_per_rank_per_step": args.batch if windows is None else windows,
+            "nap_fit_rows": (0 if args.no_nap else args.fit_rows) if fit_rows is None else fit_rows,
+            "weights": f"random init + {TRAIN_WARM_STEPS} Adam steps (B=256) before freezing (SURVEY 8d)",
+            "precision": precision, "l2": "per-step input (%.0f MB) exceeds the 126 MB L2" % ((args.batch if windows is None else windows) * D * 4 / 1e6),
             "parallelism": f"sample-sharded x{args.gpus}, no data-path collective"}
+
+
+# ---------------------------------------------------------------------------------------
+# preparation: weights after 20 train steps of THIS library (fp32 mode), NAP fit with timed phases
+# ---------------------------------------------------------------------------------------
+def trained_state_dict(local):
+    import types
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    from icra2021_multimodal_ad_b200.models.auto_encoder import AutoEncoder
+    from icra2021_multimodal_ad_b200.optim import Adam
+    from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+    cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision="fp32")
+    m = get_model(cfg)
+    m.load_state_dict(synth_state_dict(D, BTL, NL, 0))
+    eng = types.SimpleNamespace(model=m, optimizer=Adam(m.parameters(), lr=1e-3), config=cfg)
+    xw, _ = synth_windows(256 * 8, D, 7, anomaly_rate=0.0)
+    xw = xw.cuda(local)
+    for i in range(TRAIN_WARM_STEPS):
+        AutoEncoder.step(eng, (xw[(i % 8) * 256:(i % 8 + 1) * 256], None))
+    torch.cuda.synchronize()
+    return {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+
+
+def timed_nap_fit(eng, xtr_dev, world):
+    """Engine.nap_fit with wall-clock phases (setup, untimed in the metric): chain+sum, Gram, exchange, eig+pack, restandardise."""
+    ph = {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fit = eng.nap_fit(xtr_dev, 0, NL + 1, distributed=world > 1, phases=ph)
+    torch.cuda.synchronize()
+    ph["total_s"] = time.perf_counter() - t0
+    return fit, ph
+
+
+# ---------------------------------------------------------------------------------------
+# scoring measurement of one precision mode
+# ---------------------------------------------------------------------------------------
+def measure_scoring(eng, precision, x_dev, x_host_np, want_nap, steps, warmup, world, dev, local, L, B, detailed):
+    import torch.distributed as dist
+    from icra2021_multimodal_ad_b200 import _lib
+
+    def step_dev():
+        return eng.score(x_dev, 0, NL + 1, base=True, sap=True, nap=want_nap)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
+        out = step_dev()
+    barrier()
+    sampler = ClockSampler(local) if detailed else None
+    if sampler:
+        sampler.start()
+    launches0 = L.mmad_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if detailed:
+        torch.cuda.profiler.start()        # ncu --profile-from-start off captures exactly the timed region
+    ev0.record()
+    for _ in range(steps):
+        out = step_dev()
+    ev1.record()
+    barrier()
+    if detailed:
+        torch.cuda.profiler.stop()
+    launches = L.mmad_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms = rmax(ev0.elapsed_time(ev1))
+    value = world * B * steps / (ms / 1e3)
+    res = {"value": value, "unit": "samples/s", "ms_per_step": ms / steps, "dtype": DTYPE_NAME[precision],
+           "gpu_launches": int(launches), "algorithmic_tflops": value * (FLOP_SAP + (FLOP_NAP_ROT if want_nap else 0)) / 1e12}
+    if clocks:
+        res["clocks"] = clocks
+
+    # ---- per-kernel timing of the dominant kernel (fused GEMM) with CUDA events on the launching stream ----
+    if detailed:
+        buf = (C.c_double * 3)()
+        _lib.check(L.mmad_profile_begin(eng._h))
+        psteps = min(steps, 3)
+        for _ in range(psteps):
+            step_dev()
+        _lib.check(L.mmad_profile_end(eng._h, buf))
+        gemm_ms, gemm_flops, gemm_launches = buf[0], buf[1], buf[2]
+        pk, pk_kind = peaks()
+        achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused GEMM, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            tj = tj.get(precision, tj)
+            if tj.get("precision") == precision and tj.get("batch") == B:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        # tensor work per product in fp16-pass units: f16x3 three fp16 MMAs; f16f8 one fp16 MMA + one fp8 MMA over twice the
+        # contraction length at twice the rate (= one more unit); the triangular NAP factor executes half of the rotation
+        mma_passes = {"f16x3": 3, "f16f8": 2}.get(precision, 1)
+        executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT / 2 if want_nap else 0))
+        executed_tf = value / world * executed_per_window / 1e12 if precision != "fp32" else None
+        res["roofline"] = {
+            "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+            "kernel": "fused layer GEMM (%s)" % precision, "peak_source": pk_kind + " bf16 sustained",
+            "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / steps),
+            "executed_mma_tflops": executed_tf, "executed_frac_of_peak": executed_tf / peak_tf if executed_tf and peak_tf else None,
+            "mode_cap_frac": {"f16x3": 1 / 3, "f16f8": 1 / 2}.get(precision),
+            "note": "achieved counts ONE product per MAC of the reference's dense algorithm (SURVEY 8d); f16x3 issues 3 fp16 MMAs per "
+                    "product, so dense work is capped at peak/3 (f16f8: one fp16 + one double-length fp8 MMA = 2 units, cap peak/2); the "
+                    "triangular NAP factor executes half of the rotation, which is why achieved may exceed the dense cap; "
+                    "executed_frac_of_peak is the share of the tensor pipe's peak actually issued"}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host input, scores back on host) ----
+    for _ in range(max(1, warmup // 2)):
+        eng.score_host(x_host_np, 0, NL + 1, base=True, sap=True, nap=want_nap)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(steps, 5))
+    for _ in range(e2e_steps):
+        r = eng.score_host(x_host_np, 0, NL + 1, base=True, sap=True, nap=want_nap)
+    torch.cuda.synchronize()
+    dt = rmax(time.perf_counter() - t0)
+    res["e2e"] = {"value": world * B * e2e_steps / dt, "unit": "samples/s",
+                  "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * 4 * (3 if want_nap else 2), "steps": e2e_steps}
+    assert np.allclose(r["sap"][:1024], out["sap"][:1024].cpu().numpy(), rtol=1e-5)
+    return res, out
 
 
 def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
@@ -181,6 +340,7 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
     import types
     import torch.distributed as dist
     from icra2021_multimodal_ad_b200 import train as T
+    from icra2021_multimodal_ad_b200 import _lib
     from icra2021_multimodal_ad_b200.model_builder import get_model
     from icra2021_multimodal_ad_b200.models.auto_encoder import AutoEncoder
     from icra2021_multimodal_ad_b200.optim import Adam
@@ -213,6 +373,7 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        l0 = _lib.lib().mmad_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
@@ -222,19 +383,24 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / n
-    ms_dev = timed(xd, steps)
-    ms_e2e = timed(xh, steps)
+        return float(t.item()) / n, (_lib.lib().mmad_launch_count() - l0) / n
+    ms_dev, launches = timed(xd, steps)
+    ms_e2e, _ = timed(xh, steps)
     flop = 56366196.0 * batch * world     # fwd + dW + dX per sample
+    pk, _ = peaks()
+    # HBM floor of one step: parameters + Adam moments read and written, gradients written and read
+    step_bytes = 7 * 10225670 * 4
     return {"metric": "VIB-AE train samples/sec" if vib else "AE train samples/sec", "batch_per_gpu": batch, "value": world * batch / (ms_dev / 1e3),
             "ms_per_step": ms_dev, "unit": "samples/s", "algorithmic_tflops": flop / (ms_dev / 1e3) / 1e12,
+            "launches_per_step": launches,
+            "hbm_floor_ms": step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3, "frac_of_hbm_floor": step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3 / ms_dev,
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
                     "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16", "f16f8": "tcgen05 f16x3 split"}[precision],
             "graph": True, "collectives": None if world == 1 else
-            "library-owned NCCL communicator: BatchNorm statistics all-reduced inside the captured step, flat gradient once per step"}
+            "library-owned communicator: BatchNorm statistics all-reduced inside the captured step, flat gradient once per step"}
 
 
-def bench_stream(eng, batches=(1, 8, 10, 64), calls=300, warm=50):
+def bench_stream(eng, batches=(1, 8, 10, 64), calls=400, warm=60):
     """configs[4]: realtime_tester-style scoring (test_file/realtime_tester.py:291-309): one host->device->host
     call per window batch, base + SAP (nap=False there).  p50/p99 wall latency per call."""
     out = {}
@@ -253,6 +419,155 @@ def bench_stream(eng, batches=(1, 8, 10, 64), calls=300, warm=50):
     return out
 
 
+# ---------------------------------------------------------------------------------------
+# comparators
+# ---------------------------------------------------------------------------------------
+def bench_reference_cuda(sd, dev, n=16384, steps=3):
+    """The "existing Blackwell library path" (SURVEY 2 / 8d): the REFERENCE's module structure (nn.Linear -> LeakyReLU(0.2)
+    -> BatchNorm1d, model_builder.py:21-37) in eager PyTorch on cuda:0, cuBLAS SGEMM, scored the way
+    reconstruction_aggregation.py:6-37 + utils/metric.py:132-171,183-222 do it.  Two variants each for fp32 and TF32:
+    'as_written' keeps the reference's per-layer .cpu() copies and host-side NumPy reductions; 'device_only' keeps
+    everything on the device (what a maintainer would get by deleting the copies).  A comparator, not product code."""
+    import torch.nn as nn
+    from icra2021_multimodal_ad_b200.utils.synth import synth_windows
+
+    def module(prefix, w):
+        layers = []
+        for i in range(len(w) - 1):
+            lin = nn.Linear(w[i], w[i + 1])
+            lin.weight.data.copy_(sd[f"{prefix}.net.{i}.layer.weight"]); lin.bias.data.copy_(sd[f"{prefix}.net.{i}.layer.bias"])
+            if i < len(w) - 2:
+                bn = nn.BatchNorm1d(w[i + 1])
+                bn.weight.data.copy_(sd[f"{prefix}.net.{i}.bn.weight"]); bn.bias.data.copy_(sd[f"{prefix}.net.{i}.bn.bias"])
+                bn.running_mean.copy_(sd[f"{prefix}.net.{i}.bn.running_mean"]); bn.running_var.copy_(sd[f"{prefix}.net.{i}.bn.running_var"])
+                layers.append(nn.Sequential(lin, nn.LeakyReLU(0.2), bn))
+            else:
+                layers.append(lin)
+        return layers
+    we = widths(D)
+    enc, dec = module("encoder", we), module("decoder", we[::-1])
+    net_e, net_d = nn.Sequential(*enc).to(dev).eval(), nn.Sequential(*dec).to(dev).eval()
+    x_host, _ = synth_windows(n, D, 1236)
+    dprime = sum(we)
+    g = torch.Generator().manual_seed(3)
+    V = torch.linalg.qr(torch.randn(dprime, dprime, generator=g)).Q.to(dev)      # any orthogonal basis times the rotation
+    mu, var = torch.zeros(dprime, device=dev), torch.ones(dprime, device=dev)
+
+    def as_written(bs=698):
+        per = []
+        for xb in x_host.split(bs):
+            xb = xb.to(dev).float()
+            xt = net_d(net_e(xb))
+            diffs = [(xt - xb).cpu()]
+            for layer in enc:
+                xb = layer(xb); xt = layer(xt)
+                diffs.append((xt - xb).cpu())
+            per.append(diffs)
+        cat = [torch.cat(s, dim=0).numpy() for s in zip(*per)]
+        d = np.concatenate(cat, axis=1)
+        base = (cat[0] ** 2).mean(axis=1); sap = (d ** 2).mean(axis=1)
+        rot = []
+        for i in range(0, len(d), 20000):                     # Rotater.run, utils/normalize.py:72-103
+            rot.append(torch.matmul(torch.from_numpy(d[i:i + 20000]).to(dev) - mu, V).cpu())
+        rot = torch.cat(rot).numpy()
+        nap = (np.abs(rot / np.sqrt(var.cpu().numpy())) ** 2).mean(axis=1)
+        return base, sap, nap
+
+    def device_only(bs=16384):
+        outs = []
+        for xb in x_dev.split(bs):
+            xt = net_d(net_e(xb))
+            diffs = [xt - xb]
+            for layer in enc:
+                xb = layer(xb); xt = layer(xt)
+                diffs.append(xt - xb)
+            d = torch.cat(diffs, dim=1)
+            rot = torch.matmul(d - mu, V)
+            outs.append(((diffs[0] ** 2).mean(1), (d ** 2).mean(1), ((rot * rot) / var).mean(1)))
+        return outs
+
+    x_dev = x_host.to(dev)
+    res = {"rows": n, "note": "eager PyTorch " + torch.__version__ + " on the same B200, the reference's layer structure and get_diffs order "
+                              "(encoder(x) evaluated twice, 20 GEMMs per batch + dense D'xD' rotation)"}
+    with torch.no_grad():
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for name, fn in (("as_written", as_written), ("device_only", device_only)):
+                fn(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    fn()
+                torch.cuda.synchronize()
+                res[("tf32_" if tf32 else "fp32_") + name] = n * steps / (time.perf_counter() - t0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    res["unit"] = "samples/s"
+    return res
+
+
+def bench_metrics(n=10_000_000):
+    """utils/metric.py:29-130 at 10 M scores: device AUROC / AUPRC / quantile / confusion (bit-identical to sklearn / NumPy,
+    tests/test_gpu_metrics.py) against sklearn + NumPy on the host cores, same arrays."""
+    from icra2021_multimodal_ad_b200.utils import metric as M
+    rng = np.random.default_rng(1)
+    y = rng.random(n) < 0.1
+    s = (rng.random(n) + 0.3 * y * rng.random(n)).astype(np.float32)
+    sd_, yd = torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()
+    out = {"n": n}
+    for name, fn in (("auroc", lambda: M.get_auc_roc(sd_, yd)), ("auprc", lambda: M.get_auc_prc(sd_, yd)),
+                     ("quantile_f1", lambda: M.get_f1_score(sd_, sd_, yd))):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v = fn()
+        torch.cuda.synchronize()
+        out[name + "_device_ms"] = (time.perf_counter() - t0) * 1e3
+        out[name] = float(v[0] if isinstance(v, tuple) else v)
+    t0 = time.perf_counter(); a = M.get_auc_roc(s, y); out["auroc_host_arrays_ms"] = (time.perf_counter() - t0) * 1e3   # incl. H2D of 50 MB
+    try:
+        from sklearn import metrics as SK
+        t0 = time.perf_counter(); fpr, tpr, _ = SK.roc_curve(y, s); b = SK.auc(fpr, tpr); out["auroc_sklearn_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); pr, rc, _ = SK.precision_recall_curve(y, s); c = SK.auc(rc, pr); out["auprc_sklearn_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); np.quantile(s, 0.9); out["quantile_numpy_ms"] = (time.perf_counter() - t0) * 1e3
+        out["auroc_bit_identical"] = bool(a == b) and bool(out["auroc"] == b)
+        out["auprc_bit_identical"] = bool(out["auprc"] == c)
+        out["confusion_python_loop_note"] = "the reference's get_confusion_matrix loops over samples in Python (utils/metric.py:84-89): seconds at 10 M; not timed"
+    except Exception as e:   # sklearn missing on the box
+        out["sklearn"] = "unavailable: %s" % e
+    return out
+
+
+def bench_shapes(local, dev, rows=4 * 148 * 128, steps=5):
+    """SURVEY 8d shape sweep: the per-modality networks (utils/data_loaders.py:16-29) and btl=10/n_layers=3, base+SAP scoring,
+    device resident, every arithmetic mode the shape supports."""
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+    out = {}
+    for d, btl, nl in ((64, 100, 5), (128, 100, 5), (512, 100, 5), (1024, 100, 5), (2048, 100, 5), (1728, 10, 3)):
+        x, _ = synth_windows(8192, d, 9)
+        x = x.repeat((rows + 8191) // 8192, 1)[:rows].contiguous().to(dev)
+        rec = {}
+        for prec in ("fp32", "f16x3"):
+            m = get_model(argparse.Namespace(input_size=d, btl_size=btl, n_layers=nl, gpu_id=local, precision=prec)).eval()
+            m.load_state_dict(synth_state_dict(d, btl, nl, 0))
+            eng = m.engine()
+            n = rows if prec != "fp32" or d <= 128 else rows // 4
+            for _ in range(2):
+                eng.score(x[:n], 0, nl + 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                eng.score(x[:n], 0, nl + 1)
+            e1.record()
+            torch.cuda.synchronize()
+            rate = n * steps / (e0.elapsed_time(e1) / 1e3)
+            rec[prec] = {"samples_per_s": rate, "algorithmic_tflops": rate * flops(d, btl, nl)[0] / 1e12,
+                         "hbm_gbs_input": rate * d * 4 / 1e9}
+        out[f"D{d}_btl{btl}_l{nl}"] = rec
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -261,7 +576,7 @@ def main():
     import torch.distributed as dist
     from icra2021_multimodal_ad_b200 import _lib
     from icra2021_multimodal_ad_b200.model_builder import get_model
-    from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+    from icra2021_multimodal_ad_b200.utils.synth import synth_windows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -271,171 +586,85 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     L = _lib.lib()
+    if world > 1:      # communicator set-up (seconds at 8 ranks) is not part of any measured phase
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
 
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("MMAD_DEFAULT_PRECISION", DEFAULT_PRECISION)
-    sd = synth_state_dict(D, BTL, NL, 0)
+    sd = trained_state_dict(local)              # identical on every rank (same seeds, deterministic kernels)
     cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
     model = get_model(cfg).eval()
     model.load_state_dict(sd)
     eng = model.engine()
+    want_nap = not args.no_nap
 
     # ---- NAP fit (setup, untimed): rows sharded over ranks, sum + Gram all-reduced ----
-    fit, fit_s = None, 0.0
-    if not args.no_nap:
-        per = N_FIT // world
-        xtr, _ = synth_windows(per, D, 1234 + rank, anomaly_rate=0.0)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        fit = eng.nap_fit(xtr.to(dev), 0, NL + 1, distributed=world > 1)
-        torch.cuda.synchronize()
-        fit_s = time.perf_counter() - t0
+    fit, fit_ph, xtr = None, {}, None
+    if want_nap:
+        per = args.fit_rows // world
+        xs, _ = synth_windows(8192, D, 1234 + rank, anomaly_rate=0.0)
+        xtr = xs.repeat((per + 8191) // 8192, 1)[:per]
+        xtr = (xtr + 1e-3 * torch.randn(xtr.shape, generator=torch.Generator().manual_seed(rank))).clamp_(0, 1).to(dev)
+        fit, fit_ph = timed_nap_fit(eng, xtr, world)
 
-    # ---- device-resident inputs (generated on the host from the seed, then uploaded) ----
+    # ---- inputs: generated on the host from the seed, pinned, uploaded ----
     B = args.batch
     xh_small, _ = synth_windows(8192, D, 1236 + rank)
     x_host = xh_small.repeat((B + 8191) // 8192, 1)[:B].contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    want_nap = not args.no_nap
-
-    def step_dev():
-        return eng.score(x_dev, 0, NL + 1, base=True, sap=True, nap=want_nap)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        out = step_dev()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = L.mmad_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.profiler.start()        # ncu --profile-from-start off captures exactly the timed region
-    ev0.record()
-    for _ in range(args.steps):
-        out = step_dev()
-    ev1.record()
-    barrier()
-    torch.cuda.profiler.stop()
-    launches = L.mmad_launch_count() - launches0
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms / 1e3)
-
-    # ---- per-kernel timing of the dominant kernel (fused GEMM) with CUDA events, same workload ----
-    import ctypes as C
-    buf = (C.c_double * 3)()
-    _lib.check(L.mmad_profile_begin(eng._h))
-    psteps = min(args.steps, 3)
-    for _ in range(psteps):
-        step_dev()
-    _lib.check(L.mmad_profile_end(eng._h, buf))
-    gemm_ms, gemm_flops, gemm_launches = buf[0], buf[1], buf[2]
-    pk, pk_kind = peaks()
-    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused GEMM, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        tj = tj.get(precision, tj)            # one record per precision mode
-        if tj.get("precision") == precision and tj.get("batch") == args.batch:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    # what the tensor pipe actually executes per window in this mode: 3 (f16x3) or 1 MMA per chain product, and the
-    # triangular NAP factor's half of the rotation products
-    # tensor work per product in fp16-pass units: f16x3 three fp16 MMAs; f16f8 one fp16 MMA + one fp8 MMA over twice the
-    # contraction length at twice the rate (= one more unit)
-    mma_passes = {"f16x3": 3, "f16f8": 2}.get(precision, 1)
-    executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT / 2 if want_nap else 0))
-    executed_tf = value / world * executed_per_window / 1e12 if precision != "fp32" else None
-    pipe_pct = None
-    try:   # time-weighted tensor-pipe activity of the fused GEMM launches from the committed ncu launch list
-        import csv
-        rows = [r for r in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r1_launches_scoring_%s.csv" % precision)) if not l.startswith("=="))]
-        t, a = {}, {}
-        for r in rows:
-            if "gemm_tc" in r["Kernel Name"]:
-                v = float(r["Metric Value"].replace(",", ""))
-                (t if r["Metric Name"].startswith("gpu__time") else a)[r["ID"]] = v
-        if t:
-            pipe_pct = sum(t[k] * a.get(k, 0.0) for k in t) / sum(t.values())
-    except Exception:
-        pass
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                "kernel": "fused layer GEMM (%s)" % precision, "peak_source": pk_kind + " bf16 sustained",
-                "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / args.steps),
-                "executed_mma_tflops": executed_tf, "executed_frac_of_peak": executed_tf / peak_tf if executed_tf and peak_tf else None,
-                "ncu_tensor_pipe_active_pct": pipe_pct,
-                "note": "achieved counts ONE product per MAC of the reference's dense algorithm; f16x3 issues 3 fp16 MMAs per product "
-                        "(cap = peak/3 for dense work), f16f8 one fp16 + one double-length fp8 MMA (= 2 fp16-pass units, cap = peak/2); "
-                        "the triangular NAP factor executes half of the rotation"}
-
-    # ---- end to end through the host-buffer C-ABI call (pinned host input, scores back on host) ----
     xh_np = x_host.numpy()
-    for _ in range(max(1, args.warmup // 2)):
-        eng.score_host(xh_np, 0, NL + 1, base=True, sap=True, nap=want_nap)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        res = eng.score_host(xh_np, 0, NL + 1, base=True, sap=True, nap=want_nap)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * B * e2e_steps / float(t.item()), "unit": "samples/s",
-           "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * 4 * (3 if want_nap else 2), "steps": e2e_steps}
-    assert np.allclose(res["sap"][:1024], out["sap"][:1024].cpu().numpy(), rtol=1e-5)
+
+    primary, out = measure_scoring(eng, precision, x_dev, xh_np, want_nap, args.steps, args.warmup, world, dev, local, L, B, True)
 
     extras = {}
+
+    def extra(name, fn):
+        try:
+            extras[name] = fn()
+        except Exception as e:      # an extra never costs the headline line
+            extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if not args.no_extras:
         tsteps = max(3, min(args.steps * 3, 30))
-        extras["train"] = bench_train(dev, local, world, args.train_batch, tsteps, 3, precision)
-        extras["train_vib"] = bench_train(dev, local, world, args.train_batch, tsteps, 3, precision, vib=True)   # configs[3]
+        tprec = precision
+        extra("train", lambda: bench_train(dev, local, world, args.train_batch, tsteps, 3, tprec))
+        extra("train_vib", lambda: bench_train(dev, local, world, args.train_batch, tsteps, 3, tprec, vib=True))   # configs[3]
+        extra("train_b7000", lambda: bench_train(dev, local, world, 7000, max(3, tsteps // 3), 2, tprec))
         if world == 1:
-            extras["train_b7000"] = bench_train(dev, local, world, 7000, max(3, tsteps // 3), 2, precision)
-            extras["stream_latency"] = bench_stream(eng)
-    # ---- the same step in the full fp16 split (three fp16 MMAs per product), for comparison ----
-    if precision == "f16f8" and not args.no_extras:
-        eng.set_precision("f16x3")
-        if want_nap:
-            eng.nap_fit(xtr.to(dev), 0, NL + 1, distributed=world > 1)
-        for _ in range(2):
-            step_dev()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            step_dev()
-        a1.record()
-        barrier()
-        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        extras["f16x3"] = {"value": world * B * args.steps / (float(t.item()) / 1e3), "unit": "samples/s",
-                           "ms_per_step": float(t.item()) / args.steps, "dtype": DTYPE_NAME["f16x3"]}
+            extra("stream_latency", lambda: bench_stream(eng))
+        # ---- the other arithmetic modes on the same workload, each with its own fit and e2e ----
+        for other in ("f16f8", "fp32"):
+            if other == precision:
+                continue
+
+            def run_other(other=other):
+                eng.set_precision(other)
+                ph = {}
+                if want_nap:
+                    _, ph = timed_nap_fit(eng, xtr, world)
+                nb = B if other != "fp32" else min(B, 148 * 128)        # CUDA-core mode: one wave per step keeps the run short
+                r, _ = measure_scoring(eng, other, x_dev[:nb], xh_np[:nb], want_nap, max(2, args.steps // 3), 2, world, dev, local, L, nb, False)
+                r["windows_per_rank_per_step"] = nb
+                r["nap_fit_s"] = ph.get("total_s")
+                return r
+            extra(other, run_other)
+        eng.set_precision(precision)
+        if world == 1:
+            extra("reference_cuda", lambda: bench_reference_cuda(sd, dev))
+            extra("metrics_10m", bench_metrics)
+            extra("shape_sweep", lambda: bench_shapes(local, dev))
     if rank == 0:
-        cpu_rate, cores = cpu_scoring_rate(args.cpu_sample, sd, fit, want_nap) if world == 1 else (None, None)
-        flop_per_window = FLOP_SAP + (FLOP_NAP_ROT if want_nap else 0)
-        line = {"metric": "anomaly-scored samples/sec (SAP+NAP)", "value": value, "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[precision],
-                "data": "synthetic", "config": workload_config(args, precision), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "clocks": clocks,
-                "algorithmic_tflops": value * flop_per_window / 1e12, "nap_fit_s": fit_s}
+        line = {"metric": "anomaly-scored samples/sec (SAP+NAP)", "value": primary["value"], "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": primary["dtype"],
+                "data": "synthetic", "config": workload_config(args, precision), "e2e": primary["e2e"],
+                "gpu_launches": primary["gpu_launches"], "roofline": primary["roofline"], "clocks": primary["clocks"],
+                "algorithmic_tflops": primary["algorithmic_tflops"], "nap_fit_s": fit_ph.get("total_s", 0.0), "nap_fit_phases": fit_ph}
         line.update(extras)
-        if cpu_rate is not None:
+        if world == 1:
+            cpu_rate, cores = cpu_scoring_rate(args.cpu_sample, sd, fit, want_nap)
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} windows, oracle get_diffs(batch 256)+base+SAP" +
                                               ("+NAP score with the same fit" if want_nap else "")}

@@ -70,6 +70,8 @@ SIGNATURES = {
     "mmad_gram_accumulate": (_i, [_vp, _i, _ll, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmad_rotate": (_i, [_vp, _i, _ll, _i, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]),
     "mmad_standardize": (_i, [_vp, _i, _ll, _i, _vp, _vp, _vp, _i, _vp]),
+    "mmad_tri_pack": (_i, [_vp, _i, _vp, _vp]),
+    "mmad_tri_unpack": (_i, [_vp, _i, _vp, _vp]),
     "mmad_metric_workspace_bytes": (_sz, [_ll]),
     "mmad_auc_roc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),
     "mmad_auc_prc": (_i, [_vp, _vp, _ll, C.POINTER(C.c_double), _vp, _sz, _vp]),

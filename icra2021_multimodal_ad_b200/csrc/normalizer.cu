@@ -69,6 +69,23 @@ size_t ws_need(int cols) {
     return round_up_sz((size_t)kRows * cp * 4, 256) + round_up_sz(cp * cp * 4, 256) + 4 * round_up_sz((size_t)cols * 8, 256) + 1024;
 }
 
+// upper triangle (row-major, row i holds columns i..D-1) <-> full symmetric matrix: the cross-rank exchange of the NAP Gram
+// matrix moves D(D+1)/2 doubles instead of D^2
+__global__ void tri_pack_kernel(const double* __restrict__ full, int D, double* __restrict__ packed) {
+    const int i = blockIdx.x;
+    const size_t off = (size_t)i * D - (size_t)i * (i - 1) / 2 - i;      // packed index of (i, j) = off + j
+    for (int j = i + threadIdx.x; j < D; j += blockDim.x) packed[off + j] = full[(size_t)i * D + j];
+}
+__global__ void tri_unpack_kernel(const double* __restrict__ packed, int D, double* __restrict__ full) {
+    const int i = blockIdx.x;
+    const size_t off = (size_t)i * D - (size_t)i * (i - 1) / 2 - i;
+    for (int j = i + threadIdx.x; j < D; j += blockDim.x) {
+        const double v = packed[off + j];
+        full[(size_t)i * D + j] = v;
+        full[(size_t)j * D + i] = v;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -151,6 +168,22 @@ int mmad_standardize(const float* d_d, int ld, long long n, int cols, const floa
                                                                          d_out + (size_t)r0 * ldo, ldo, cols);
         MMAD_LAUNCHED();
     }
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int mmad_tri_pack(const double* d_full, int D, double* d_packed, void* stream) {
+    if (!d_full || !d_packed || D < 1) { set_error("bad argument"); return MMAD_E_ARG; }
+    tri_pack_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(d_full, D, d_packed);
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+int mmad_tri_unpack(const double* d_packed, int D, double* d_full, void* stream) {
+    if (!d_full || !d_packed || D < 1) { set_error("bad argument"); return MMAD_E_ARG; }
+    tri_unpack_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(d_packed, D, d_full);
+    MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
 }

@@ -80,6 +80,7 @@ class Engine:
         check(lib().mmad_set_precision(self._h, PREC[precision]))
         if precision != self.precision:
             self.nap_range = None        # the library dropped the fit: its variances belong to the old arithmetic
+            self.nap_fit_state = None
         self.precision = precision
         self._ws = None
         self._ws_rows = 0
@@ -92,6 +93,7 @@ class Engine:
         """Pack a reference-format state dict (keys ``encoder.net.{i}.layer.weight`` ...).  An installed NAP fit
         belongs to the old weights and is dropped (the reference refits on every test() call)."""
         self.nap_range = None
+        self.nap_fit_state = None
         with torch.cuda.device(self.device):
             for m, prefix, widths in ((0, "encoder", self.enc_widths), (1, "decoder", self.dec_widths)):
                 for i in range(len(widths) - 1):
@@ -237,38 +239,74 @@ class Engine:
         self._ws = None      # NAP slot count may have changed
         self._ws_rows = 0
 
+    def _allreduce(self, t: torch.Tensor, group=None):
+        """SUM all-reduce of a device tensor across the ranks: through the library's own communicator when one is
+        installed (``mmad_comm_init``, fp32 / fp64), else ``torch.distributed``."""
+        import torch.distributed as dist
+        if group is None and lib().mmad_comm_world(self._h) > 1 and t.dtype in (torch.float32, torch.float64) and t.is_contiguous():
+            fn = lib().mmad_comm_allreduce_f64 if t.dtype == torch.float64 else lib().mmad_comm_allreduce_f32
+            with torch.cuda.device(self.device):
+                check(fn(self._h, t.data_ptr(), t.numel(), _stream()))
+        else:
+            dist.all_reduce(t, group=group)
+
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
                 batch_rows: int = 16384, distributed: Optional[bool] = None,
-                restandardize: bool = True, factor: str = "triangular") -> Dict[str, torch.Tensor]:
+                restandardize: bool = True, factor: str = "triangular", phases: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
         ``distributed`` (default: whether torch.distributed is initialised) / ``group``: the row
-        shards' sum and Gram are all-reduced (one exchange per pass).  mu2 (the Standardizer mean of the rotated
-        train data) is identically zero in exact arithmetic and is installed as zero."""
+        shards' sum and Gram are all-reduced (one exchange per pass; the Gram exchange moves the
+        upper triangle only).  mu2 (the Standardizer mean of the rotated train data) is identically zero in exact
+        arithmetic and is installed as zero.  ``phases`` (a dict) receives wall-clock seconds per phase (adds syncs)."""
+        import time
         import torch.distributed as dist
         use_dist = (dist.is_available() and dist.is_initialized()) if distributed is None else bool(distributed)
         hi = self.n_diffs if hi is None else hi
         dsel = self.concat_width(lo, hi)
         dev = self.device
         n_local = x_train.shape[0]
-        s = torch.zeros(dsel, dtype=torch.float64, device=dev)
+        t_last = [time.perf_counter()]
+
+        def mark(name):
+            if phases is not None:
+                torch.cuda.synchronize(dev)
+                now = time.perf_counter()
+                phases[name] = phases.get(name, 0.0) + now - t_last[0]
+                t_last[0] = now
+        if phases is not None:
+            torch.cuda.synchronize(dev)
+            t_last[0] = time.perf_counter()
+        s = torch.zeros(dsel + 1, dtype=torch.float64, device=dev)      # column sums and, last, the row count
         for r0 in range(0, n_local, batch_rows):
             self.nap_accumulate_sum(x_train[r0:r0 + batch_rows], lo, hi, s)
-        n_total = torch.tensor([n_local], dtype=torch.float64, device=dev)
+        s[dsel] = n_local
+        mark("chain_sum_s")
         if use_dist:
-            dist.all_reduce(s, group=group)
-            dist.all_reduce(n_total, group=group)
-        N = int(n_total.item())
-        mu = (s / N).float()
+            self._allreduce(s, group)
+        N = int(round(s[dsel].item()))
+        mu = (s[:dsel] / N).float()
+        mark("exchange_s")
         gram = torch.zeros(dsel, dsel, dtype=torch.float64, device=dev)
         for r0 in range(0, n_local, batch_rows):
             self.nap_accumulate_gram(x_train[r0:r0 + batch_rows], lo, hi, mu, gram)
+        mark("chain_gram_s")
         if use_dist:
-            dist.all_reduce(gram, group=group)
+            tri = torch.empty(dsel * (dsel + 1) // 2, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                check(lib().mmad_tri_pack(gram.data_ptr(), dsel, tri.data_ptr(), _stream()))
+            self._allreduce(tri, group)
+            with torch.cuda.device(dev):
+                check(lib().mmad_tri_unpack(tri.data_ptr(), dsel, gram.data_ptr(), _stream()))
+            del tri
+        mark("exchange_s")
         fit = nap_fit_from_stats(mu, gram, N, factor=factor)
+        del gram
+        mark("eig_factor_s")
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
         check(lib().mmad_nap_set_structure(self._h, 1 if fit["factor"] == "triangular" else 0))
+        mark("pack_s")
         if restandardize:
             # Standardizer.fit on Rotater.run(train) (utils/metric.py:214-216): third pass, the rotation done
             # by the scoring kernels themselves so their rounding noise in near-null directions (SURVEY F5)
@@ -277,13 +315,40 @@ class Engine:
             rs = torch.zeros(2, K, dtype=torch.float64, device=dev)
             for r0 in range(0, n_local, batch_rows):
                 self.nap_rotate_stats(x_train[r0:r0 + batch_rows], lo, hi, rs[0], rs[1])
+            mark("chain_rotate_s")
             if use_dist:
-                dist.all_reduce(rs, group=group)
+                self._allreduce(rs, group)
             mu2 = rs[0] / N
             var = (rs[1] - N * mu2 * mu2) / (N - 1)
             fit["mu2"], fit["var_eig"], fit["var"] = mu2.float(), fit["var"], var.float()
             self.nap_set_standardizer(fit["var"], fit["mu2"])
+            mark("exchange_s")
+        fit["lo"], fit["hi"], fit["precision"] = lo, hi, self.precision
+        self.nap_fit_state = fit
         return fit
+
+    # ---- NAP-fit checkpoint: (mu, factor rows, var, mu2, N) instead of the raw N x D' train diffs ----
+    def nap_state_dict(self) -> Dict[str, object]:
+        """The installed NAP fit as a compact artefact -- what replaces ``torch.save(train_diffs, config.train_diffs)``
+        (utils/metric.py:205; test_file/FullTest.py:33-44 re-runs the SVD from those diffs on every call)."""
+        f = getattr(self, "nap_fit_state", None)
+        if f is None or self.nap_range is None:
+            raise _lib.MmadError("no NAP fit installed")
+        return {"format": "mmad-nap-fit-1", "lo": f["lo"], "hi": f["hi"], "n": f["n"], "factor": f["factor"],
+                "precision": f["precision"], "enc_widths": list(self.enc_widths),
+                "mu": f["mu"].cpu(), "vt": f["vt"].cpu(), "var": f["var"].cpu(), "mu2": f["mu2"].cpu()}
+
+    def load_nap_state_dict(self, st: Dict[str, object]):
+        if st.get("format") != "mmad-nap-fit-1":
+            raise ValueError("not a NAP-fit checkpoint")
+        if list(st["enc_widths"]) != list(self.enc_widths):
+            raise ValueError("NAP-fit checkpoint belongs to a model with other widths")
+        if st["precision"] != self.precision:
+            raise ValueError(f"NAP fit was made in {st['precision']} arithmetic, the engine runs {self.precision}: refit "
+                             "(the variances of near-null directions carry the mode's rounding noise)")
+        self.nap_set_fit(st["lo"], st["hi"], st["mu"], st["vt"], st["var"], st["mu2"])
+        check(lib().mmad_nap_set_structure(self._h, 1 if st["factor"] == "triangular" else 0))
+        self.nap_fit_state = {k: st[k] for k in ("mu", "vt", "var", "mu2", "n", "factor", "lo", "hi", "precision")}
 
 
 def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "eigen") -> Dict[str, torch.Tensor]:

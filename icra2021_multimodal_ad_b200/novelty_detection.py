@@ -104,7 +104,12 @@ class NoveltyDetecter():
         return (b_auroc, b_aupr), (s_auroc, s_aupr), (n_auroc, n_aupr), df_test
 
     def score_fast(self, model, train_x, valid_x, test_x, test_y, nap=True):
-        """Fused path: per-sample scores never leave the device and diffs are never materialised."""
+        """Fused path: per-sample scores never leave the device and diffs are never materialised.
+
+        NAP-fit checkpoint: with ``config.nap_fit`` set to a path, the fit made from ``train_x`` is saved
+        there as ``(mu, factor rows, var, mu2, N)`` (``Engine.nap_state_dict``) -- the compact replacement of the raw
+        ``train_diffs`` array the reference saves (utils/metric.py:205) and re-SVDs on every offline call
+        (test_file/FullTest.py:33-44).  ``train_x=None`` loads that checkpoint instead of refitting."""
         cfg = self.config
         y = self._labels(test_y)
         end = cfg.n_layers + 1 - getattr(cfg, "end_layer_index", -1)
@@ -112,9 +117,18 @@ class NoveltyDetecter():
         eng = model.eval().engine()
         from .engine import clamp_layer_range
         lo, hi = clamp_layer_range(eng.n_diffs, start, end)
-        if nap:
+        ckpt = getattr(cfg, "nap_fit", None)
+        if nap and train_x is None:
+            if not ckpt:
+                raise ValueError("score_fast(train_x=None) needs config.nap_fit (a saved NAP-fit checkpoint)")
+            eng.load_nap_state_dict(torch.load(ckpt, weights_only=False))
+            if eng.nap_range != (lo, hi):
+                raise ValueError("the NAP-fit checkpoint covers layers %s, the config selects %s" % (eng.nap_range, (lo, hi)))
+        elif nap:
             xt = train_x if isinstance(train_x, torch.Tensor) else torch.from_numpy(np.asarray(train_x))
             eng.nap_fit(xt.to(eng.device).float().reshape(len(xt), -1), lo, hi)
+            if ckpt:
+                torch.save(eng.nap_state_dict(), ckpt)
         with torch.no_grad():
             sv = get_scores(valid_x, model, start, end, nap=nap)
             st = get_scores(test_x, model, start, end, nap=nap)

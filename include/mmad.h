@@ -201,6 +201,10 @@ int mmad_rotate(const float* d_d, int ld, long long n, int cols, const float* d_
                 float* d_out, int ldo, void* d_ws, size_t ws_bytes, void* stream);
 int mmad_standardize(const float* d_d, int ld, long long n, int cols, const float* d_mu, const float* d_var,
                      float* d_out, int ldo, void* stream);
+/* utils/normalize.py:52-70 across ranks: the centred Gram matrix is symmetric, so the cross-rank SUM moves its upper triangle
+ * only.  d_packed holds D(D+1)/2 doubles, row i = columns i..D-1; unpack writes both triangles of d_full[D*D]. */
+int mmad_tri_pack(const double* d_full, int D, double* d_packed, void* stream);
+int mmad_tri_unpack(const double* d_packed, int D, double* d_full, void* stream);
 
 /* ---- metrics: utils/metric.py:29-130 (sklearn roc_curve/auc, precision_recall_curve,
  * np.quantile, F1, confusion) on device.  d_score fp32, d_label uint8 (0/1).

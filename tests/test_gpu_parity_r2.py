@@ -1,0 +1,246 @@
+"""GPU parity tests added in round 2 ("Parity tests for what is benchmarked"):
+
+* the BENCHMARKED NAP -- D = 1728, all layers (novelty_detection.py:56-57,69-70 -> utils/metric.py:183-238), eigen and
+  triangular factor, every tensor-core mode -- against the reference's golden scores and the fp64 value of its formula;
+* single-layer (well-conditioned) NAP within 1e-4 of the fp64 closed form;
+* the pipelined bulk path of mmad_score_host (>= 2048 rows, several host chunks) against the oracle;
+* the VIB decorator kernel (decorators/variational_info_bottleneck.py:19-42) against the reference golden: k > 1
+  expansion, deterministic branch, ValueError / NotImplementedError;
+* trained autoencoders at D in {64, 128, 1728} over 65 536 windows: every window within 1e-4 in the benchmarked mode;
+* state invalidation: new weights / a precision switch drop cached launch graphs and the installed NAP fit.
+"""
+import argparse
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from icra2021_multimodal_ad_b200.utils.synth import synth_state_dict, synth_windows
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(D, btl, nl, sd, precision):
+    from icra2021_multimodal_ad_b200.model_builder import get_model
+    m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=precision))
+    m.load_state_dict(sd)
+    return m.eval()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# NAP, D = 1728, all layers: what bench.py times
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def _nap_case(name, sel):
+    """(golden, state dict, train / test windows, labels, fp64 NAP of the oracle's diffs) -- computed once."""
+    from oracle import rapp_oracle as RO
+    g = load_golden(name)
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    sd = synth_state_dict(D, btl, nl, seed)
+    xtr, _ = synth_windows(g["n_tr"], D, seed + 1, anomaly_rate=0.0)
+    xte, yte = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    lo, hi = sel
+    dtr, dte = RO.get_diffs(xtr, sd), RO.get_diffs(xte, sd)
+    truth = RO.nap_score_fp64(RO.concat_diffs(dtr, lo, hi), RO.concat_diffs(dte, lo, hi))
+    return g, sd, xtr, xte, yte.numpy().astype(bool), truth
+
+
+@pytest.mark.parametrize("factor", ["eigen", "triangular"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16f8"])
+def test_nap_all_layers_protocol_headline_width(precision, factor):
+    """SURVEY 8c-4 at the benchmarked shape.  N_tr = 2048 < D' = 5482, so K = 2048 and besides the w_L = 100
+    structurally null directions (F5: d_5 = W_5 d_4) the last centred component is null too: the reference's own fp32
+    result is far from the fp64 value of its formula.  Required: our median error against that fp64 value is no worse
+    than the reference's, the ranking agrees, and the AUROC (what the score is for) matches the reference's."""
+    from scipy.stats import spearmanr
+    from icra2021_multimodal_ad_b200.utils import metric as M
+    g, sd, xtr, xte, y, truth = _nap_case("score_D1728.pt", (0, 6))
+    D, btl, nl = g["D"], g["btl"], g["n_layers"]
+    ref = g["nap"]["0:7"]["score"].numpy().astype(np.float64)
+    eng = _model(D, btl, nl, sd, precision).engine()
+    eng.nap_fit(xtr.cuda(), 0, nl + 1, distributed=False, factor=factor)
+    new = eng.score(xte.cuda(), 0, nl + 1, base=False, sap=False, nap=True)["nap"].cpu().numpy().astype(np.float64)
+    ok = np.isfinite(new) & np.isfinite(ref)
+    assert ok.mean() > 0.99
+    err_new = np.median(np.abs(new[ok] - truth[ok]) / truth[ok])
+    err_ref = np.median(np.abs(ref[ok] - truth[ok]) / truth[ok])
+    rho_new = spearmanr(new[ok], truth[ok]).correlation
+    rho_ref = spearmanr(ref[ok], truth[ok]).correlation
+    auc_new = M.get_auc_roc(new.astype(np.float32), y)
+    auc_ref = g["nap"]["0:7"]["metrics"][0]
+    print("NAP all layers D=1728 [%s %s]: err_new %.3g err_ref %.3g rho_new %.4f rho_ref %.4f auroc_new %.4f auroc_ref %.4f"
+          % (precision, factor, err_new, err_ref, rho_new, rho_ref, auc_new, auc_ref))
+    assert err_new <= max(err_ref * 1.05, 1e-3)
+    # the fp64 value is computed from the reference's own fp32 diffs and so shares the rounding-noise realisation of
+    # the null directions with the reference only (tests/test_gpu_metrics.py::test_nap_all_layers_protocol)
+    assert rho_new >= min(rho_ref, 0.8)
+    assert abs(auc_new - auc_ref) <= 0.03
+
+
+@pytest.mark.parametrize("factor", ["eigen", "triangular"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+@pytest.mark.parametrize("name,sels", [("score_D64.pt", ((0, 1), (1, 2), (5, 6))), ("score_D1728.pt", ((0, 1),))])
+def test_nap_single_layers_within_1e4_of_fp64(name, sels, precision, factor):
+    """NAP on well-conditioned selections within 1e-4 relative per window.  The yardstick is the fp64
+    closed form on the oracle's diffs: the reference's own fp32 SVD carries ~1e-4 of noise (its golden scores are held
+    to 1e-3 in test_nap_single_layers_match_reference), the fp64 value does not."""
+    for sel in sels:
+        g, sd, xtr, xte, y, truth = _nap_case(name, sel)
+        D, btl, nl = g["D"], g["btl"], g["n_layers"]
+        eng = _model(D, btl, nl, sd, precision).engine()
+        eng.nap_fit(xtr.cuda(), sel[0], sel[1], distributed=False, factor=factor)
+        s = eng.score(xte.cuda(), sel[0], sel[1], base=False, sap=False, nap=True)["nap"].cpu().numpy().astype(np.float64)
+        err = np.abs(s - truth) / truth
+        print(f"NAP {name} {sel} [{precision} {factor}]: max {err.max():.2e} median {np.median(err):.2e}")
+        assert err.max() < 1e-4, (sel, precision, factor)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# mmad_score_host, bulk (pipelined) path
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16f8"])
+@pytest.mark.parametrize("D,btl,nl,n", [(300, 17, 2, 2 * 18944 + 1301), (1728, 100, 5, 18944 + 2100)])
+def test_score_host_pipelined_path_matches_oracle(D, btl, nl, n, precision):
+    """> 2048 rows: double-buffered H2D / compute / D2H over several host chunks with a ragged last chunk; pinned and
+    pageable input give the same scores; base, SAP and NAP against the oracle / the device-resident call."""
+    from oracle import rapp_oracle as RO
+    if precision == "fp32" and D == 1728:
+        n = 2048 + 700          # CUDA-core mode: keep the test short, still the bulk path
+    sd = synth_state_dict(D, btl, nl, 77)
+    x, _ = synth_windows(n, D, 5)
+    ref = RO.get_diffs(x, sd)
+    eng = _model(D, btl, nl, sd, precision).engine()
+    xtr, _ = synth_windows(max(2 * D, 1024), D, 6, anomaly_rate=0.0)
+    eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+    tol = 1e-4 if (precision != "f16f8" or D > 128) else 5e-4
+    xp = x.pin_memory()
+    o = eng.score_host(xp.numpy(), 0, nl + 1, nap=False)
+    np.testing.assert_allclose(o["sap"], RO.sap_score(ref), rtol=tol)
+    np.testing.assert_allclose(o["base"], RO.recon_score(ref[0]), rtol=tol)
+    o2 = eng.score_host(x.numpy().copy(), 0, nl + 1, nap=False)          # pageable
+    assert np.array_equal(o2["sap"], o["sap"]) and np.array_equal(o2["base"], o["base"])
+    # NAP through the host path == NAP through the device path (same kernels, same chunk arithmetic)
+    oh = eng.score_host(xp.numpy(), 0, 1, base=False, sap=False, nap=True)["nap"]
+    od = eng.score(x.cuda(), 0, 1, base=False, sap=False, nap=True)["nap"].cpu().numpy()
+    np.testing.assert_allclose(oh, od, rtol=2e-5)
+    # strict mode rejects pageable bulk input
+    from icra2021_multimodal_ad_b200._lib import MmadError
+    eng.set_option("require_pinned", 1)
+    with pytest.raises(MmadError):
+        eng.score_host(x.numpy().copy(), 0, nl + 1)
+    eng.score_host(xp.numpy(), 0, nl + 1)
+    eng.set_option("require_pinned", 0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# VIB decorator kernel
+# ------------------------------------------------------------------------------------------------------------
+def test_vib_decorator_kernel_matches_reference_golden():
+    from icra2021_multimodal_ad_b200.modules.fc_module import FCModule
+    g = load_golden("vib_D64.pt")
+    k = g["k"]
+    enc = FCModule(input_size=64, output_size=40, hidden_sizes=[56, 48], use_batch_norm=True, act="leakyrelu", last_act=None)
+    enc.load_state_dict(g["sd"])
+    enc = enc.cuda().eval()
+    x = g["x"].cuda()
+    rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())  # noqa: E731
+    with torch.no_grad():
+        assert rel(enc(x), g["plain"]) < 1e-5
+        r = enc(x, distribution="normal", k=k, eps=g["eps"].cuda())
+        assert tuple(r["z"].shape) == tuple(g["z"].shape) and tuple(r["mu"].shape) == tuple(g["mu"].shape)
+        assert rel(r["z"], g["z"]) < 1e-5 and rel(r["mu"], g["mu"]) < 1e-5 and rel(r["logvar"], g["logvar"]) < 1e-5
+        det = enc(x, distribution="normal", k=k, stochastic_inference=False)
+        assert tuple(det["z"].shape) == tuple(g["z_det"].shape) and rel(det["z"], g["z_det"]) < 1e-5
+        for j in range(k):                                     # deterministic branch: mu repeated k times
+            assert torch.equal(det["z"][j], det["mu"])
+        # stochastic_inference=True without eps draws device noise: right shape, mean mu, not mu itself
+        s = enc(x, distribution="normal", k=k)
+        assert tuple(s["z"].shape) == tuple(g["z"].shape) and not torch.equal(s["z"][0], s["mu"])
+        with pytest.raises(ValueError):
+            enc(x, distribution="normal", k=0)
+        with pytest.raises(NotImplementedError):
+            enc(x, distribution="laplace")
+        # the (k, B, h) code goes through a decoder FCModule like the reference's (BatchNorm flattens, fc_layer.py:41-43)
+        dec = FCModule(input_size=20, output_size=64, hidden_sizes=[48], use_batch_norm=True).cuda().eval()
+        out = dec(r["z"])
+        assert tuple(out.shape) == (k, x.shape[0], 64)
+        flat = dec(r["z"].reshape(-1, 20)).reshape(k, x.shape[0], 64)
+        assert torch.equal(out, flat)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# trained models, 65 536 windows
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def _trained_case(D, steps, n):
+    from oracle import rapp_oracle as RO
+    btl, nl = 100, 5
+    sd = synth_state_dict(D, btl, nl, 0)
+    xtr, _ = synth_windows(256 * 8, D, 7, anomaly_rate=0.0)
+    opt = {}
+    for i in range(steps):
+        RO.train_step(xtr[(i % 8) * 256:(i % 8 + 1) * 256], sd, opt)
+    x, _ = synth_windows(n, D, 1236)
+    ref = RO.get_diffs(x, sd, batch_size=4096)
+    return sd, x, RO.sap_score(ref).astype(np.float64), RO.recon_score(ref[0]).astype(np.float64)
+
+
+# (median, max) relative error per window; the benchmarked mode (f16x3) must hold max <= 1e-4 at every width
+TRAINED_BARS = {"fp32": (2e-6, 2e-5), "f16x3": (2e-5, 1e-4)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+@pytest.mark.parametrize("D,steps", [(64, 100), (128, 100), (1728, 60)])
+def test_trained_models_65536_windows(D, steps, precision):
+    """a TRAINED autoencoder (diffs are small differences of large activations) over 65 536 windows,
+    every window's base and SAP score within 1e-4 of the oracle's fp32 scores in the mode bench.py reports."""
+    n = 65536 if precision != "fp32" or D < 1728 else 8192          # CUDA-core mode at D = 1728: 8192 windows
+    sd, x, sap_o, base_o = _trained_case(D, steps, 65536)
+    m = _model(D, 100, 5, sd, precision)
+    o = m.engine().score(x[:n].cuda(), 0, 6)
+    b_med, b_max = TRAINED_BARS[precision]
+    for name, got, want in (("sap", o["sap"], sap_o[:n]), ("base", o["base"], base_o[:n])):
+        err = np.abs(got.cpu().numpy() - want) / want
+        print(f"trained D={D} n={n} {precision} {name}: max {err.max():.2e} p99.9 {np.quantile(err, 0.999):.2e} median {np.median(err):.2e}")
+        assert np.median(err) < b_med and err.max() < b_max, (precision, name)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# state invalidation
+# ------------------------------------------------------------------------------------------------------------
+def test_new_weights_drop_cached_graphs_and_nap_fit():
+    """f16f8: the power-of-two fp8 weight scale is a kernel argument baked into the cached latency-path graph; weights
+    scaled by 4 cross a power of two.  After set_layer the same host call must score the NEW model."""
+    from icra2021_multimodal_ad_b200._lib import MmadError
+    D, btl, nl = 300, 17, 2
+    sd = synth_state_dict(D, btl, nl, 3)
+    x, _ = synth_windows(256, D, 11)
+    m8 = _model(D, btl, nl, sd, "f16f8")
+    m32 = _model(D, btl, nl, sd, "fp32")
+    a = m8.engine().score_host(x.numpy(), 0, nl + 1)
+    np.testing.assert_allclose(a["sap"], m32.engine().score_host(x.numpy(), 0, nl + 1)["sap"], rtol=5e-4)
+    xtr, _ = synth_windows(1024, D, 6, anomaly_rate=0.0)
+    eng = m8.engine()
+    eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+    eng.score(x.cuda(), 0, 1, nap=True)
+    sd4 = {k: (v * 4 if k.endswith("layer.weight") else v) for k, v in sd.items()}
+    m8.load_state_dict(sd4)
+    m32.load_state_dict(sd4)
+    b = m8.engine().score_host(x.numpy(), 0, nl + 1)
+    np.testing.assert_allclose(b["sap"], m32.engine().score_host(x.numpy(), 0, nl + 1)["sap"], rtol=5e-4)
+    assert not np.allclose(a["sap"], b["sap"], rtol=1e-2)
+    # the NAP fit belonged to the old weights
+    assert m8.engine().nap_range is None
+    with pytest.raises(MmadError):
+        m8.engine().score(x.cuda(), 0, 1, nap=True)
+    # ... and to the old arithmetic
+    eng = m8.engine()
+    eng.nap_fit(xtr.cuda(), 0, 1, distributed=False)
+    eng.set_precision("f16x3")
+    assert eng.nap_range is None
+    with pytest.raises(MmadError):
+        eng.score(x.cuda(), 0, 1, nap=True)
+    with pytest.raises(MmadError):
+        eng.set_option("no_such_option", 1)

@@ -40,6 +40,19 @@ def test_train_then_test_like_the_reference_driver():
     fast = det.score_fast(model, xtr, xva, xte, yte.numpy().astype(int))
     assert abs(float(fast["sap"]["auroc"]) - float(sap[0])) < 1e-6      # same scores -> same curve
     assert abs(float(fast["base"]["auroc"]) - float(base[0])) < 1e-6
+    # NAP-fit checkpoint: the compact (mu, factor, var, mu2, N) artefact replaces the raw train diffs --
+    # a second detector scores from it without the train set and gets the same NAP scores
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg.nap_fit = os.path.join(tmp, "nap_fit.pt")
+        a = det.score_fast(model, xtr, xva, xte, yte.numpy().astype(int))
+        raw_bytes = len(xtr) * model.engine().concat_width(0, cfg.n_layers + 1) * 4
+        assert os.path.getsize(cfg.nap_fit) < raw_bytes          # smaller than torch.save(train_diffs) (utils/metric.py:205)
+        model.engine().load_state_dict(model.state_dict())        # drops the installed fit
+        assert model.engine().nap_range is None
+        b = NoveltyDetecter(cfg).score_fast(model, None, xva, xte, yte.numpy().astype(int))
+        assert torch.equal(a["nap"]["score"], b["nap"]["score"]) and a["nap"]["auroc"] == b["nap"]["auroc"]
 
 
 def _free_port():
