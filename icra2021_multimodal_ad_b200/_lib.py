@@ -53,6 +53,7 @@ SIGNATURES = {
     "mmad_recon_loss": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "mmad_score": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmad_score_host": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp]),
+    "mmad_stream_input": (_i, [_vp, _i, _i, C.POINTER(C.POINTER(C.c_float)), C.POINTER(_i)]),
     "mmad_concat_width": (_i, [_vp, _i, _i]),
     "mmad_nap_accumulate_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmad_nap_accumulate_gram": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -68,7 +68,7 @@ struct NapFit {
 using namespace mmad;
 
 // Measured on B200 (scripts/calibrate_acc_comp.py): the value that centres the score error of a trained D = 1728 model.
-constexpr double kAccCompDefault = 0.0;
+constexpr double kAccCompDefault = 1.6e-8;
 
 struct mmad_handle {
     mmad_desc_t desc;
@@ -108,6 +108,8 @@ struct mmad_handle {
     // TMA descriptors of workspace operands, keyed by (base, rows, k, ld, kind): encoded once, not per layer per call
     struct MapRec { const void* base; int rows, k, ld, kind; CUtensorMap map; };
     std::vector<MapRec> maps;
+    unsigned long long weights_gen = 0;   // incremented by every mmad_set_layer
+    void* stream_state = nullptr;         // one-launch realtime kernel (stream.cu)
 };
 
 namespace mmad {
@@ -506,6 +508,14 @@ cudaStream_t handle_capture_stream(mmad_t h) {
     return h->s_capture;
 }
 
+LayerF32 handle_layer_f32(mmad_t h, int module, int index) {
+    const Layer& L = (module == 0 ? h->enc : h->dec)[index];
+    return LayerF32{L.K, L.N, L.Kp, L.Np, L.has_bn, L.W, L.bias, L.scale, L.shift};
+}
+unsigned long long handle_weights_gen(mmad_t h) { return h->weights_gen; }
+void* handle_stream_get(mmad_t h) { return h->stream_state; }
+void handle_stream_set(mmad_t h, void* state) { h->stream_state = state; }
+
 LayerView handle_layer(mmad_t h, int module, int index) {
     const Layer& L = (module == 0 ? h->enc : h->dec)[index];
     LayerView v;
@@ -585,6 +595,8 @@ int mmad_create(const mmad_desc_t* d, mmad_t* out) {
 int mmad_destroy(mmad_t h) {
     if (!h) return MMAD_OK;
     mmad_comm_destroy(h);
+    stream_state_free(h->stream_state);
+    h->stream_state = nullptr;
     for (auto& L : h->enc) free_layer(L);
     for (auto& L : h->dec) free_layer(L);
     cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);
@@ -654,6 +666,7 @@ int mmad_set_layer(mmad_t h, int module, int index, const float* d_W, const floa
     // installed NAP fit belongs to the old model (the reference refits on every test() call, novelty_detection.py:56-73)
     handle_graph_clear(h);
     h->nap.ready = false;
+    h->weights_gen += 1;
     MMAD_CUDA_OK(cudaMemsetAsync(L.W, 0, (size_t)L.N * L.Kp * 4, s));
     MMAD_CUDA_OK(cudaMemcpy2DAsync(L.W, (size_t)L.Kp * 4, d_W, (size_t)L.K * 4, (size_t)L.K * 4, L.N,
                                    cudaMemcpyDeviceToDevice, s));
@@ -1039,6 +1052,13 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         return MMAD_E_STATE;
     }
     const int D = D_of(h);
+    if (n <= stream_max_rows() && !h_nap && stream_enabled() && !h->prof) {
+        // ---- realtime path (test_file/realtime_tester.py:291-309): the whole chain in ONE cooperative launch, input and
+        // scores through mapped pinned memory (stream.cu); exact fp32 whatever the handle's precision mode ----
+        for (auto& L : h->enc) if (!L.loaded) { set_error("weights not loaded"); return MMAD_E_STATE; }
+        rc = stream_score(h, h_x, ldx, (int)n, lo, hi, h_base, h_sap);
+        if (rc != MMAD_E_UNSUPPORTED) return rc;       // unsupported shape: the graph-replay path below
+    }
     if (n > kStreamRows) {
         // bulk path: cudaMemcpyAsync from PAGEABLE memory stages through the driver and blocks the issuing thread, so the
         // H2D / compute overlap degrades to what the staging copy allows.  Accepted (documented in mmad.h) unless the
@@ -1171,6 +1191,18 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         rc = drain(k & 1);
         if (rc) return rc;
     }
+    return MMAD_OK;
+}
+
+int mmad_stream_input(mmad_t h, int lo, int hi, float** h_in, int* max_rows) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((rc = check_range(h, lo, hi))) return rc;
+    if (!h_in) { set_error("null argument"); return MMAD_E_ARG; }
+    float* p = stream_input_buffer(h, lo, hi);
+    if (!p) return MMAD_E_UNSUPPORTED;
+    *h_in = p;
+    if (max_rows) *max_rows = stream_max_rows();
     return MMAD_OK;
 }
 

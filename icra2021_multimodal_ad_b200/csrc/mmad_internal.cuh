@@ -133,6 +133,18 @@ struct LayerView { int K, N, Kp, Np; __half* Wh; __half* Wl; float wscale; };
 const mmad_desc_t* handle_desc(mmad_t h);
 LayerView handle_layer(mmad_t h, int module, int index);
 
+// fp32 view of a packed layer (stream.cu): W [N, Kp] zero padded, bias / eval-BN scale / shift [Np]
+struct LayerF32 { int K, N, Kp, Np; bool has_bn; const float* W; const float* bias; const float* scale; const float* shift; };
+LayerF32 handle_layer_f32(mmad_t h, int module, int index);
+unsigned long long handle_weights_gen(mmad_t h);      // incremented by every mmad_set_layer
+void* handle_stream_get(mmad_t h);                    // opaque state of the one-launch realtime kernel (stream.cu)
+void handle_stream_set(mmad_t h, void* state);
+void stream_state_free(void* state);
+bool stream_enabled();                                // MMAD_NO_STREAM_KERNEL=1 disables
+int stream_max_rows();
+int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, float* h_base, float* h_sap);
+float* stream_input_buffer(mmad_t h, int lo, int hi);
+
 // CUDA-graph cache of a handle (launch-bound sequences: the train step, small-batch scoring)
 bool graphs_enabled();                       // MMAD_NO_GRAPHS=1 disables
 cudaGraphExec_t handle_graph_find(mmad_t h, const std::string& key, unsigned long long* launches);

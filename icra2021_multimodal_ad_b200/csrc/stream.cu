@@ -1,0 +1,458 @@
+// Realtime scoring in ONE launch (test_file/realtime_tester.py:291-309: batch_size = 10 windows per call, base + SAP,
+// nap=False): the whole 15-step chain  enc(x) -> dec -> enc(xhat) + diffs + score reduction  runs inside one cooperative
+// kernel, exact fp32 FMA arithmetic, for calls of <= 64 windows.
+//
+// Why not the per-layer kernels: a call touches 61 MB of fp32 weights (L2-resident between calls) and 15 dependent
+// layers; fifteen launches (graph replay) + one H2D + one D2H cost 127 us at one window, of which ~10 us is math.  Here:
+//   * one CTA per SM (148 x 512 threads), launched cooperatively; layers are separated by a device-wide barrier
+//     (one atomic arrive + acquire poll per CTA, ~1 us), not by kernel boundaries;
+//   * every CTA owns ceil(N / grid) output columns of a layer (10 of 1402, 12 of 1728 ...) over the full K extent, so all SMs
+//     pull the layer's weights from L2 at once; its weight slice for layer l+1 is prefetched into shared memory with
+//     cp.async BEFORE it waits at the barrier of layer l (weights do not depend on the previous layer);
+//   * the input comes straight from the caller's pinned, device-mapped buffer (staged once by the grid), the two score
+//     vectors go straight back to mapped host memory followed by a sequence flag the host spins on -- the call is a
+//     doorbell, not H2D + graph + D2H + stream synchronise.
+// Inside a CTA the 16 warps form 4 column groups x 4 k-quarters; a warp accumulates NB rows x 4 columns from shared memory
+// (activations re-used across its columns), lanes split k; partial sums meet in shared memory in a fixed order, so
+// results are deterministic.  Diffs are taken against the stashed enc(x) activations in the epilogue; their squares are
+// summed per CTA and row, and the last CTA to finish adds the per-CTA partials in a fixed order.
+#include <chrono>
+
+#include "mmad_internal.cuh"
+
+namespace mmad {
+
+namespace {
+
+constexpr int ST_THREADS = 512;
+constexpr int ST_CW = 4;              // columns per warp
+constexpr int ST_CG = 4;              // column groups per CTA
+constexpr int ST_KQ = 4;              // k quarters per CTA
+constexpr int ST_CPC = ST_CW * ST_CG; // columns per CTA and layer (upper bound)
+constexpr int ST_MAX_ROWS = 64;
+constexpr int ST_MAX_STEPS = 3 * MMAD_MAX_LAYERS;
+constexpr int ST_SMEM_CAP = 227 * 1024 - 1024;
+
+struct StStep {
+    const float* W; const float* bias; const float* scale; const float* shift;   // scale == nullptr: bare Linear
+    const float* in; float* out; const float* ref;
+    int K4;            // padded contraction length / 4 (== row stride of W and of `in` in float4)
+    int N, ldout, ldref;
+    int cpc;           // columns per CTA = ceil(N / grid)
+    int diff;          // partial-sum slot of the diff this step produces, -1: none
+};
+
+struct StPlan {
+    int n_steps, n_diffs, lo, hi, D, ldx, grid;
+    float inv_base, inv_sap, slope;
+    float* x_dev;      // [ST_MAX_ROWS, ldx] staged input, zero padded
+    float* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2
+    int nact[MMAD_MAX_LAYERS + 2];   // CTAs that own columns of diff l
+    StStep step[ST_MAX_STEPS];
+};
+
+__device__ __forceinline__ void st_cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void st_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Device-wide barrier of a cooperatively launched grid: monotonically increasing arrival counter (never reset; `target`
+// carries the call's base).  The poll is bounded: a protocol bug traps instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ULL);
+        const long long t0 = clock64();
+        while (ld_acquire(bar) < target) {
+            if (clock64() - t0 > 2000000000LL) {
+                printf("mmad stream kernel: grid barrier timed out (block %d, target %llu)\n", blockIdx.x, target);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
+                    unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base) {
+    extern __shared__ __align__(16) float st_smem[];
+    __shared__ float s_red[ST_KQ][NB][ST_CPC];
+    __shared__ float s_sq[NB][ST_CPC];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, grid = gridDim.x;
+    const int n_steps = P->n_steps;
+    const float slope = P->slope;
+    unsigned long long arrivals = bar_base;
+
+    // ---- weight slice of step 0 (independent of the input) ----
+    auto prefetch_weights = [&](int s) -> uint32_t {    // returns the float4 count of the slice
+        const StStep& st = P->step[s];
+        const int c_lo = cta * st.cpc;
+        int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
+        const int n4 = ncols * st.K4;
+        const float4* src = reinterpret_cast<const float4*>(st.W) + (size_t)c_lo * st.K4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st_smem);
+        for (int i = tid; i < n4; i += ST_THREADS) st_cp16(dst + i * 16, src + i);
+        st_cp_commit();
+        return (uint32_t)(st.cpc * st.K4);
+    };
+    uint32_t w4 = prefetch_weights(0);
+
+    // ---- stage the input rows from the caller's mapped host buffer into device memory (once, by the whole grid) ----
+    {
+        const int D4 = P->D >> 2, ld4 = P->ldx >> 2;         // D % 4 == 0 is checked at open
+        const int total = rows * D4;
+        float4* xd = reinterpret_cast<float4*>(P->x_dev);
+        const float4* xs = reinterpret_cast<const float4*>(x_src);
+        for (int i = cta * ST_THREADS + tid; i < total; i += grid * ST_THREADS) {
+            const int r = i / D4, c = i - r * D4;
+            xd[(size_t)r * ld4 + c] = xs[i];
+        }
+    }
+    arrivals += grid;
+    grid_barrier(bar, arrivals);
+
+    for (int s = 0; s < n_steps; ++s) {
+        const StStep st = P->step[s];
+        const int K4 = st.K4;
+        const int c_lo = cta * st.cpc;
+        int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
+        const float4* wsm = reinterpret_cast<const float4*>(st_smem);
+        float4* asm4 = reinterpret_cast<float4*>(st_smem) + w4;
+        const int cg = warp & (ST_CG - 1), kq = warp >> 2;
+        const int cl0 = cg * ST_CW;
+        int nj = ncols - cl0; if (nj > ST_CW) nj = ST_CW;
+        const int q = K4 / ST_KQ;                                  // K4 is a multiple of 16
+        const int k_lo = kq * q, k_hi = k_lo + q;
+        for (int r0 = 0; r0 < rows; r0 += NB) {
+            int nb = rows - r0; if (nb > NB) nb = NB;
+            if (ncols > 0) {
+                // activations of rows r0 .. r0 + nb (contiguous: row stride == padded K)
+                const float4* src = reinterpret_cast<const float4*>(st.in) + (size_t)r0 * K4;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(asm4);
+                for (int i = tid; i < nb * K4; i += ST_THREADS) st_cp16(dst + i * 16, src + i);
+            }
+            st_cp_commit();
+            st_cp_wait_all();
+            __syncthreads();
+            if (nj > 0) {
+                float acc[NB][ST_CW];
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int j = 0; j < ST_CW; ++j) acc[b][j] = 0.f;
+                for (int k4 = k_lo + lane; k4 < k_hi; k4 += 32) {
+                    float4 w[ST_CW];
+#pragma unroll
+                    for (int j = 0; j < ST_CW; ++j) w[j] = j < nj ? wsm[(cl0 + j) * K4 + k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float4 a = asm4[b * K4 + k4];
+#pragma unroll
+                        for (int j = 0; j < ST_CW; ++j) acc[b][j] = dot4(a, w[j], acc[b][j]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int j = 0; j < ST_CW; ++j) {
+                        float v = acc[b][j];
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        if (lane == 0) s_red[kq][b][cl0 + j] = v;
+                    }
+            }
+            __syncthreads();
+            // ---- epilogue: thread (b, cl) ----
+            if (tid < NB * ST_CPC) {
+                const int b = tid / ST_CPC, cl = tid % ST_CPC;
+                float sq = 0.f;
+                if (b < nb && cl < ncols) {
+                    const int c = c_lo + cl, r = r0 + b;
+                    float v = ((s_red[0][b][cl] + s_red[1][b][cl]) + s_red[2][b][cl]) + s_red[3][b][cl];
+                    v += __ldg(st.bias + c);
+                    if (st.scale) {
+                        v = v > 0.f ? v : v * slope;
+                        v = fmaf(v, __ldg(st.scale + c), __ldg(st.shift + c));
+                    }
+                    if (st.out) st.out[(size_t)r * st.ldout + c] = v;
+                    if (st.ref) {
+                        const float d = v - __ldcg(st.ref + (size_t)r * st.ldref + c);
+                        sq = d * d;
+                    }
+                }
+                if (st.diff >= 0) s_sq[b][cl] = sq;
+            }
+            __syncthreads();
+            if (st.diff >= 0 && tid < nb && ncols > 0) {
+                float t = 0.f;
+                for (int cl = 0; cl < ncols; ++cl) t += s_sq[tid][cl];
+                P->partial[((size_t)st.diff * grid + cta) * ST_MAX_ROWS + r0 + tid] = t;
+            }
+        }
+        // the next step's weight slice travels while this CTA waits for the others
+        if (s + 1 < n_steps) {
+            __syncthreads();            // everybody is done reading the current slice
+            w4 = prefetch_weights(s + 1);
+            arrivals += grid;
+            grid_barrier(bar, arrivals);
+        }
+    }
+
+    // ---- the last CTA to finish adds the per-CTA partial sums (fixed order) and rings the doorbell ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(bar, 1ULL);
+        s_last = (old + 1 == arrivals + grid) ? 1 : 0;
+        if (s_last) __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    const int nd = P->n_diffs;
+    for (int r = warp; r < rows; r += ST_THREADS / 32) {
+        float base = 0.f, sap = 0.f;
+        for (int l = 0; l < nd; ++l) {
+            const int na = P->nact[l];
+            float t = 0.f;
+            for (int c = lane; c < na; c += 32) t += __ldcg(P->partial + ((size_t)l * grid + c) * ST_MAX_ROWS + r);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if (l == 0) base = t;
+            if (l >= P->lo && l < P->hi) sap += t;
+        }
+        if (lane == 0) {
+            out_host[r] = base * P->inv_base;
+            out_host[ST_MAX_ROWS + r] = sap * P->inv_sap;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flag_host) = seq;
+        __threadfence_system();
+    }
+}
+
+struct StreamState {
+    int lo = -1, hi = -1, grid = 0;
+    bool ok = false;
+    size_t smem[3] = {0, 0, 0};          // dynamic shared memory of the NB = 1 / 4 / 16 instantiations
+    bool fits[3] = {false, false, false};
+    StPlan* d_plan = nullptr;
+    float* d_x = nullptr;                // staged input
+    float* d_act = nullptr;              // activation buffers (stash, decoder ping-pong, enc(xhat) ping-pong)
+    float* d_partial = nullptr;
+    unsigned long long* d_bar = nullptr;
+    float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
+    float* h_out = nullptr; float* d_out = nullptr;     // pinned + mapped scores [2][64] + flag
+    unsigned long long seq = 0, bar_base = 0;
+    unsigned long long weights_gen = 0;
+    cudaStream_t stream = nullptr;
+    int D = 0, n_steps = 0;
+};
+
+void stream_free(StreamState* s) {
+    if (!s) return;
+    cudaFree(s->d_plan); cudaFree(s->d_x); cudaFree(s->d_act); cudaFree(s->d_partial); cudaFree(s->d_bar);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+template <int NB> int launch(StreamState* S, int rows) {
+    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, nullptr, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base};
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(S->d_out + 2 * ST_MAX_ROWS);
+    args[4] = (void*)&flag;
+    const int idx = NB == 1 ? 0 : (NB == 4 ? 1 : 2);
+    MMAD_CUDA_OK(cudaLaunchCooperativeKernel((const void*)stream_chain_kernel<NB>, dim3(S->grid), dim3(ST_THREADS), args, S->smem[idx], S->stream));
+    return MMAD_OK;
+}
+
+}  // namespace
+
+void stream_state_free(void* p) { stream_free(static_cast<StreamState*>(p)); }
+
+bool stream_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMAD_NO_STREAM_KERNEL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+int stream_max_rows() { return ST_MAX_ROWS; }
+
+// (Re)build the plan for diffs [lo, hi) of the handle's current weights.  Returns MMAD_E_UNSUPPORTED when the model does
+// not fit the kernel (width > grid * 16 columns, D % 4 != 0, shared memory).
+static int stream_prepare(mmad_t h, int lo, int hi) {
+    StreamState* S = static_cast<StreamState*>(handle_stream_get(h));
+    const mmad_desc_t* d = handle_desc(h);
+    const int L = d->n_enc, Ld = d->n_dec, D = d->enc_widths[0];
+    if (S && S->ok && S->lo == lo && S->hi == hi && S->weights_gen == handle_weights_gen(h)) return MMAD_OK;
+    if (!S) {
+        S = new StreamState();
+        handle_stream_set(h, S);
+        int dev = 0, sms = 0, coop = 0;
+        MMAD_CUDA_OK(cudaGetDevice(&dev));
+        MMAD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MMAD_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (!coop) { set_error("device does not support cooperative launches"); return MMAD_E_UNSUPPORTED; }
+        S->grid = sms;
+        S->D = D;
+        MMAD_CUDA_OK(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_plan, sizeof(StPlan)));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_bar, 8));
+        MMAD_CUDA_OK(cudaMemset(S->d_bar, 0, 8));
+        MMAD_CUDA_OK(cudaHostAlloc(&S->h_in, (size_t)ST_MAX_ROWS * D * 4, cudaHostAllocMapped));
+        MMAD_CUDA_OK(cudaHostAlloc(&S->h_out, (size_t)(2 * ST_MAX_ROWS + 4) * 4, cudaHostAllocMapped));
+        memset(S->h_out, 0, (size_t)(2 * ST_MAX_ROWS + 4) * 4);
+        MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_in, S->h_in, 0));
+        MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_out, S->h_out, 0));
+    }
+    S->ok = false;
+    if (D % 4) { set_error("stream kernel needs D %% 4 == 0"); return MMAD_E_UNSUPPORTED; }
+    // activation buffers: stash H_1..H_L, decoder ping-pong (2), xhat, enc(xhat) ping-pong (2)
+    std::vector<LayerF32> enc(L), dec(Ld);
+    int maxw = round_up(D, kPad);
+    for (int i = 0; i < L; ++i) { enc[i] = handle_layer_f32(h, 0, i); maxw = std::max(maxw, enc[i].Np); }
+    for (int i = 0; i < Ld; ++i) { dec[i] = handle_layer_f32(h, 1, i); maxw = std::max(maxw, dec[i].Np); }
+    for (auto& l : enc) if (l.N > S->grid * ST_CPC) { set_error("layer too wide for the stream kernel"); return MMAD_E_UNSUPPORTED; }
+    for (auto& l : dec) if (l.N > S->grid * ST_CPC) { set_error("layer too wide for the stream kernel"); return MMAD_E_UNSUPPORTED; }
+    const size_t buf = (size_t)ST_MAX_ROWS * maxw;
+    const int n_buf = L + 5;
+    if (!S->d_act) {
+        MMAD_CUDA_OK(cudaMalloc(&S->d_act, buf * n_buf * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_x, buf * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_partial, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
+    }
+    MMAD_CUDA_OK(cudaMemset(S->d_act, 0, buf * n_buf * 4));       // padding columns stay zero for ever
+    MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 4));
+    MMAD_CUDA_OK(cudaMemset(S->d_partial, 0, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
+    auto B = [&](int i) { return S->d_act + buf * i; };           // 0..L-1 stash, L/L+1 decoder, L+2 xhat, L+3/L+4 enc(xhat)
+    StPlan P;
+    memset(&P, 0, sizeof P);
+    P.lo = lo; P.hi = hi; P.D = D; P.ldx = round_up(D, kPad); P.grid = S->grid;
+    P.n_diffs = L + 1;
+    P.slope = d->lrelu_slope;
+    P.x_dev = S->d_x; P.partial = S->d_partial;
+    P.inv_base = 1.f / D;
+    int dsel = 0;
+    for (int l = lo; l < hi; ++l) dsel += d->enc_widths[l];
+    P.inv_sap = 1.f / dsel;
+    int ns = 0;
+    size_t need[3] = {0, 0, 0};
+    auto add = [&](const LayerF32& Lr, const float* in, float* out, int ldout, const float* ref, int ldref, int diff) {
+        StStep& st = P.step[ns++];
+        st.W = Lr.W; st.bias = Lr.bias; st.scale = Lr.has_bn ? Lr.scale : nullptr; st.shift = Lr.has_bn ? Lr.shift : nullptr;
+        st.in = in; st.out = out; st.ref = ref;
+        st.K4 = Lr.Kp / 4; st.N = Lr.N; st.ldout = ldout; st.ldref = ldref;
+        st.cpc = (Lr.N + S->grid - 1) / S->grid;
+        st.diff = diff;
+        if (diff >= 0) P.nact[diff] = (Lr.N + st.cpc - 1) / st.cpc;
+        const int nbs[3] = {1, 4, 16};
+        for (int i = 0; i < 3; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + nbs[i]) * Lr.Kp * 4);
+    };
+    const float* cur = S->d_x;
+    for (int l = 0; l < L; ++l) { add(enc[l], cur, B(l), enc[l].Np, nullptr, 0, -1); cur = B(l); }
+    const int want_enc2 = hi > 1;
+    for (int l = 0; l < Ld; ++l) {
+        const bool last = l == Ld - 1;
+        float* out = last ? B(L + 2) : B(L + (l & 1));
+        add(dec[l], cur, out, dec[l].Np, last ? S->d_x : nullptr, P.ldx, last ? 0 : -1);
+        cur = out;
+    }
+    if (want_enc2) {
+        const int last = std::min(L, hi - 1);
+        for (int l = 1; l <= last; ++l) {
+            float* out = l == last ? nullptr : B(L + 3 + (l & 1));
+            add(enc[l - 1], cur, out, enc[l - 1].Np, B(l - 1), enc[l - 1].Np, l);
+            cur = out;
+        }
+    }
+    P.n_steps = ns;          // diffs beyond `last` have no producers: nact == 0, their sum is 0
+    S->n_steps = ns;
+    MMAD_CUDA_OK(cudaMemcpy(S->d_plan, &P, sizeof P, cudaMemcpyHostToDevice));
+    const void* kern[3] = {(const void*)stream_chain_kernel<1>, (const void*)stream_chain_kernel<4>, (const void*)stream_chain_kernel<16>};
+    for (int i = 0; i < 3; ++i) {
+        S->smem[i] = need[i];
+        S->fits[i] = need[i] <= (size_t)ST_SMEM_CAP;
+        if (S->fits[i]) {
+            MMAD_CUDA_OK(cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[i]));
+            int nblk = 0;
+            MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern[i], ST_THREADS, need[i]));
+            if (nblk < 1) S->fits[i] = false;
+        }
+    }
+    S->lo = lo; S->hi = hi;
+    S->weights_gen = handle_weights_gen(h);
+    S->ok = true;
+    return MMAD_OK;
+}
+
+// One realtime call: rows <= 64 windows from host memory, base and SAP scores back on the host.  Returns
+// MMAD_E_UNSUPPORTED (without side effects) when the model / row count does not fit, so the caller can take the graph path.
+int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, float* h_base, float* h_sap) {
+    if (rows < 1 || rows > ST_MAX_ROWS) { set_error("stream kernel: 1..64 rows"); return MMAD_E_UNSUPPORTED; }
+    int rc = stream_prepare(h, lo, hi);
+    if (rc) return rc;
+    StreamState* S = static_cast<StreamState*>(handle_stream_get(h));
+    const int idx = rows <= 1 ? 0 : (rows <= 4 ? 1 : 2);
+    if (!S->fits[idx]) { set_error("stream kernel: shared memory"); return MMAD_E_UNSUPPORTED; }
+    const int D = S->D;
+    if (h_x != S->h_in) {
+        if (ldx == D) memcpy(S->h_in, h_x, (size_t)rows * D * 4);
+        else for (int r = 0; r < rows; ++r) memcpy(S->h_in + (size_t)r * D, h_x + (size_t)r * ldx, (size_t)D * 4);
+    }
+    S->seq += 1;
+    if (idx == 0) rc = launch<1>(S, rows); else if (idx == 1) rc = launch<4>(S, rows); else rc = launch<16>(S, rows);
+    if (rc) return rc;
+    MMAD_LAUNCHED();
+    S->bar_base += (unsigned long long)S->grid * (unsigned long long)(S->n_steps + 1);
+    // the doorbell: the kernel's last store is the sequence number, written after the scores (system-scope fences)
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(S->h_out + 2 * ST_MAX_ROWS);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*flag != S->seq) {
+        __builtin_ia32_pause();
+        if ((++spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) break;
+    }
+    if (*flag != S->seq) {        // never rang: fetch the launch / execution error
+        cudaError_t e = cudaStreamSynchronize(S->stream);
+        if (e != cudaSuccess || *flag != S->seq) {
+            S->ok = false;
+            set_error("stream kernel did not complete: %s", cudaGetErrorString(e));
+            return MMAD_E_CUDA;
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (h_base) memcpy(h_base, S->h_out, (size_t)rows * 4);
+    if (h_sap) memcpy(h_sap, S->h_out + ST_MAX_ROWS, (size_t)rows * 4);
+    return MMAD_OK;
+}
+
+float* stream_input_buffer(mmad_t h, int lo, int hi) {
+    if (stream_prepare(h, lo, hi)) return nullptr;
+    return static_cast<StreamState*>(handle_stream_get(h))->h_in;
+}
+
+}  // namespace mmad

@@ -197,6 +197,15 @@ class Engine:
             check(lib().mmad_score_host(self._h, x.ctypes.data, x.shape[1], n, lo, hi, p("base"), p("sap"), p("nap")))
         return out
 
+    def stream_input(self, lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+        """``mmad_stream_input``: the pinned, device-mapped ``[64, D]`` input buffer of the one-launch realtime kernel as a
+        NumPy array.  ``score_host(buf[:n], ...)`` on a leading slice of it skips the staging copy."""
+        hi = self.n_diffs if hi is None else hi
+        p, mr = C.POINTER(C.c_float)(), C.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().mmad_stream_input(self._h, lo, hi, C.byref(p), C.byref(mr)))
+        return np.ctypeslib.as_array(p, shape=(mr.value, self.D))
+
     # ---- NAP fit ------------------------------------------------------------------------
     def nap_accumulate_sum(self, x: torch.Tensor, lo: int, hi: int, acc: torch.Tensor):
         x = self._check_x(x)

@@ -140,6 +140,15 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int lay
 int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int layer_lo, int layer_hi,
                     float* h_base, float* h_sap, float* h_nap);
 
+/* Realtime calls (test_file/realtime_tester.py:291-309: 10 windows per call, base + SAP, nap=False): mmad_score_host with
+ * n <= 64 and h_nap == NULL runs the whole chain in ONE cooperative launch of exact-fp32 kernels, whatever the handle's
+ * precision mode; input and scores travel through pinned, device-mapped memory and completion is a sequence flag the
+ * host spins on (no H2D / D2H copies, no stream synchronise).  mmad_stream_input returns that pinned input buffer
+ * ([*max_rows, D] floats, owned by the handle): a caller that assembles its windows there and passes the same pointer to
+ * mmad_score_host saves the staging memcpy.  MMAD_E_UNSUPPORTED when the model does not fit the kernel (D % 4 != 0, a
+ * layer wider than 16 columns per SM); such models keep the graph-replay path inside mmad_score_host. */
+int mmad_stream_input(mmad_t h, int layer_lo, int layer_hi, float** h_in, int* max_rows);
+
 /* modules/loss.py:31-32 nn.MSELoss(reduction='sum'): *d_out += sum_i (a_i - b_i)^2 (zero it first). */
 int mmad_sq_diff_sum(const float* d_a, const float* d_b, long long n, float* d_out, void* stream);
 /* models/auto_encoder.py:73 loss.backward(): the gradients of the fused step are d(loss)/d(param) for a unit seed;

@@ -90,6 +90,26 @@ def scoring_case(name, D, btl, nl, seed, n_tr, n_va, n_te, bs, selections, keep_
     print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
 
 
+def nap_full_rank_case(name, D, btl, nl, seed, n_tr, n_te):
+    """All-layers NAP (novelty_detection.py:56-57,69-70) with N_tr >= D' so that K = D' like the benchmarked fit: only the
+    per-window NAP scores and their metrics are kept."""
+    model, cfg = ref_model(D, btl, nl, seed)
+    xtr, _ = synth_windows(n_tr, D, seed + 1, anomaly_rate=0.0)
+    xva, _ = synth_windows(256, D, seed + 2, anomaly_rate=0.0)
+    xte, yte = synth_windows(n_te, D, seed + 3, anomaly_rate=0.15)
+    y = yte.numpy().astype(bool)
+    with torch.no_grad():
+        dtr = get_diffs(xtr, model, batch_size=256)
+        dva = get_diffs(xva, model)
+        dte = get_diffs(xte, model, batch_size=256)
+    nap = quiet(M.get_d_norm_loss, dtr, dva, dte, y, cfg, start_layer_index=0, end_layer_index=nl + 2,
+                gpu_id=-1, norm_type=2, f1_quantiles=[.90])
+    torch.save(dict(D=D, btl=btl, n_layers=nl, seed=seed, n_tr=n_tr, n_te=n_te,
+                    nap=dict(score=torch.from_numpy(np.asarray(nap[0])), metrics=[float(v) for v in nap[1:]])),
+               os.path.join(HERE, name))
+    print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
+
+
 def train_case(name, D, btl, nl, seed, B, steps, full_state):
     model, cfg = ref_model(D, btl, nl, seed)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
@@ -217,6 +237,9 @@ def metric_cases(name):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nap_full":     # the slow case alone (SVD of 6144 x 5482 on the CPU)
+        nap_full_rank_case("nap_D1728_full.pt", 1728, 100, 5, 31, n_tr=6144, n_te=384)
+        sys.exit(0)
     # real per-modality dims (utils/data_loaders.py:16-29): force_torque 64, mic 128
     scoring_case("score_D64.pt", 64, 100, 5, 11, n_tr=700, n_va=90, n_te=130, bs=48,
                  selections=[(0, 7), (0, 1), (1, 2), (2, 5), (5, 6), (9, 3), (0, None)])
@@ -230,3 +253,4 @@ if __name__ == "__main__":
     vib_case("vib_D64.pt")
     feature_case("features.pt")
     metric_cases("metrics_golden.json")
+    nap_full_rank_case("nap_D1728_full.pt", 1728, 100, 5, 31, n_tr=6144, n_te=384)

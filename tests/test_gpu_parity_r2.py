@@ -47,18 +47,31 @@ def _nap_case(name, sel):
     return g, sd, xtr, xte, yte.numpy().astype(bool), truth
 
 
+@functools.lru_cache(maxsize=None)
+def _nap_full_case():
+    from oracle import rapp_oracle as RO
+    g = load_golden("nap_D1728_full.pt")
+    D, btl, nl, seed = g["D"], g["btl"], g["n_layers"], g["seed"]
+    sd = synth_state_dict(D, btl, nl, seed)
+    xtr, _ = synth_windows(g["n_tr"], D, seed + 1, anomaly_rate=0.0)
+    xte, yte = synth_windows(g["n_te"], D, seed + 3, anomaly_rate=0.15)
+    truth = RO.nap_score_fp64(RO.concat_diffs(RO.get_diffs(xtr, sd)), RO.concat_diffs(RO.get_diffs(xte, sd)))
+    return g, sd, xtr, xte, yte.numpy().astype(bool), truth
+
+
 @pytest.mark.parametrize("factor", ["eigen", "triangular"])
 @pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16f8"])
 def test_nap_all_layers_protocol_headline_width(precision, factor):
-    """SURVEY 8c-4 at the benchmarked shape.  N_tr = 2048 < D' = 5482, so K = 2048 and besides the w_L = 100
-    structurally null directions (F5: d_5 = W_5 d_4) the last centred component is null too: the reference's own fp32
-    result is far from the fp64 value of its formula.  Required: our median error against that fp64 value is no worse
-    than the reference's, the ranking agrees, and the AUROC (what the score is for) matches the reference's."""
+    """SURVEY 8c-4 at the BENCHMARKED shape: D = 1728, all six diffs (D' = 5482), fit set of N_tr = 6144 >= D' rows so
+    that K = D' like bench.py's fit, golden scores from the unmodified reference (tests/golden/make_golden.py nap_full).
+    The selection is rank deficient by construction (F5: d_5 = W_5 d_4), so the reference's own fp32 result is far from
+    the fp64 value of its formula.  Required: our median error against that fp64 value is no worse than the
+    reference's, the ranking agrees with it about as well as the reference's does, and the AUROC matches."""
     from scipy.stats import spearmanr
     from icra2021_multimodal_ad_b200.utils import metric as M
-    g, sd, xtr, xte, y, truth = _nap_case("score_D1728.pt", (0, 6))
+    g, sd, xtr, xte, y, truth = _nap_full_case()
     D, btl, nl = g["D"], g["btl"], g["n_layers"]
-    ref = g["nap"]["0:7"]["score"].numpy().astype(np.float64)
+    ref = g["nap"]["score"].numpy().astype(np.float64)
     eng = _model(D, btl, nl, sd, precision).engine()
     eng.nap_fit(xtr.cuda(), 0, nl + 1, distributed=False, factor=factor)
     new = eng.score(xte.cuda(), 0, nl + 1, base=False, sap=False, nap=True)["nap"].cpu().numpy().astype(np.float64)
@@ -69,14 +82,32 @@ def test_nap_all_layers_protocol_headline_width(precision, factor):
     rho_new = spearmanr(new[ok], truth[ok]).correlation
     rho_ref = spearmanr(ref[ok], truth[ok]).correlation
     auc_new = M.get_auc_roc(new.astype(np.float32), y)
-    auc_ref = g["nap"]["0:7"]["metrics"][0]
-    print("NAP all layers D=1728 [%s %s]: err_new %.3g err_ref %.3g rho_new %.4f rho_ref %.4f auroc_new %.4f auroc_ref %.4f"
-          % (precision, factor, err_new, err_ref, rho_new, rho_ref, auc_new, auc_ref))
+    auc_ref, auc_truth = g["nap"]["metrics"][0], M.get_auc_roc(truth.astype(np.float32), y)
+    print("NAP all layers D=1728 N_tr=6144 [%s %s]: err_new %.3g err_ref %.3g rho_new %.4f rho_ref %.4f auroc new %.4f ref %.4f fp64 %.4f"
+          % (precision, factor, err_new, err_ref, rho_new, rho_ref, auc_new, auc_ref, auc_truth))
     assert err_new <= max(err_ref * 1.05, 1e-3)
-    # the fp64 value is computed from the reference's own fp32 diffs and so shares the rounding-noise realisation of
-    # the null directions with the reference only (tests/test_gpu_metrics.py::test_nap_all_layers_protocol)
-    assert rho_new >= min(rho_ref, 0.8)
+    # the fp64 value is computed from the oracle's fp32 diffs: it shares the rounding-noise realisation of the null
+    # directions with the reference only (tests/test_gpu_metrics.py::test_nap_all_layers_protocol)
+    assert rho_new >= min(rho_ref - 0.1, 0.8)
     assert abs(auc_new - auc_ref) <= 0.03
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16f8"])
+def test_nap_all_layers_rank_limited_fit(precision):
+    """The other committed reference golden, score_D1728.pt: N_tr = 2048 < D' = 5482.  The centred fit matrix has rank
+    N_tr - 1, its last component is a pure rounding-noise direction with variance ~0, and the score is dominated by it:
+    the REFERENCE's own scores are uncorrelated with the fp64 value of its formula (measured rho_ref = -0.0015,
+    err_ref = 1.0), so no per-window comparison means anything here.  What can be held: finite scores and the AUROC."""
+    from icra2021_multimodal_ad_b200.utils import metric as M
+    g, sd, xtr, xte, y, _ = _nap_case("score_D1728.pt", (0, 1))        # cheap selection: only the inputs are used here
+    D, btl, nl = g["D"], g["btl"], g["n_layers"]
+    eng = _model(D, btl, nl, sd, precision).engine()
+    eng.nap_fit(xtr.cuda(), 0, nl + 1, distributed=False)
+    new = eng.score(xte.cuda(), 0, nl + 1, base=False, sap=False, nap=True)["nap"].cpu().numpy()
+    assert np.isfinite(new).mean() > 0.99
+    auc_new, auc_ref = M.get_auc_roc(new, y), g["nap"]["0:7"]["metrics"][0]
+    print("NAP all layers D=1728 N_tr=2048 [%s]: auroc new %.4f ref %.4f" % (precision, auc_new, auc_ref))
+    assert abs(auc_new - auc_ref) <= 0.05
 
 
 @pytest.mark.parametrize("factor", ["eigen", "triangular"])
@@ -244,3 +275,47 @@ def test_new_weights_drop_cached_graphs_and_nap_fit():
         eng.score(x.cuda(), 0, 1, nap=True)
     with pytest.raises(MmadError):
         eng.set_option("no_such_option", 1)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# realtime entry point
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,btl,nl", [(1728, 100, 5), (128, 100, 5), (300, 17, 2)])
+def test_realtime_detecter_test_call(D, btl, nl, tmp_path):
+    """test_file/realtime_tester.py:291-304: ``detecter.test(model, fusion_representation, config, nap=False)`` -> one SAP
+    score per window of the (batch_size = 10, D) matrix; host matrices run in one launch (stream kernel), every batch
+    size 1..64, deterministic; nap=True scores from a NAP-fit checkpoint."""
+    from icra2021_multimodal_ad_b200.NoveltyDetecter import NoveltyDetecter
+    from icra2021_multimodal_ad_b200.novelty_detection import NoveltyDetecter as Trainer
+    from icra2021_multimodal_ad_b200._lib import lib
+    from oracle import rapp_oracle as RO
+    sd = synth_state_dict(D, btl, nl, 9)
+    cfg = argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision="f16x3", batch_size=10,
+                             start_layer_index=0, end_layer_index=-1)
+    m = _model(D, btl, nl, sd, "f16x3")
+    det = NoveltyDetecter(cfg)
+    for n in (1, 2, 4, 5, 10, 16, 17, 40, 64):
+        x, _ = synth_windows(n, D, 200 + n)
+        want = RO.sap_score(RO.get_diffs(x, sd))
+        l0 = lib().mmad_launch_count()
+        got = det.test(m, x, cfg, nap=False)
+        assert lib().mmad_launch_count() - l0 == 1          # one kernel launch per realtime call
+        assert isinstance(got, list) and len(got) == n
+        np.testing.assert_allclose(np.asarray(got), want, rtol=5e-5)
+        assert det.test(m, x.numpy(), cfg, nap=False) == got
+        np.testing.assert_allclose(np.asarray(det.test(m, x.cuda(), cfg, nap=False)), want, rtol=1e-4)
+    buf = det.window_buffer(m, cfg)
+    assert buf.shape == (64, D) and buf.dtype == np.float32
+    x, _ = synth_windows(10, D, 77)
+    buf[:10] = x.numpy()
+    np.testing.assert_allclose(np.asarray(det.test(m, buf[:10], cfg)), RO.sap_score(RO.get_diffs(x, sd)), rtol=5e-5)
+    # NAP from a checkpoint (well-conditioned selection d_0)
+    cfg.end_layer_index = nl                    # diffs[0:1]
+    cfg.nap_fit = str(tmp_path / "nap_fit.pt")
+    xtr, _ = synth_windows(max(2 * D, 600), D, 6, anomaly_rate=0.0)
+    xva, _ = synth_windows(64, D, 7, anomaly_rate=0.0)
+    xte, yte = synth_windows(100, D, 8)
+    fast = Trainer(cfg).score_fast(m, xtr, xva, xte, yte.numpy().astype(int))
+    m.engine().load_state_dict(m.state_dict())          # drop the fit; the realtime detector reloads it from the checkpoint
+    got = det.test(m, xte[:10], cfg, nap=True)
+    np.testing.assert_allclose(np.asarray(got), fast["nap"]["score"][:10].cpu().numpy(), rtol=1e-3)
