@@ -31,7 +31,7 @@ namespace {
 struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n;
-    int tri;             // B is upper triangular (B[n,k] = 0 for k < n): k-blocks left of the tile's first row are skipped
+    int tri;             // leading rows of B that are upper triangular (B[n,k] = 0 for k < n): tiles inside skip the k-blocks left of their first row
     int splits;          // split-K factor (plain epilogue only): work item = (tile, split), atomically accumulated
 };
 
@@ -63,7 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     const int num_tiles = p.tiles_m * p.tiles_n * p.splits;     // work items: tile-major, split fastest
     // k-block range of split sp: [sp * num_kb / splits, (sp + 1) * num_kb / splits)  (host guarantees splits <= num_kb)
     auto tile_kb = [&](int n0, int sp) {
-        const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+        const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
         return kb_hi - kb_lo;
     };
 
@@ -91,7 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w % p.splits;
                 const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
-                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
@@ -134,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w % p.splits;
                 const int n0 = (t % p.tiles_n) * BN;
-                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
                 const uint32_t idesc = make_idesc(n_eff, A_MN, B_MN);
@@ -326,7 +326,7 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (K + BK - 1) / BK;
     p.splits = 1;
-    p.tri = e.b_upper_tri ? 1 : 0;
+    p.tri = e.b_upper_tri;     // leading rows of B that are upper triangular (tiles entirely inside skip k-blocks left of them)
     if (!p.tri && e.plain && e.split_k_ok) {
         // split-K when it fills the machine better: cost ~ waves x k-blocks per item; ties go to fewer splits
         // (every split adds one atomic pass over the output)

@@ -120,7 +120,8 @@ __device__ __forceinline__ void tile_coords(const Tc2Params& p, int t, int& tm, 
 
 // k-blocks accumulated into the tile at column n0, split sp (the producer's / issuer's kb_lo..kb_hi range)
 __device__ __forceinline__ int tile_kb(const Tc2Params& p, int num_kb, int n0, int sp) {
-    const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+    constexpr int BN = BN2;
+    const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
     return kb_hi - kb_lo;
 }
 
@@ -185,7 +186,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                 n_eff = (n_eff + 15) & ~15;
                 const int m0 = tm * 256 + (int)rank * BM;                     // this CTA's 128 rows of A
                 const int nb0 = n0 + (int)rank * (n_eff >> 1);                // this CTA's half of the B rows
-                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     if (rank == 0) mbar_expect_tx(smem_u32(&full[stage]), 2 * C::kStageBytes);
@@ -230,7 +231,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                 int tm, tn;
                 tile_coords(p, t, tm, tn);
                 const int n0 = tn * BN;
-                const int kb_lo = p.tri ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
+                const int kb_lo = ((n0 + BN < p.N ? n0 + BN : p.N) <= p.tri) ? n0 / BK : sp * num_kb / p.splits, kb_hi = (sp + 1) * num_kb / p.splits;
                 int n_eff = p.N - n0; if (n_eff > BN) n_eff = BN;
                 n_eff = (n_eff + 15) & ~15;
                 const uint32_t idesc = make_idesc_pair(n_eff) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16);
@@ -370,7 +371,7 @@ int gemm_tc2(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pa
     p.M = M; p.N = N; p.K = K;
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + BN2 - 1) / BN2;
-    p.tri = e.b_upper_tri ? 1 : 0;
+    p.tri = e.b_upper_tri;     // leading rows of B that are upper triangular (tiles entirely inside skip k-blocks left of them)
     // balanced bands of at most 12 n-tiles: the NAP factor's 22 n-tiles run as 2 x 11 (A is streamed twice, the 61 MB band
     // of B plus the ~7 row panels in flight stay L2 resident); MMAD_TC2_BAND overrides for experiments
     p.band = (p.tiles_n + (p.tiles_n + 11) / 12 - 1) / ((p.tiles_n + 11) / 12);

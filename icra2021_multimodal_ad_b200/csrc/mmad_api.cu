@@ -51,7 +51,7 @@ struct NapFit {
     float* bias = nullptr;      // [K] -(mu.v_j + mu2_j) var_j^-1/2
     float* bias_rot = nullptr;  // [K] -mu.v_j  (rotation alone, for the Standardizer refit pass)
     float wscale = 256.f;
-    bool upper_tri = false;     // rows are an upper-triangular whitening factor (mmad_nap_set_structure)
+    int tri_rows = 0;           // leading rows that form an upper-triangular whitening factor (mmad_nap_set_structure)
     __half* Bh = nullptr;
     __half* Bl = nullptr;
     TcOperand tcB, tcB2;
@@ -808,7 +808,7 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         if (rc) return rc;
         A.rows = rows; A.k = f.Dp;
         e.acc_scale = 1.f / ((f8 ? f.wscale8 : f.wscale) * diff_scale(h));
-        e.b_upper_tri = f.upper_tri ? 1 : 0;
+        e.b_upper_tri = f.tri_rows;
         // f16x3: full split by default.  MMAD_NAP_PASSES=2 keeps the diffs' hi+lo pair but takes the whitening rows as
         // fp16 (two MMAs per product, +17 % scoring throughput): fine for well-conditioned layer selections (score
         // error ~1e-4), NOT for the rank-deficient all-layers default, whose near-null directions it perturbs beyond
@@ -993,8 +993,10 @@ int mmad_nap_set_fit(mmad_t h, int lo, int hi, int K, const float* d_mu, const f
 int mmad_nap_set_structure(mmad_t h, int upper_triangular) {
     if (!h) { set_error("null handle"); return MMAD_E_ARG; }
     if (!h->nap.ready) { set_error("no NAP fit installed"); return MMAD_E_STATE; }
-    if (upper_triangular && h->nap.K > h->nap.D) { set_error("triangular factor needs K <= D'"); return MMAD_E_ARG; }
-    h->nap.upper_tri = upper_triangular != 0;
+    if (upper_triangular < 0 || upper_triangular > h->nap.K || upper_triangular > h->nap.D) {
+        set_error("triangular rows must be in [0, min(K, D')]"); return MMAD_E_ARG;
+    }
+    h->nap.tri_rows = upper_triangular;
     handle_graph_clear(h);
     return MMAD_OK;
 }

@@ -65,7 +65,7 @@ struct Epilogue {
     int sq_self = 0;
     float* pre = nullptr; int ldpre = 0;                // train: pre-activation (bias added, before act)
     int plain = 0;                                      // Y = acc * acc_scale + bias only, rows of Y may be unaligned
-    int b_upper_tri = 0;                                // B[n, k] == 0 for k < n (tensor-core kernel skips those k-blocks)
+    int b_upper_tri = 0;                                // number of leading rows n of B with B[n, k] == 0 for k < n (tensor-core kernels skip those k-blocks)
     int pre_zeroed = 0;                                 // split-K: the caller already zeroed Y (no memset inside gemm_tc)
     int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
     float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)

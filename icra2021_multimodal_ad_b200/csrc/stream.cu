@@ -67,8 +67,8 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1ULL);
+        // release-add (one way, no return value to wait for) orders this CTA's stores (bar.sync above) before the arrival
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ULL) : "memory");
         const long long t0 = clock64();
         while (ld_acquire(bar) < target) {
             if (clock64() - t0 > 2000000000LL) {
@@ -87,11 +87,21 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 template <int NB>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
-                    unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base) {
+                    unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base,
+                    unsigned long long* dbg) {
     extern __shared__ __align__(16) float st_smem[];
     __shared__ float s_red[ST_KQ][NB][ST_CPC];
     __shared__ float s_sq[NB][ST_CPC];
+    __shared__ float s_vec[3][ST_CPC];        // bias, BN scale, BN shift of this CTA's columns
     __shared__ int s_last;
+    auto stamp = [&](int i) {                 // MMAD_STREAM_DEBUG: CTA 0's wall clock at the phase boundaries
+        if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            dbg[i] = t;
+        }
+    };
+    stamp(0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, grid = gridDim.x;
     const int n_steps = P->n_steps;
@@ -111,6 +121,18 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         return (uint32_t)(st.cpc * st.K4);
     };
     uint32_t w4 = prefetch_weights(0);
+    // per-column epilogue vectors of the NEXT step: loaded into a register before the barrier wait (their L2 round trip hides
+    // behind it), parked in shared memory after it
+    auto prefetch_vec = [&](int s) -> float {
+        if (tid >= 3 * ST_CPC) return 0.f;
+        const StStep& st = P->step[s];
+        const int which = tid / ST_CPC, cl = tid % ST_CPC;
+        const int c = cta * st.cpc + cl;
+        if (cl >= st.cpc || c >= st.N) return 0.f;
+        const float* v = which == 0 ? st.bias : (which == 1 ? st.scale : st.shift);
+        return v ? __ldg(v + c) : 0.f;
+    };
+    float vpre = prefetch_vec(0);
 
     // ---- stage the input rows from the caller's mapped host buffer into device memory (once, by the whole grid) ----
     {
@@ -125,8 +147,10 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     }
     arrivals += grid;
     grid_barrier(bar, arrivals);
+    stamp(1);
 
     for (int s = 0; s < n_steps; ++s) {
+        if (tid < 3 * ST_CPC) s_vec[tid / ST_CPC][tid % ST_CPC] = vpre;      // visible after the __syncthreads below
         const StStep st = P->step[s];
         const int K4 = st.K4;
         const int c_lo = cta * st.cpc;
@@ -187,10 +211,10 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
                 if (b < nb && cl < ncols) {
                     const int c = c_lo + cl, r = r0 + b;
                     float v = ((s_red[0][b][cl] + s_red[1][b][cl]) + s_red[2][b][cl]) + s_red[3][b][cl];
-                    v += __ldg(st.bias + c);
+                    v += s_vec[0][cl];
                     if (st.scale) {
                         v = v > 0.f ? v : v * slope;
-                        v = fmaf(v, __ldg(st.scale + c), __ldg(st.shift + c));
+                        v = fmaf(v, s_vec[1][cl], s_vec[2][cl]);
                     }
                     if (st.out) st.out[(size_t)r * st.ldout + c] = v;
                     if (st.ref) {
@@ -211,8 +235,10 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         if (s + 1 < n_steps) {
             __syncthreads();            // everybody is done reading the current slice
             w4 = prefetch_weights(s + 1);
+            vpre = prefetch_vec(s + 1);
             arrivals += grid;
             grid_barrier(bar, arrivals);
+            stamp(2 + s);
         }
     }
 
@@ -251,6 +277,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(flag_host) = seq;
         __threadfence_system();
+        if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[1 + n_steps] = t; }
     }
 }
 
@@ -267,6 +294,7 @@ struct StreamState {
     float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
     float* h_out = nullptr; float* d_out = nullptr;     // pinned + mapped scores [2][64] + flag
     unsigned long long seq = 0, bar_base = 0;
+    unsigned long long* d_dbg = nullptr;  // MMAD_STREAM_DEBUG=1: per-phase globaltimer stamps of CTA 0
     unsigned long long weights_gen = 0;
     cudaStream_t stream = nullptr;
     int D = 0, n_steps = 0;
@@ -274,7 +302,7 @@ struct StreamState {
 
 void stream_free(StreamState* s) {
     if (!s) return;
-    cudaFree(s->d_plan); cudaFree(s->d_x); cudaFree(s->d_act); cudaFree(s->d_partial); cudaFree(s->d_bar);
+    cudaFree(s->d_plan); cudaFree(s->d_x); cudaFree(s->d_act); cudaFree(s->d_partial); cudaFree(s->d_bar); cudaFree(s->d_dbg);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -282,7 +310,8 @@ void stream_free(StreamState* s) {
 }
 
 template <int NB> int launch(StreamState* S, int rows) {
-    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, nullptr, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base};
+    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, nullptr, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base,
+                    (void*)&S->d_dbg};
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(S->d_out + 2 * ST_MAX_ROWS);
     args[4] = (void*)&flag;
     const int idx = NB == 1 ? 0 : (NB == 4 ? 1 : 2);
@@ -328,6 +357,11 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         memset(S->h_out, 0, (size_t)(2 * ST_MAX_ROWS + 4) * 4);
         MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_in, S->h_in, 0));
         MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_out, S->h_out, 0));
+        const char* dbg = getenv("MMAD_STREAM_DEBUG");
+        if (dbg && dbg[0] == '1') {
+            MMAD_CUDA_OK(cudaMalloc(&S->d_dbg, (ST_MAX_STEPS + 4) * 8));
+            MMAD_CUDA_OK(cudaMemset(S->d_dbg, 0, (ST_MAX_STEPS + 4) * 8));
+        }
     }
     S->ok = false;
     if (D % 4) { set_error("stream kernel needs D %% 4 == 0"); return MMAD_E_UNSUPPORTED; }
@@ -445,6 +479,16 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
         }
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    if (S->d_dbg) {      // per-phase times of this call (ns): staging, then every step incl. its barrier
+        unsigned long long t[ST_MAX_STEPS + 4];
+        const double host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        cudaStreamSynchronize(S->stream);
+        cudaMemcpy(t, S->d_dbg, (S->n_steps + 2) * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "mmad stream rows=%d launch->doorbell %.1f us | kernel %.1f us: staging %.1f |", rows, host_us,
+                (t[S->n_steps + 1] - t[0]) / 1e3, (t[1] - t[0]) / 1e3);
+        for (int i = 0; i < S->n_steps; ++i) fprintf(stderr, " %.1f", (t[2 + i] - t[1 + i]) / 1e3);
+        fprintf(stderr, "\n");
+    }
     if (h_base) memcpy(h_base, S->h_out, (size_t)rows * 4);
     if (h_sap) memcpy(h_sap, S->h_out + ST_MAX_ROWS, (size_t)rows * 4);
     return MMAD_OK;

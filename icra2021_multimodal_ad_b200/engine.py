@@ -261,7 +261,7 @@ class Engine:
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
                 batch_rows: int = 16384, distributed: Optional[bool] = None,
-                restandardize: bool = True, factor: str = "triangular", phases: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                restandardize: bool = True, factor: str = "hybrid", phases: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
@@ -314,7 +314,7 @@ class Engine:
         del gram
         mark("eig_factor_s")
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
-        check(lib().mmad_nap_set_structure(self._h, 1 if fit["factor"] == "triangular" else 0))
+        check(lib().mmad_nap_set_structure(self._h, int(fit["tri_rows"])))
         mark("pack_s")
         if restandardize:
             # Standardizer.fit on Rotater.run(train) (utils/metric.py:214-216): third pass, the rotation done
@@ -343,7 +343,7 @@ class Engine:
         f = getattr(self, "nap_fit_state", None)
         if f is None or self.nap_range is None:
             raise _lib.MmadError("no NAP fit installed")
-        return {"format": "mmad-nap-fit-1", "lo": f["lo"], "hi": f["hi"], "n": f["n"], "factor": f["factor"],
+        return {"format": "mmad-nap-fit-1", "lo": f["lo"], "hi": f["hi"], "n": f["n"], "factor": f["factor"], "tri_rows": int(f["tri_rows"]),
                 "precision": f["precision"], "enc_widths": list(self.enc_widths),
                 "mu": f["mu"].cpu(), "vt": f["vt"].cpu(), "var": f["var"].cpu(), "mu2": f["mu2"].cpu()}
 
@@ -356,11 +356,11 @@ class Engine:
             raise ValueError(f"NAP fit was made in {st['precision']} arithmetic, the engine runs {self.precision}: refit "
                              "(the variances of near-null directions carry the mode's rounding noise)")
         self.nap_set_fit(st["lo"], st["hi"], st["mu"], st["vt"], st["var"], st["mu2"])
-        check(lib().mmad_nap_set_structure(self._h, 1 if st["factor"] == "triangular" else 0))
-        self.nap_fit_state = {k: st[k] for k in ("mu", "vt", "var", "mu2", "n", "factor", "lo", "hi", "precision")}
+        check(lib().mmad_nap_set_structure(self._h, int(st["tri_rows"])))
+        self.nap_fit_state = {k: st[k] for k in ("mu", "vt", "var", "mu2", "n", "factor", "tri_rows", "lo", "hi", "precision")}
 
 
-def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "eigen") -> Dict[str, torch.Tensor]:
+def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "hybrid", tau: float = 1e-3) -> Dict[str, torch.Tensor]:
     """Eigendecomposition of the centred Gram matrix (fp64, cuSOLVER syevd through
     torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2).
 
@@ -369,7 +369,14 @@ def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, facto
     factor="triangular": the same score sum_j ((d-mu).v_j)^2 / var_j = |R (d-mu)|^2 through the upper
     triangular factor R of the whitening matrix diag(var^-1/2) V^T = Q R (fp64 Householder QR): half of R is
     zero, so the scoring GEMM does half the products.  Rows are normalised to unit max (the scale goes into
-    ``var``) so they split cleanly into fp16 pairs."""
+    ``var``) so they split cleanly into fp16 pairs.
+    factor="hybrid" (default): triangular factor of the WELL-CONDITIONED part of the spectrum (singular values
+    >= tau * the largest) followed by the plain eigenvector rows of the weak directions.  Every row of a triangular
+    factor carries the gain of the weakest direction it spans, so on a rank-deficient selection (all layers, SURVEY
+    F5: ~770 of 5482 directions at the fp32 noise floor) rounding noise of size eps * |d| / sigma_min lands in EVERY
+    output; the eigenvector form confines it to the weak outputs.  Measured at D = 1728, all layers (rank agreement
+    with the fp64 value): eigen 0.97, triangular 0.86, reference 0.97.  Well-conditioned selections have no weak
+    part and keep the full triangular factor (half the MMA work)."""
     lam, V = torch.linalg.eigh(gram)            # ascending
     # near-null directions (SURVEY F5) can come out slightly negative; floor at fp64 resolution of the
     # largest eigenvalue so that var stays positive like the reference's np.cov diagonal
@@ -377,16 +384,22 @@ def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, facto
     V = V.flip(1)
     K = min(n_total, gram.shape[0])
     var64 = lam[:K] / (n_total - 1)
-    if factor == "triangular":
-        W = V[:, :K].t() / var64.sqrt().unsqueeze(1)                     # K x D' whitening matrix
-        R = torch.linalg.qr(W, mode="r").R                                 # K x D', upper triangular / trapezoidal
+    tri_rows = 0
+    if factor in ("triangular", "hybrid"):
+        ks = K if factor == "triangular" else int((lam[:K] >= (tau * tau) * lam[0]).sum().item())
+        W = V[:, :ks].t() / var64[:ks].sqrt().unsqueeze(1)                 # ks x D' whitening matrix of the strong part
+        R = torch.linalg.qr(W, mode="r").R                                 # ks x D', upper triangular / trapezoidal
         scale = R.abs().amax(dim=1).clamp_min(1e-300)
-        vt = torch.triu(R / scale.unsqueeze(1)).contiguous().float()
-        var = (1.0 / (scale * scale)).float()
+        vt = torch.triu(R / scale.unsqueeze(1))
+        var = 1.0 / (scale * scale)
+        if ks < K:                                                         # weak directions: plain eigenvector rows
+            vt = torch.cat([vt, V[:, ks:K].t()], dim=0)
+            var = torch.cat([var, var64[ks:K]])
+        vt, var, tri_rows = vt.contiguous().float(), var.float(), ks
     elif factor == "eigen":
         vt = V[:, :K].t().contiguous().float()
         var = var64.float()
     else:
-        raise ValueError("factor must be 'eigen' or 'triangular'")
+        raise ValueError("factor must be 'eigen', 'triangular' or 'hybrid'")
     return {"mu": mu.float(), "vt": vt, "var": var, "mu2": torch.zeros(K, dtype=torch.float32, device=mu.device),
-            "n": n_total, "factor": factor}
+            "n": n_total, "factor": factor, "tri_rows": tri_rows}

@@ -186,10 +186,12 @@ int mmad_nap_set_fit(mmad_t h, int layer_lo, int layer_hi, int K, const float* d
 int mmad_nap_rotate_stats(mmad_t h, const float* d_x, int ldx, int n, int layer_lo, int layer_hi,
                           double* d_rsum, double* d_rsq, void* d_ws, size_t ws_bytes, void* stream);
 int mmad_nap_set_standardizer(mmad_t h, const float* d_var, const float* d_mu2, void* stream);
-/* Declare that the installed d_vt is upper triangular in the concatenated-diff coordinates
- * (vt[j, c] == 0 for c < j): a whitening factor R with R^T R = V diag(1/var) V^T gives the same score
- * sum_j ((d-mu).v_j)^2 / var_j = |R (d-mu)|^2 (utils/metric.py:220-222) with half the products; the
- * tensor-core kernel then skips the zero k-blocks.  The caller guarantees the structure. */
+/* Declare that the first `upper_triangular` rows of the installed d_vt are upper triangular in the concatenated-diff
+ * coordinates (vt[j, c] == 0 for c < j; 0 = dense, K = all rows): a whitening factor R with R^T R = V diag(1/var) V^T
+ * gives the same score sum_j ((d-mu).v_j)^2 / var_j = |R (d-mu)|^2 (utils/metric.py:220-222) with half the products;
+ * the tensor-core kernels then skip the zero k-blocks of those rows.  A fit may mix both: a triangular factor of the
+ * well-conditioned part of the spectrum followed by plain eigenvector rows for the weak directions (Engine.nap_fit,
+ * factor="hybrid").  The caller guarantees the structure. */
 int mmad_nap_set_structure(mmad_t h, int upper_triangular);
 
 /* ---- stand-alone normaliser ops (utils/normalize.py API compatibility: Rotater / Standardizer on
