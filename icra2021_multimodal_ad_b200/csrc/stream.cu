@@ -35,9 +35,10 @@ constexpr int ST_SMEM_CAP = 227 * 1024 - 1024;
 
 struct StStep {
     const float* W; const float* bias; const float* scale; const float* shift;   // scale == nullptr: bare Linear
-    const float* in; float* out; const float* ref;
-    int K4;            // padded contraction length / 4 (== row stride of W and of `in` in float4)
-    int N, ldout, ldref;
+    const uint2* in; uint2* out; const uint2* ref;     // (value, sequence) pairs, row stride ld* pairs
+    int K;             // contraction length (valid input columns)
+    int K4;            // padded contraction length / 4 (row stride of W in float4, of the shared activation tile)
+    int N, ldin, ldout, ldref;
     int cpc;           // columns per CTA = ceil(N / grid)
     int diff;          // partial-sum slot of the diff this step produces, -1: none
 };
@@ -45,7 +46,7 @@ struct StStep {
 struct StPlan {
     int n_steps, n_diffs, lo, hi, D, ldx, grid;
     float inv_base, inv_sap, slope;
-    float* x_dev;      // [ST_MAX_ROWS, ldx] staged input, zero padded
+    uint2* x_dev;      // [ST_MAX_ROWS, ldx] staged input as (value, sequence) pairs
     float* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2
     int nact[MMAD_MAX_LAYERS + 2];   // CTAs that own columns of diff l
     StStep step[ST_MAX_STEPS];
@@ -56,34 +57,25 @@ __device__ __forceinline__ void st_cp16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void st_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void st_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+// 8-byte (value, sequence) pair: single-copy atomic, so a reader that sees the call's sequence number sees the value
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-
-// Device-wide barrier of a cooperatively launched grid: monotonically increasing arrival counter (never reset; `target`
-// carries the call's base).  The poll is bounded: a protocol bug traps instead of hanging the device.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // release-add (one way, no return value to wait for) orders this CTA's stores (bar.sync above) before the arrival
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ULL) : "memory");
-        const long long t0 = clock64();
-        while (ld_acquire(bar) < target) {
-            if (clock64() - t0 > 2000000000LL) {
-                printf("mmad stream kernel: grid barrier timed out (block %d, target %llu)\n", blockIdx.x, target);
-                __trap();
-            }
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ void st_pair(uint2* p, float value, uint32_t seq) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(seq) : "memory");
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+// Layers are chained WITHOUT grid barriers: every activation travels as an 8-byte (value, call sequence number) pair -- the
+// low-latency protocol of collective libraries.  A consumer polls the pairs it needs until they carry this call's number:
+// per layer one store becomes visible and one load returns (~1.5 us), where an arrive-and-poll barrier costs a fence, an
+// atomic and at least one more round trip before the activations can even be requested (3.0-5.1 us measured per layer).
+// All polls are bounded: a protocol bug traps instead of hanging the device.
 template <int NB>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
@@ -93,6 +85,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     __shared__ float s_red[ST_KQ][NB][ST_CPC];
     __shared__ float s_sq[NB][ST_CPC];
     __shared__ float s_vec[3][ST_CPC];        // bias, BN scale, BN shift of this CTA's columns
+    __shared__ float s_fin[MMAD_MAX_LAYERS + 2][ST_MAX_ROWS];
     __shared__ int s_last;
     auto stamp = [&](int i) {                 // MMAD_STREAM_DEBUG: CTA 0's wall clock at the phase boundaries
         if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -106,10 +99,9 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     const int cta = blockIdx.x, grid = gridDim.x;
     const int n_steps = P->n_steps;
     const float slope = P->slope;
-    unsigned long long arrivals = bar_base;
+    const uint32_t seq32 = (uint32_t)seq;
 
-    // ---- weight slice of step 0 (independent of the input) ----
-    auto prefetch_weights = [&](int s) -> uint32_t {    // returns the float4 count of the slice
+    auto prefetch_weights = [&](int s) -> uint32_t {    // cp.async of this CTA's weight slice; returns its float4 extent
         const StStep& st = P->step[s];
         const int c_lo = cta * st.cpc;
         int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
@@ -120,10 +112,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         st_cp_commit();
         return (uint32_t)(st.cpc * st.K4);
     };
-    uint32_t w4 = prefetch_weights(0);
-    // per-column epilogue vectors of the NEXT step: loaded into a register before the barrier wait (their L2 round trip hides
-    // behind it), parked in shared memory after it
-    auto prefetch_vec = [&](int s) -> float {
+    auto prefetch_vec = [&](int s) -> float {           // bias / BN scale / BN shift of this CTA's columns, one per thread
         if (tid >= 3 * ST_CPC) return 0.f;
         const StStep& st = P->step[s];
         const int which = tid / ST_CPC, cl = tid % ST_CPC;
@@ -132,46 +121,71 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         const float* v = which == 0 ? st.bias : (which == 1 ? st.scale : st.shift);
         return v ? __ldg(v + c) : 0.f;
     };
+    uint32_t w4 = prefetch_weights(0);
     float vpre = prefetch_vec(0);
 
-    // ---- stage the input rows from the caller's mapped host buffer into device memory (once, by the whole grid) ----
+    // ---- stage the input rows from the caller's mapped host buffer as pairs (once, by the whole grid) ----
     {
-        const int D4 = P->D >> 2, ld4 = P->ldx >> 2;         // D % 4 == 0 is checked at open
-        const int total = rows * D4;
-        float4* xd = reinterpret_cast<float4*>(P->x_dev);
-        const float4* xs = reinterpret_cast<const float4*>(x_src);
+        const int D = P->D, ldx = P->ldx;
+        const int total = rows * D;
         for (int i = cta * ST_THREADS + tid; i < total; i += grid * ST_THREADS) {
-            const int r = i / D4, c = i - r * D4;
-            xd[(size_t)r * ld4 + c] = xs[i];
+            const int r = i / D, c = i - r * D;
+            st_pair(P->x_dev + (size_t)r * ldx + c, __ldcv(x_src + i), seq32);     // host memory rewritten between calls: uncached load
         }
     }
-    arrivals += grid;
-    grid_barrier(bar, arrivals);
     stamp(1);
 
     for (int s = 0; s < n_steps; ++s) {
-        if (tid < 3 * ST_CPC) s_vec[tid / ST_CPC][tid % ST_CPC] = vpre;      // visible after the __syncthreads below
         const StStep st = P->step[s];
-        const int K4 = st.K4;
+        const int K4 = st.K4, Kp = 4 * st.K4;
         const int c_lo = cta * st.cpc;
         int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
+        if (tid < 3 * ST_CPC) s_vec[tid / ST_CPC][tid % ST_CPC] = vpre;      // visible after the __syncthreads below
         const float4* wsm = reinterpret_cast<const float4*>(st_smem);
-        float4* asm4 = reinterpret_cast<float4*>(st_smem) + w4;
+        float* asm_f = st_smem + 4 * (size_t)w4;
+        const float4* asm4 = reinterpret_cast<const float4*>(asm_f);
         const int cg = warp & (ST_CG - 1), kq = warp >> 2;
         const int cl0 = cg * ST_CW;
         int nj = ncols - cl0; if (nj > ST_CW) nj = ST_CW;
         const int q = K4 / ST_KQ;                                  // K4 is a multiple of 16
         const int k_lo = kq * q, k_hi = k_lo + q;
-        for (int r0 = 0; r0 < rows; r0 += NB) {
+        for (int r0 = 0; r0 < rows && ncols > 0; r0 += NB) {
             int nb = rows - r0; if (nb > NB) nb = NB;
-            if (ncols > 0) {
-                // activations of rows r0 .. r0 + nb (contiguous: row stride == padded K)
-                const float4* src = reinterpret_cast<const float4*>(st.in) + (size_t)r0 * K4;
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(asm4);
-                for (int i = tid; i < nb * K4; i += ST_THREADS) st_cp16(dst + i * 16, src + i);
+            // ---- activations of rows r0 .. r0 + nb: poll the pairs, park the values in shared memory ----
+            for (int i = tid; i < nb * (Kp - st.K); i += ST_THREADS) {            // zero padding of the contraction dim
+                const int r = i / (Kp - st.K), k = st.K + i % (Kp - st.K);
+                asm_f[r * Kp + k] = 0.f;
             }
-            st_cp_commit();
-            st_cp_wait_all();
+            const int total = nb * st.K;
+            const long long t0 = clock64();
+            for (int base = 0; base < total; base += ST_THREADS * 8) {
+                unsigned pending = 0;
+                const uint2* src[8];
+                int dsti[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = base + j * ST_THREADS + tid;
+                    if (i < total) {
+                        const int r = i / st.K, k = i - r * st.K;
+                        src[j] = st.in + (size_t)(r0 + r) * st.ldin + k;
+                        dsti[j] = r * Kp + k;
+                        pending |= 1u << j;
+                    }
+                }
+                while (pending) {
+                    uint2 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (pending & (1u << j)) v[j] = ld_pair(src[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((pending & (1u << j)) && v[j].y == seq32) { asm_f[dsti[j]] = __uint_as_float(v[j].x); pending &= ~(1u << j); }
+                    if (pending && clock64() - t0 > 2000000000LL) {
+                        printf("mmad stream kernel: activations of step %d never arrived (block %d thread %d)\n", s, cta, tid);
+                        __trap();
+                    }
+                }
+            }
+            st_cp_wait_all();                 // this CTA's weight slice (issued one step earlier)
             __syncthreads();
             if (nj > 0) {
                 float acc[NB][ST_CW];
@@ -216,30 +230,28 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
                         v = v > 0.f ? v : v * slope;
                         v = fmaf(v, s_vec[1][cl], s_vec[2][cl]);
                     }
-                    if (st.out) st.out[(size_t)r * st.ldout + c] = v;
+                    if (st.out) st_pair(st.out + (size_t)r * st.ldout + c, v, seq32);
                     if (st.ref) {
-                        const float d = v - __ldcg(st.ref + (size_t)r * st.ldref + c);
+                        // complete by now: a consumer of step s has seen every output of step s-1, recursively
+                        const float d = v - __uint_as_float(ld_pair(st.ref + (size_t)r * st.ldref + c).x);
                         sq = d * d;
                     }
                 }
                 if (st.diff >= 0) s_sq[b][cl] = sq;
             }
             __syncthreads();
-            if (st.diff >= 0 && tid < nb && ncols > 0) {
+            if (st.diff >= 0 && tid < nb) {
                 float t = 0.f;
                 for (int cl = 0; cl < ncols; ++cl) t += s_sq[tid][cl];
                 P->partial[((size_t)st.diff * grid + cta) * ST_MAX_ROWS + r0 + tid] = t;
             }
         }
-        // the next step's weight slice travels while this CTA waits for the others
         if (s + 1 < n_steps) {
-            __syncthreads();            // everybody is done reading the current slice
+            __syncthreads();            // everybody is done reading the current slice and activation tile
             w4 = prefetch_weights(s + 1);
             vpre = prefetch_vec(s + 1);
-            arrivals += grid;
-            grid_barrier(bar, arrivals);
-            stamp(2 + s);
         }
+        stamp(2 + s);
     }
 
     // ---- the last CTA to finish adds the per-CTA partial sums (fixed order) and rings the doorbell ----
@@ -247,30 +259,36 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     if (tid == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(bar, 1ULL);
-        s_last = (old + 1 == arrivals + grid) ? 1 : 0;
+        s_last = (old + 1 == bar_base + grid) ? 1 : 0;
         if (s_last) __threadfence();
     }
     __syncthreads();
     if (!s_last) return;
     const int nd = P->n_diffs;
-    for (int r = warp; r < rows; r += ST_THREADS / 32) {
-        float base = 0.f, sap = 0.f;
-        for (int l = 0; l < nd; ++l) {
-            const int na = P->nact[l];
-            float t = 0.f;
-            for (int c = lane; c < na; c += 32) t += __ldcg(P->partial + ((size_t)l * grid + c) * ST_MAX_ROWS + r);
-            t += __shfl_xor_sync(0xffffffffu, t, 16);
-            t += __shfl_xor_sync(0xffffffffu, t, 8);
-            t += __shfl_xor_sync(0xffffffffu, t, 4);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            if (l == 0) base = t;
-            if (l >= P->lo && l < P->hi) sap += t;
+    for (int l = warp; l < nd; l += ST_THREADS / 32) {          // warp l: diff l, lanes split the CTAs (<= 8 loads in flight each)
+        const int na = P->nact[l];
+        for (int r = 0; r < rows; ++r) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                t[j] = c < na ? __ldcg(P->partial + ((size_t)l * grid + c) * ST_MAX_ROWS + r) : 0.f;
+            }
+            float v = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (lane == 0) s_fin[l][r] = v;
         }
-        if (lane == 0) {
-            out_host[r] = base * P->inv_base;
-            out_host[ST_MAX_ROWS + r] = sap * P->inv_sap;
-        }
+    }
+    __syncthreads();
+    if (tid < rows) {
+        float sap = 0.f;
+        for (int l = P->lo; l < P->hi; ++l) sap += s_fin[l][tid];
+        out_host[tid] = s_fin[0][tid] * P->inv_base;
+        out_host[ST_MAX_ROWS + tid] = sap * P->inv_sap;
     }
     __syncthreads();
     if (tid == 0) {
@@ -287,8 +305,8 @@ struct StreamState {
     size_t smem[3] = {0, 0, 0};          // dynamic shared memory of the NB = 1 / 4 / 16 instantiations
     bool fits[3] = {false, false, false};
     StPlan* d_plan = nullptr;
-    float* d_x = nullptr;                // staged input
-    float* d_act = nullptr;              // activation buffers (stash, decoder ping-pong, enc(xhat) ping-pong)
+    uint2* d_x = nullptr;                // staged input, (value, sequence) pairs
+    uint2* d_act = nullptr;              // one pair buffer per step output (nothing is reused inside a call)
     float* d_partial = nullptr;
     unsigned long long* d_bar = nullptr;
     float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
@@ -365,24 +383,25 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     }
     S->ok = false;
     if (D % 4) { set_error("stream kernel needs D %% 4 == 0"); return MMAD_E_UNSUPPORTED; }
-    // activation buffers: stash H_1..H_L, decoder ping-pong (2), xhat, enc(xhat) ping-pong (2)
+    // pair buffers: one per step output (L encoder + Ld decoder + L - 1 enc(xhat)), nothing is reused inside a call, so a
+    // pair that carries the call's sequence number is final
     std::vector<LayerF32> enc(L), dec(Ld);
     int maxw = round_up(D, kPad);
     for (int i = 0; i < L; ++i) { enc[i] = handle_layer_f32(h, 0, i); maxw = std::max(maxw, enc[i].Np); }
     for (int i = 0; i < Ld; ++i) { dec[i] = handle_layer_f32(h, 1, i); maxw = std::max(maxw, dec[i].Np); }
     for (auto& l : enc) if (l.N > S->grid * ST_CPC) { set_error("layer too wide for the stream kernel"); return MMAD_E_UNSUPPORTED; }
     for (auto& l : dec) if (l.N > S->grid * ST_CPC) { set_error("layer too wide for the stream kernel"); return MMAD_E_UNSUPPORTED; }
-    const size_t buf = (size_t)ST_MAX_ROWS * maxw;
-    const int n_buf = L + 5;
+    const size_t buf = (size_t)ST_MAX_ROWS * maxw;       // pairs per buffer
+    const int n_buf = 2 * L + Ld;
     if (!S->d_act) {
-        MMAD_CUDA_OK(cudaMalloc(&S->d_act, buf * n_buf * 4));
-        MMAD_CUDA_OK(cudaMalloc(&S->d_x, buf * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_act, buf * n_buf * 8));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_x, buf * 8));
         MMAD_CUDA_OK(cudaMalloc(&S->d_partial, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
+        MMAD_CUDA_OK(cudaMemset(S->d_act, 0, buf * n_buf * 8));       // sequence 0 is never used by a call
+        MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 8));
     }
-    MMAD_CUDA_OK(cudaMemset(S->d_act, 0, buf * n_buf * 4));       // padding columns stay zero for ever
-    MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 4));
     MMAD_CUDA_OK(cudaMemset(S->d_partial, 0, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
-    auto B = [&](int i) { return S->d_act + buf * i; };           // 0..L-1 stash, L/L+1 decoder, L+2 xhat, L+3/L+4 enc(xhat)
+    auto B = [&](int i) { return S->d_act + buf * i; };           // 0..L-1 enc(x) (the diff references), L..L+Ld-1 decoder, then enc(xhat)
     StPlan P;
     memset(&P, 0, sizeof P);
     P.lo = lo; P.hi = hi; P.D = D; P.ldx = round_up(D, kPad); P.grid = S->grid;
@@ -395,31 +414,31 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     P.inv_sap = 1.f / dsel;
     int ns = 0;
     size_t need[3] = {0, 0, 0};
-    auto add = [&](const LayerF32& Lr, const float* in, float* out, int ldout, const float* ref, int ldref, int diff) {
+    auto add = [&](const LayerF32& Lr, const uint2* in, int ldin, uint2* out, int ldout, const uint2* ref, int ldref, int diff) {
         StStep& st = P.step[ns++];
         st.W = Lr.W; st.bias = Lr.bias; st.scale = Lr.has_bn ? Lr.scale : nullptr; st.shift = Lr.has_bn ? Lr.shift : nullptr;
         st.in = in; st.out = out; st.ref = ref;
-        st.K4 = Lr.Kp / 4; st.N = Lr.N; st.ldout = ldout; st.ldref = ldref;
+        st.K = Lr.K; st.K4 = Lr.Kp / 4; st.N = Lr.N; st.ldin = ldin; st.ldout = ldout; st.ldref = ldref;
         st.cpc = (Lr.N + S->grid - 1) / S->grid;
         st.diff = diff;
         if (diff >= 0) P.nact[diff] = (Lr.N + st.cpc - 1) / st.cpc;
         const int nbs[3] = {1, 4, 16};
         for (int i = 0; i < 3; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + nbs[i]) * Lr.Kp * 4);
     };
-    const float* cur = S->d_x;
-    for (int l = 0; l < L; ++l) { add(enc[l], cur, B(l), enc[l].Np, nullptr, 0, -1); cur = B(l); }
+    const uint2* cur = S->d_x;
+    int ldcur = P.ldx;
+    for (int l = 0; l < L; ++l) { add(enc[l], cur, ldcur, B(l), maxw, nullptr, 0, -1); cur = B(l); ldcur = maxw; }
     const int want_enc2 = hi > 1;
     for (int l = 0; l < Ld; ++l) {
         const bool last = l == Ld - 1;
-        float* out = last ? B(L + 2) : B(L + (l & 1));
-        add(dec[l], cur, out, dec[l].Np, last ? S->d_x : nullptr, P.ldx, last ? 0 : -1);
-        cur = out;
+        add(dec[l], cur, ldcur, B(L + l), maxw, last ? S->d_x : nullptr, P.ldx, last ? 0 : -1);
+        cur = B(L + l); ldcur = maxw;
     }
     if (want_enc2) {
         const int last = std::min(L, hi - 1);
         for (int l = 1; l <= last; ++l) {
-            float* out = l == last ? nullptr : B(L + 3 + (l & 1));
-            add(enc[l - 1], cur, out, enc[l - 1].Np, B(l - 1), enc[l - 1].Np, l);
+            uint2* out = l == last ? nullptr : B(L + Ld + l - 1);
+            add(enc[l - 1], cur, ldcur, out, maxw, B(l - 1), maxw, l);
             cur = out;
         }
     }
@@ -461,7 +480,7 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
     if (idx == 0) rc = launch<1>(S, rows); else if (idx == 1) rc = launch<4>(S, rows); else rc = launch<16>(S, rows);
     if (rc) return rc;
     MMAD_LAUNCHED();
-    S->bar_base += (unsigned long long)S->grid * (unsigned long long)(S->n_steps + 1);
+    S->bar_base += (unsigned long long)S->grid;          // one arrival per CTA and call (the last one finalises)
     // the doorbell: the kernel's last store is the sequence number, written after the scores (system-scope fences)
     volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(S->h_out + 2 * ST_MAX_ROWS);
     const auto t0 = std::chrono::steady_clock::now();
