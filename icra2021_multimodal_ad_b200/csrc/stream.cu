@@ -35,10 +35,11 @@ constexpr int ST_SMEM_CAP = 227 * 1024 - 1024;
 
 struct StStep {
     const float* W; const float* bias; const float* scale; const float* shift;   // scale == nullptr: bare Linear
-    const uint2* in; uint2* out; const uint2* ref;     // (value, sequence) pairs, row stride ld* pairs
+    int ibuf, obuf, rbuf;   // input / output / diff-reference buffer: -2 none, -1 the staged input x, >= 0 activation buffer
+    int nprod;         // CTAs that produce the input buffer (flag protocol)
     int K;             // contraction length (valid input columns)
     int K4;            // padded contraction length / 4 (row stride of W in float4, of the shared activation tile)
-    int N, ldin, ldout, ldref;
+    int N;
     int cpc;           // columns per CTA = ceil(N / grid)
     int diff;          // partial-sum slot of the diff this step produces, -1: none
 };
@@ -46,7 +47,13 @@ struct StStep {
 struct StPlan {
     int n_steps, n_diffs, lo, hi, D, ldx, grid;
     float inv_base, inv_sap, slope;
-    uint2* x_dev;      // [ST_MAX_ROWS, ldx] staged input as (value, sequence) pairs
+    // every step output exists twice: as (value, sequence) pairs for calls of <= 4 rows and as plain floats + one flag per
+    // producer CTA for taller calls; buffer i starts at base + i * bufsz elements, rows are ld (x: ldx) elements apart
+    uint2* xp; uint2* pbase;
+    float* xf; float* fbase;
+    uint32_t* flags;   // [n_steps + 1][grid]: flags[0] = x staged, flags[s + 1] = outputs of step s
+    size_t bufsz;
+    int ld;
     float* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2
     int nact[MMAD_MAX_LAYERS + 2];   // CTAs that own columns of diff l
     StStep step[ST_MAX_STEPS];
@@ -67,6 +74,16 @@ __device__ __forceinline__ void st_pair(uint2* p, float value, uint32_t seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(seq) : "memory");
 }
 
+// flag protocol (taller calls): plain float activations, one release-store flag per producer CTA and step
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
@@ -76,7 +93,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 // per layer one store becomes visible and one load returns (~1.5 us), where an arrive-and-poll barrier costs a fence, an
 // atomic and at least one more round trip before the activations can even be requested (3.0-5.1 us measured per layer).
 // All polls are bounded: a protocol bug traps instead of hanging the device.
-template <int NB>
+template <int NB, bool LL>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
                     unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base,
@@ -124,13 +141,26 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     uint32_t w4 = prefetch_weights(0);
     float vpre = prefetch_vec(0);
 
-    // ---- stage the input rows from the caller's mapped host buffer as pairs (once, by the whole grid) ----
-    {
+    // ---- stage the input rows from the caller's mapped host buffer (once, by the whole grid) ----
+    if constexpr (LL) {
         const int D = P->D, ldx = P->ldx;
         const int total = rows * D;
         for (int i = cta * ST_THREADS + tid; i < total; i += grid * ST_THREADS) {
             const int r = i / D, c = i - r * D;
-            st_pair(P->x_dev + (size_t)r * ldx + c, __ldcv(x_src + i), seq32);     // host memory rewritten between calls: uncached load
+            st_pair(P->xp + (size_t)r * ldx + c, __ldcv(x_src + i), seq32);     // host memory rewritten between calls: uncached load
+        }
+    } else {
+        const int D4 = P->D >> 2, ld4 = P->ldx >> 2;
+        const int total = rows * D4;
+        float4* xd = reinterpret_cast<float4*>(P->xf);
+        const float4* xs = reinterpret_cast<const float4*>(x_src);
+        for (int i = cta * ST_THREADS + tid; i < total; i += grid * ST_THREADS) {
+            const int r = i / D4, c = i - r * D4;
+            xd[(size_t)r * ld4 + c] = __ldcv(xs + i);
+        }
+        if (cta * ST_THREADS < total) {
+            __syncthreads();
+            if (tid == 0) { __threadfence(); st_flag(P->flags + cta, seq32); }
         }
     }
     stamp(1);
@@ -151,39 +181,68 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         const int k_lo = kq * q, k_hi = k_lo + q;
         for (int r0 = 0; r0 < rows && ncols > 0; r0 += NB) {
             int nb = rows - r0; if (nb > NB) nb = NB;
-            // ---- activations of rows r0 .. r0 + nb: poll the pairs, park the values in shared memory ----
-            for (int i = tid; i < nb * (Kp - st.K); i += ST_THREADS) {            // zero padding of the contraction dim
-                const int r = i / (Kp - st.K), k = st.K + i % (Kp - st.K);
-                asm_f[r * Kp + k] = 0.f;
-            }
-            const int total = nb * st.K;
+            // ---- activations of rows r0 .. r0 + nb into shared memory ----
             const long long t0 = clock64();
-            for (int base = 0; base < total; base += ST_THREADS * 8) {
-                unsigned pending = 0;
-                const uint2* src[8];
-                int dsti[8];
+            if constexpr (LL) {
+                // poll the (value, sequence) pairs; park the values
+                const uint2* in = st.ibuf < 0 ? P->xp : P->pbase + (size_t)st.ibuf * P->bufsz;
+                const int ldin = st.ibuf < 0 ? P->ldx : P->ld;
+                for (int i = tid; i < nb * (Kp - st.K); i += ST_THREADS) {            // zero padding of the contraction dim
+                    const int r = i / (Kp - st.K), k = st.K + i % (Kp - st.K);
+                    asm_f[r * Kp + k] = 0.f;
+                }
+                const int total = nb * st.K;
+                for (int base = 0; base < total; base += ST_THREADS * 8) {
+                    unsigned pending = 0;
+                    const uint2* src[8];
+                    int dsti[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = base + j * ST_THREADS + tid;
-                    if (i < total) {
-                        const int r = i / st.K, k = i - r * st.K;
-                        src[j] = st.in + (size_t)(r0 + r) * st.ldin + k;
-                        dsti[j] = r * Kp + k;
-                        pending |= 1u << j;
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = base + j * ST_THREADS + tid;
+                        if (i < total) {
+                            const int r = i / st.K, k = i - r * st.K;
+                            src[j] = in + (size_t)(r0 + r) * ldin + k;
+                            dsti[j] = r * Kp + k;
+                            pending |= 1u << j;
+                        }
+                    }
+                    while (pending) {
+                        uint2 v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (pending & (1u << j)) v[j] = ld_pair(src[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if ((pending & (1u << j)) && v[j].y == seq32) { asm_f[dsti[j]] = __uint_as_float(v[j].x); pending &= ~(1u << j); }
+                        if (pending && clock64() - t0 > 2000000000LL) {
+                            printf("mmad stream kernel: activations of step %d never arrived (block %d thread %d)\n", s, cta, tid);
+                            __trap();
+                        }
                     }
                 }
-                while (pending) {
-                    uint2 v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (pending & (1u << j)) v[j] = ld_pair(src[j]);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if ((pending & (1u << j)) && v[j].y == seq32) { asm_f[dsti[j]] = __uint_as_float(v[j].x); pending &= ~(1u << j); }
-                    if (pending && clock64() - t0 > 2000000000LL) {
-                        printf("mmad stream kernel: activations of step %d never arrived (block %d thread %d)\n", s, cta, tid);
-                        __trap();
+            } else {
+                // wait for the flags of the CTAs that produce the input (first row chunk only), then bulk-copy the rows
+                if (r0 == 0) {
+                    const int nprod = s == 0 ? min(grid, (rows * (P->D >> 2) + ST_THREADS - 1) / ST_THREADS) : st.nprod;
+                    if (tid < nprod) {
+                        const uint32_t* f = P->flags + (size_t)s * grid + tid;
+                        while (ld_flag(f) != seq32) {
+                            if (clock64() - t0 > 2000000000LL) {
+                                printf("mmad stream kernel: producer %d of step %d never signalled (block %d)\n", tid, s, cta);
+                                __trap();
+                            }
+                        }
                     }
+                    __syncthreads();
                 }
+                const float* in = st.ibuf < 0 ? P->xf : P->fbase + (size_t)st.ibuf * P->bufsz;
+                const int ld4 = (st.ibuf < 0 ? P->ldx : P->ld) >> 2;
+                const float4* src = reinterpret_cast<const float4*>(in) + (size_t)r0 * ld4;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(asm_f);
+                for (int i = tid; i < nb * K4; i += ST_THREADS) {
+                    const int r = i / K4, k4 = i - r * K4;
+                    st_cp16(dst + i * 16, src + (size_t)r * ld4 + k4);
+                }
+                st_cp_commit();
             }
             st_cp_wait_all();                 // this CTA's weight slice (issued one step earlier)
             __syncthreads();
@@ -230,10 +289,17 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
                         v = v > 0.f ? v : v * slope;
                         v = fmaf(v, s_vec[1][cl], s_vec[2][cl]);
                     }
-                    if (st.out) st_pair(st.out + (size_t)r * st.ldout + c, v, seq32);
-                    if (st.ref) {
-                        // complete by now: a consumer of step s has seen every output of step s-1, recursively
-                        const float d = v - __uint_as_float(ld_pair(st.ref + (size_t)r * st.ldref + c).x);
+                    if (st.obuf >= 0) {
+                        if constexpr (LL) st_pair(P->pbase + (size_t)st.obuf * P->bufsz + (size_t)r * P->ld + c, v, seq32);
+                        else P->fbase[(size_t)st.obuf * P->bufsz + (size_t)r * P->ld + c] = v;
+                    }
+                    if (st.rbuf > -2) {
+                        // the reference is complete by now: a consumer of step s has seen every output of step s-1, recursively
+                        const size_t ri = st.rbuf < 0 ? (size_t)r * P->ldx + c : (size_t)st.rbuf * P->bufsz + (size_t)r * P->ld + c;
+                        float refv;
+                        if constexpr (LL) refv = __uint_as_float(ld_pair((st.rbuf < 0 ? P->xp : P->pbase) + ri).x);
+                        else refv = __ldcg((st.rbuf < 0 ? P->xf : P->fbase) + ri);
+                        const float d = v - refv;
                         sq = d * d;
                     }
                 }
@@ -248,6 +314,9 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         }
         if (s + 1 < n_steps) {
             __syncthreads();            // everybody is done reading the current slice and activation tile
+            if constexpr (!LL) {
+                if (tid == 0 && ncols > 0) { __threadfence(); st_flag(P->flags + (size_t)(s + 1) * grid + cta, seq32); }
+            }
             w4 = prefetch_weights(s + 1);
             vpre = prefetch_vec(s + 1);
         }
@@ -302,11 +371,14 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
 struct StreamState {
     int lo = -1, hi = -1, grid = 0;
     bool ok = false;
-    size_t smem[3] = {0, 0, 0};          // dynamic shared memory of the NB = 1 / 4 / 16 instantiations
-    bool fits[3] = {false, false, false};
+    size_t smem[5] = {0, 0, 0, 0, 0};    // dynamic shared memory of the NB = 1 / 4 (pairs) and 8 / 12 / 16 (flags) instantiations
+    bool fits[5] = {false, false, false, false, false};
     StPlan* d_plan = nullptr;
     uint2* d_x = nullptr;                // staged input, (value, sequence) pairs
     uint2* d_act = nullptr;              // one pair buffer per step output (nothing is reused inside a call)
+    float* d_xf = nullptr;               // the same as plain floats (flag protocol)
+    float* d_actf = nullptr;
+    uint32_t* d_flags = nullptr;
     float* d_partial = nullptr;
     unsigned long long* d_bar = nullptr;
     float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
@@ -321,19 +393,29 @@ struct StreamState {
 void stream_free(StreamState* s) {
     if (!s) return;
     cudaFree(s->d_plan); cudaFree(s->d_x); cudaFree(s->d_act); cudaFree(s->d_partial); cudaFree(s->d_bar); cudaFree(s->d_dbg);
+    cudaFree(s->d_xf); cudaFree(s->d_actf); cudaFree(s->d_flags);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
-template <int NB> int launch(StreamState* S, int rows) {
-    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, nullptr, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base,
-                    (void*)&S->d_dbg};
+constexpr int kNbOf[5] = {1, 4, 8, 12, 16};
+const void* stream_kernel(int idx) {
+    switch (idx) {
+        case 0: return (const void*)stream_chain_kernel<1, true>;
+        case 1: return (const void*)stream_chain_kernel<4, true>;
+        case 2: return (const void*)stream_chain_kernel<8, false>;
+        case 3: return (const void*)stream_chain_kernel<12, false>;
+        default: return (const void*)stream_chain_kernel<16, false>;
+    }
+}
+
+int launch(StreamState* S, int idx, int rows) {
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(S->d_out + 2 * ST_MAX_ROWS);
-    args[4] = (void*)&flag;
-    const int idx = NB == 1 ? 0 : (NB == 4 ? 1 : 2);
-    MMAD_CUDA_OK(cudaLaunchCooperativeKernel((const void*)stream_chain_kernel<NB>, dim3(S->grid), dim3(ST_THREADS), args, S->smem[idx], S->stream));
+    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, (void*)&flag, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base,
+                    (void*)&S->d_dbg};
+    MMAD_CUDA_OK(cudaLaunchCooperativeKernel(stream_kernel(idx), dim3(S->grid), dim3(ST_THREADS), args, S->smem[idx], S->stream));
     return MMAD_OK;
 }
 
@@ -399,60 +481,68 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         MMAD_CUDA_OK(cudaMalloc(&S->d_partial, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
         MMAD_CUDA_OK(cudaMemset(S->d_act, 0, buf * n_buf * 8));       // sequence 0 is never used by a call
         MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 8));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_actf, buf * n_buf * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_xf, buf * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_flags, (size_t)(ST_MAX_STEPS + 1) * S->grid * 4));
+        MMAD_CUDA_OK(cudaMemset(S->d_flags, 0, (size_t)(ST_MAX_STEPS + 1) * S->grid * 4));
     }
+    MMAD_CUDA_OK(cudaMemset(S->d_actf, 0, buf * n_buf * 4));          // padding columns of the float buffers stay zero for ever
+    MMAD_CUDA_OK(cudaMemset(S->d_xf, 0, buf * 4));
     MMAD_CUDA_OK(cudaMemset(S->d_partial, 0, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
-    auto B = [&](int i) { return S->d_act + buf * i; };           // 0..L-1 enc(x) (the diff references), L..L+Ld-1 decoder, then enc(xhat)
+    // buffers: 0..L-1 enc(x) (the diff references), L..L+Ld-1 decoder, then enc(xhat)
     StPlan P;
     memset(&P, 0, sizeof P);
     P.lo = lo; P.hi = hi; P.D = D; P.ldx = round_up(D, kPad); P.grid = S->grid;
     P.n_diffs = L + 1;
     P.slope = d->lrelu_slope;
-    P.x_dev = S->d_x; P.partial = S->d_partial;
+    P.xp = S->d_x; P.pbase = S->d_act; P.xf = S->d_xf; P.fbase = S->d_actf; P.flags = S->d_flags;
+    P.bufsz = buf; P.ld = maxw;
+    P.partial = S->d_partial;
     P.inv_base = 1.f / D;
     int dsel = 0;
     for (int l = lo; l < hi; ++l) dsel += d->enc_widths[l];
     P.inv_sap = 1.f / dsel;
     int ns = 0;
-    size_t need[3] = {0, 0, 0};
-    auto add = [&](const LayerF32& Lr, const uint2* in, int ldin, uint2* out, int ldout, const uint2* ref, int ldref, int diff) {
+    size_t need[5] = {0, 0, 0, 0, 0};
+    int prev_nprod = 0;
+    auto add = [&](const LayerF32& Lr, int ibuf, int obuf, int rbuf, int diff) {
         StStep& st = P.step[ns++];
         st.W = Lr.W; st.bias = Lr.bias; st.scale = Lr.has_bn ? Lr.scale : nullptr; st.shift = Lr.has_bn ? Lr.shift : nullptr;
-        st.in = in; st.out = out; st.ref = ref;
-        st.K = Lr.K; st.K4 = Lr.Kp / 4; st.N = Lr.N; st.ldin = ldin; st.ldout = ldout; st.ldref = ldref;
+        st.ibuf = ibuf; st.obuf = obuf; st.rbuf = rbuf;
+        st.nprod = prev_nprod;
+        st.K = Lr.K; st.K4 = Lr.Kp / 4; st.N = Lr.N;
         st.cpc = (Lr.N + S->grid - 1) / S->grid;
         st.diff = diff;
-        if (diff >= 0) P.nact[diff] = (Lr.N + st.cpc - 1) / st.cpc;
-        const int nbs[3] = {1, 4, 16};
-        for (int i = 0; i < 3; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + nbs[i]) * Lr.Kp * 4);
+        prev_nprod = (Lr.N + st.cpc - 1) / st.cpc;
+        if (diff >= 0) P.nact[diff] = prev_nprod;
+        for (int i = 0; i < 5; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + kNbOf[i]) * Lr.Kp * 4);
     };
-    const uint2* cur = S->d_x;
-    int ldcur = P.ldx;
-    for (int l = 0; l < L; ++l) { add(enc[l], cur, ldcur, B(l), maxw, nullptr, 0, -1); cur = B(l); ldcur = maxw; }
+    int cur = -1;
+    for (int l = 0; l < L; ++l) { add(enc[l], cur, l, -2, -1); cur = l; }
     const int want_enc2 = hi > 1;
     for (int l = 0; l < Ld; ++l) {
         const bool last = l == Ld - 1;
-        add(dec[l], cur, ldcur, B(L + l), maxw, last ? S->d_x : nullptr, P.ldx, last ? 0 : -1);
-        cur = B(L + l); ldcur = maxw;
+        add(dec[l], cur, L + l, last ? -1 : -2, last ? 0 : -1);
+        cur = L + l;
     }
     if (want_enc2) {
         const int last = std::min(L, hi - 1);
         for (int l = 1; l <= last; ++l) {
-            uint2* out = l == last ? nullptr : B(L + Ld + l - 1);
-            add(enc[l - 1], cur, ldcur, out, maxw, B(l - 1), maxw, l);
+            const int out = l == last ? -2 : L + Ld + l - 1;
+            add(enc[l - 1], cur, out, l - 1, l);
             cur = out;
         }
     }
     P.n_steps = ns;          // diffs beyond `last` have no producers: nact == 0, their sum is 0
     S->n_steps = ns;
     MMAD_CUDA_OK(cudaMemcpy(S->d_plan, &P, sizeof P, cudaMemcpyHostToDevice));
-    const void* kern[3] = {(const void*)stream_chain_kernel<1>, (const void*)stream_chain_kernel<4>, (const void*)stream_chain_kernel<16>};
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 5; ++i) {
         S->smem[i] = need[i];
         S->fits[i] = need[i] <= (size_t)ST_SMEM_CAP;
         if (S->fits[i]) {
-            MMAD_CUDA_OK(cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[i]));
+            MMAD_CUDA_OK(cudaFuncSetAttribute(stream_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[i]));
             int nblk = 0;
-            MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern[i], ST_THREADS, need[i]));
+            MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, stream_kernel(i), ST_THREADS, need[i]));
             if (nblk < 1) S->fits[i] = false;
         }
     }
@@ -469,7 +559,10 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
     int rc = stream_prepare(h, lo, hi);
     if (rc) return rc;
     StreamState* S = static_cast<StreamState*>(handle_stream_get(h));
-    const int idx = rows <= 1 ? 0 : (rows <= 4 ? 1 : 2);
+    // <= 4 rows: pair protocol; taller calls: flags, the smallest row tile that covers the call (chunks of 16 beyond that)
+    int idx = rows <= 1 ? 0 : (rows <= 4 ? 1 : (rows <= 8 ? 2 : (rows <= 12 ? 3 : 4)));
+    while (idx >= 2 && !S->fits[idx]) --idx;          // a narrower row tile needs less shared memory (more chunks)
+    if (idx == 1 && rows > 4) idx = 2;
     if (!S->fits[idx]) { set_error("stream kernel: shared memory"); return MMAD_E_UNSUPPORTED; }
     const int D = S->D;
     if (h_x != S->h_in) {
@@ -477,7 +570,7 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
         else for (int r = 0; r < rows; ++r) memcpy(S->h_in + (size_t)r * D, h_x + (size_t)r * ldx, (size_t)D * 4);
     }
     S->seq += 1;
-    if (idx == 0) rc = launch<1>(S, rows); else if (idx == 1) rc = launch<4>(S, rows); else rc = launch<16>(S, rows);
+    rc = launch(S, idx, rows);
     if (rc) return rc;
     MMAD_LAUNCHED();
     S->bar_base += (unsigned long long)S->grid;          // one arrival per CTA and call (the last one finalises)
