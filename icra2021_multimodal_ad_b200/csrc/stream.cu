@@ -36,7 +36,6 @@ constexpr int ST_SMEM_CAP = 227 * 1024 - 1024;
 struct StStep {
     const float* W; const float* bias; const float* scale; const float* shift;   // scale == nullptr: bare Linear
     int ibuf, obuf, rbuf;   // input / output / diff-reference buffer: -2 none, -1 the staged input x, >= 0 activation buffer
-    int nprod;         // CTAs that produce the input buffer (flag protocol)
     int K;             // contraction length (valid input columns)
     int K4;            // padded contraction length / 4 (row stride of W in float4, of the shared activation tile)
     int N;
@@ -47,11 +46,10 @@ struct StStep {
 struct StPlan {
     int n_steps, n_diffs, lo, hi, D, ldx, grid;
     float inv_base, inv_sap, slope;
-    // every step output exists twice: as (value, sequence) pairs for calls of <= 4 rows and as plain floats + one flag per
-    // producer CTA for taller calls; buffer i starts at base + i * bufsz elements, rows are ld (x: ldx) elements apart
+    // every step output exists twice: as (value, sequence) pairs for calls of <= 4 rows and as plain floats (layers separated
+    // by grid barriers) for taller calls; buffer i starts at base + i * bufsz elements, rows are ld (x: ldx) elements apart
     uint2* xp; uint2* pbase;
     float* xf; float* fbase;
-    uint32_t* flags;   // [n_steps + 1][grid]: flags[0] = x staged, flags[s + 1] = outputs of step s
     size_t bufsz;
     int ld;
     float* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2
@@ -74,14 +72,28 @@ __device__ __forceinline__ void st_pair(uint2* p, float value, uint32_t seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(seq) : "memory");
 }
 
-// flag protocol (taller calls): plain float activations, one release-store flag per producer CTA and step
-__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// barrier protocol (taller calls): plain float activations, layers separated by a device-wide barrier of the cooperatively
+// launched grid -- a monotonically increasing arrival counter (never reset; `target` carries the call's base), one
+// release-add and one polling thread per CTA.  (One flag per producer CTA polled by every consumer was measured slower:
+// 148 x 148 acquire polls crowd the L2 -- 205 us against 167 us at 10 rows.)
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ULL) : "memory");
+        const long long t0 = clock64();
+        while (ld_acquire(bar) < target) {
+            if (clock64() - t0 > 2000000000LL) {
+                printf("mmad stream kernel: grid barrier timed out (block %d, target %llu)\n", blockIdx.x, target);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
@@ -97,7 +109,7 @@ template <int NB, bool LL>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
                     unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base,
-                    unsigned long long* dbg) {
+                    unsigned long long bar2_base, unsigned long long* dbg) {
     extern __shared__ __align__(16) float st_smem[];
     __shared__ float s_red[ST_KQ][NB][ST_CPC];
     __shared__ float s_sq[NB][ST_CPC];
@@ -117,6 +129,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     const int n_steps = P->n_steps;
     const float slope = P->slope;
     const uint32_t seq32 = (uint32_t)seq;
+    unsigned long long arrivals = bar2_base;      // barrier protocol: bar[1] counts the arrivals of every barrier of every call
 
     auto prefetch_weights = [&](int s) -> uint32_t {    // cp.async of this CTA's weight slice; returns its float4 extent
         const StStep& st = P->step[s];
@@ -158,10 +171,8 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
             const int r = i / D4, c = i - r * D4;
             xd[(size_t)r * ld4 + c] = __ldcv(xs + i);
         }
-        if (cta * ST_THREADS < total) {
-            __syncthreads();
-            if (tid == 0) { __threadfence(); st_flag(P->flags + cta, seq32); }
-        }
+        arrivals += grid;
+        grid_barrier(bar + 1, arrivals);
     }
     stamp(1);
 
@@ -220,20 +231,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
                     }
                 }
             } else {
-                // wait for the flags of the CTAs that produce the input (first row chunk only), then bulk-copy the rows
-                if (r0 == 0) {
-                    const int nprod = s == 0 ? min(grid, (rows * (P->D >> 2) + ST_THREADS - 1) / ST_THREADS) : st.nprod;
-                    if (tid < nprod) {
-                        const uint32_t* f = P->flags + (size_t)s * grid + tid;
-                        while (ld_flag(f) != seq32) {
-                            if (clock64() - t0 > 2000000000LL) {
-                                printf("mmad stream kernel: producer %d of step %d never signalled (block %d)\n", tid, s, cta);
-                                __trap();
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
+                // the barrier behind the previous step made its outputs visible: bulk-copy the rows
                 const float* in = st.ibuf < 0 ? P->xf : P->fbase + (size_t)st.ibuf * P->bufsz;
                 const int ld4 = (st.ibuf < 0 ? P->ldx : P->ld) >> 2;
                 const float4* src = reinterpret_cast<const float4*>(in) + (size_t)r0 * ld4;
@@ -314,11 +312,12 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         }
         if (s + 1 < n_steps) {
             __syncthreads();            // everybody is done reading the current slice and activation tile
-            if constexpr (!LL) {
-                if (tid == 0 && ncols > 0) { __threadfence(); st_flag(P->flags + (size_t)(s + 1) * grid + cta, seq32); }
-            }
-            w4 = prefetch_weights(s + 1);
+            w4 = prefetch_weights(s + 1);          // travels while this CTA waits for the others
             vpre = prefetch_vec(s + 1);
+            if constexpr (!LL) {
+                arrivals += grid;
+                grid_barrier(bar + 1, arrivals);
+            }
         }
         stamp(2 + s);
     }
@@ -371,19 +370,18 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
 struct StreamState {
     int lo = -1, hi = -1, grid = 0;
     bool ok = false;
-    size_t smem[5] = {0, 0, 0, 0, 0};    // dynamic shared memory of the NB = 1 / 4 (pairs) and 8 / 12 / 16 (flags) instantiations
+    size_t smem[5] = {0, 0, 0, 0, 0};    // dynamic shared memory of the NB = 1 / 4 (pairs) and 8 / 12 / 16 (barriers) instantiations
     bool fits[5] = {false, false, false, false, false};
     StPlan* d_plan = nullptr;
     uint2* d_x = nullptr;                // staged input, (value, sequence) pairs
     uint2* d_act = nullptr;              // one pair buffer per step output (nothing is reused inside a call)
     float* d_xf = nullptr;               // the same as plain floats (flag protocol)
     float* d_actf = nullptr;
-    uint32_t* d_flags = nullptr;
     float* d_partial = nullptr;
     unsigned long long* d_bar = nullptr;
     float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
     float* h_out = nullptr; float* d_out = nullptr;     // pinned + mapped scores [2][64] + flag
-    unsigned long long seq = 0, bar_base = 0;
+    unsigned long long seq = 0, bar_base = 0, bar2_base = 0;
     unsigned long long* d_dbg = nullptr;  // MMAD_STREAM_DEBUG=1: per-phase globaltimer stamps of CTA 0
     unsigned long long weights_gen = 0;
     cudaStream_t stream = nullptr;
@@ -393,7 +391,7 @@ struct StreamState {
 void stream_free(StreamState* s) {
     if (!s) return;
     cudaFree(s->d_plan); cudaFree(s->d_x); cudaFree(s->d_act); cudaFree(s->d_partial); cudaFree(s->d_bar); cudaFree(s->d_dbg);
-    cudaFree(s->d_xf); cudaFree(s->d_actf); cudaFree(s->d_flags);
+    cudaFree(s->d_xf); cudaFree(s->d_actf);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -414,7 +412,7 @@ const void* stream_kernel(int idx) {
 int launch(StreamState* S, int idx, int rows) {
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(S->d_out + 2 * ST_MAX_ROWS);
     void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, (void*)&flag, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base,
-                    (void*)&S->d_dbg};
+                    (void*)&S->bar2_base, (void*)&S->d_dbg};
     MMAD_CUDA_OK(cudaLaunchCooperativeKernel(stream_kernel(idx), dim3(S->grid), dim3(ST_THREADS), args, S->smem[idx], S->stream));
     return MMAD_OK;
 }
@@ -450,8 +448,8 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         S->D = D;
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         MMAD_CUDA_OK(cudaMalloc(&S->d_plan, sizeof(StPlan)));
-        MMAD_CUDA_OK(cudaMalloc(&S->d_bar, 8));
-        MMAD_CUDA_OK(cudaMemset(S->d_bar, 0, 8));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_bar, 16));
+        MMAD_CUDA_OK(cudaMemset(S->d_bar, 0, 16));
         MMAD_CUDA_OK(cudaHostAlloc(&S->h_in, (size_t)ST_MAX_ROWS * D * 4, cudaHostAllocMapped));
         MMAD_CUDA_OK(cudaHostAlloc(&S->h_out, (size_t)(2 * ST_MAX_ROWS + 4) * 4, cudaHostAllocMapped));
         memset(S->h_out, 0, (size_t)(2 * ST_MAX_ROWS + 4) * 4);
@@ -483,8 +481,6 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 8));
         MMAD_CUDA_OK(cudaMalloc(&S->d_actf, buf * n_buf * 4));
         MMAD_CUDA_OK(cudaMalloc(&S->d_xf, buf * 4));
-        MMAD_CUDA_OK(cudaMalloc(&S->d_flags, (size_t)(ST_MAX_STEPS + 1) * S->grid * 4));
-        MMAD_CUDA_OK(cudaMemset(S->d_flags, 0, (size_t)(ST_MAX_STEPS + 1) * S->grid * 4));
     }
     MMAD_CUDA_OK(cudaMemset(S->d_actf, 0, buf * n_buf * 4));          // padding columns of the float buffers stay zero for ever
     MMAD_CUDA_OK(cudaMemset(S->d_xf, 0, buf * 4));
@@ -495,7 +491,7 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     P.lo = lo; P.hi = hi; P.D = D; P.ldx = round_up(D, kPad); P.grid = S->grid;
     P.n_diffs = L + 1;
     P.slope = d->lrelu_slope;
-    P.xp = S->d_x; P.pbase = S->d_act; P.xf = S->d_xf; P.fbase = S->d_actf; P.flags = S->d_flags;
+    P.xp = S->d_x; P.pbase = S->d_act; P.xf = S->d_xf; P.fbase = S->d_actf;
     P.bufsz = buf; P.ld = maxw;
     P.partial = S->d_partial;
     P.inv_base = 1.f / D;
@@ -509,7 +505,6 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         StStep& st = P.step[ns++];
         st.W = Lr.W; st.bias = Lr.bias; st.scale = Lr.has_bn ? Lr.scale : nullptr; st.shift = Lr.has_bn ? Lr.shift : nullptr;
         st.ibuf = ibuf; st.obuf = obuf; st.rbuf = rbuf;
-        st.nprod = prev_nprod;
         st.K = Lr.K; st.K4 = Lr.Kp / 4; st.N = Lr.N;
         st.cpc = (Lr.N + S->grid - 1) / S->grid;
         st.diff = diff;
@@ -559,7 +554,7 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
     int rc = stream_prepare(h, lo, hi);
     if (rc) return rc;
     StreamState* S = static_cast<StreamState*>(handle_stream_get(h));
-    // <= 4 rows: pair protocol; taller calls: flags, the smallest row tile that covers the call (chunks of 16 beyond that)
+    // <= 4 rows: pair protocol; taller calls: barriers, the smallest row tile that covers the call (chunks of 16 beyond that)
     int idx = rows <= 1 ? 0 : (rows <= 4 ? 1 : (rows <= 8 ? 2 : (rows <= 12 ? 3 : 4)));
     while (idx >= 2 && !S->fits[idx]) --idx;          // a narrower row tile needs less shared memory (more chunks)
     if (idx == 1 && rows > 4) idx = 2;
@@ -574,6 +569,7 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
     if (rc) return rc;
     MMAD_LAUNCHED();
     S->bar_base += (unsigned long long)S->grid;          // one arrival per CTA and call (the last one finalises)
+    if (idx >= 2) S->bar2_base += (unsigned long long)S->grid * (unsigned long long)S->n_steps;   // staging + n_steps - 1 barriers
     // the doorbell: the kernel's last store is the sequence number, written after the scores (system-scope fences)
     volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(S->h_out + 2 * ST_MAX_ROWS);
     const auto t0 = std::chrono::steady_clock::now();
