@@ -1054,7 +1054,10 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         return MMAD_E_STATE;
     }
     const int D = D_of(h);
-    if (n <= stream_max_rows() && !h_nap && stream_enabled() && !h->prof) {
+    // measured on B200 (profiles/r2_stream_latency.md): 68 / 98 / 166 / 194 us at 1 / 4 / 10 / 16 rows against 127 / - / 200 / - us on the
+    // graph-replay path; beyond 16 rows every CTA re-reads the whole activation tile per layer and the per-layer kernels win
+    constexpr int kStreamKernelRows = 16;
+    if (n <= kStreamKernelRows && !h_nap && stream_enabled() && !h->prof) {
         // ---- realtime path (test_file/realtime_tester.py:291-309): the whole chain in ONE cooperative launch, input and
         // scores through mapped pinned memory (stream.cu); exact fp32 whatever the handle's precision mode ----
         for (auto& L : h->enc) if (!L.loaded) { set_error("weights not loaded"); return MMAD_E_STATE; }
