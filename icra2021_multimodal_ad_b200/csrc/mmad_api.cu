@@ -110,6 +110,8 @@ struct mmad_handle {
     std::vector<MapRec> maps;
     unsigned long long weights_gen = 0;   // incremented by every mmad_set_layer
     void* stream_state = nullptr;         // one-launch realtime kernel (stream.cu)
+    void* smallnet_state = nullptr;       // fused chain of the per-modality models (smallnet.cu)
+    bool smallnet = true;                 // mmad_set_option "smallnet"
 };
 
 namespace mmad {
@@ -514,6 +516,8 @@ LayerF32 handle_layer_f32(mmad_t h, int module, int index) {
 }
 unsigned long long handle_weights_gen(mmad_t h) { return h->weights_gen; }
 void* handle_stream_get(mmad_t h) { return h->stream_state; }
+void* handle_smallnet_get(mmad_t h) { return h->smallnet_state; }
+void handle_smallnet_set(mmad_t h, void* state) { h->smallnet_state = state; }
 void handle_stream_set(mmad_t h, void* state) { h->stream_state = state; }
 
 LayerView handle_layer(mmad_t h, int module, int index) {
@@ -597,6 +601,8 @@ int mmad_destroy(mmad_t h) {
     mmad_comm_destroy(h);
     stream_state_free(h->stream_state);
     h->stream_state = nullptr;
+    smallnet_state_free(h->smallnet_state);
+    h->smallnet_state = nullptr;
     for (auto& L : h->enc) free_layer(L);
     for (auto& L : h->dec) free_layer(L);
     cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);
@@ -643,6 +649,8 @@ int mmad_set_option(mmad_t h, const char* name, double value) {
         h->nap_passes = (int)value;
     } else if (!strcmp(name, "require_pinned")) {
         h->require_pinned = value != 0;
+    } else if (!strcmp(name, "smallnet")) {
+        h->smallnet = value != 0;
     } else {
         set_error("unknown option '%s'", name);
         return MMAD_E_ARG;
@@ -835,6 +843,13 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     // F16F8 NAP: the fit's variances carry this mode's rounding noise in the near-null directions, so scoring keeps the
     // same arithmetic at every batch size
     if (h->desc.precision == MMAD_PREC_F16F8 && d_nap) h->skinny = false;
+    // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29): base / SAP scores from ONE
+    // fused kernel, exact fp32 whatever the handle's precision mode (smallnet.cu)
+    if (n > 0 && !d_nap && !d_diffs && h->smallnet && !h->prof && smallnet_enabled() && smallnet_fits(h) && d_x && (ldx % 4 == 0) &&
+        ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) && !check_range(h, lo, hi)) {
+        rc = smallnet_score(h, d_x, ldx, n, lo, hi, d_base, d_sap, (cudaStream_t)stream);
+        if (rc != MMAD_E_UNSUPPORTED) { h->skinny = false; return rc; }      // (plan not built while the stream is capturing)
+    }
     rc = score_impl(h, d_x, ldx, n, lo, hi, d_base, d_sap, d_nap, d_diffs, d_ws, ws_bytes, stream);
     h->skinny = false;
     return rc;
@@ -1126,6 +1141,10 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         if (!exec) {
             cudaStream_t cs = handle_capture_stream(h);
             if (!cs) return MMAD_E_CUDA;
+            if (!on && h->smallnet && smallnet_enabled() && smallnet_fits(h)) {      // its plan cannot be built inside a capture
+                rc = smallnet_prepare(h, lo, hi, s);
+                if (rc) return rc;
+            }
             const unsigned long long l0 = g_launches;
             MMAD_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
             rc = mmad_score(h, h->host_x[0], D, rows, lo, hi, ob, os, on, nullptr, h->host_ws, h->host_ws_bytes, cs);

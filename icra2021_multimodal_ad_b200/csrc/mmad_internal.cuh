@@ -144,6 +144,14 @@ bool stream_enabled();                                // MMAD_NO_STREAM_KERNEL=1
 int stream_max_rows();
 int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, float* h_base, float* h_sap);
 float* stream_input_buffer(mmad_t h, int lo, int hi);
+// fused whole-chain kernel for models whose widths are all <= 128 (smallnet.cu)
+void* handle_smallnet_get(mmad_t h);
+void handle_smallnet_set(mmad_t h, void* state);
+void smallnet_state_free(void* state);
+bool smallnet_enabled();                              // MMAD_NO_SMALLNET=1 disables
+bool smallnet_fits(mmad_t h);
+int smallnet_prepare(mmad_t h, int lo, int hi, cudaStream_t s);     // (re)builds the packed plan; synchronises s
+int smallnet_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, cudaStream_t s);
 
 // CUDA-graph cache of a handle (launch-bound sequences: the train step, small-batch scoring)
 bool graphs_enabled();                       // MMAD_NO_GRAPHS=1 disables
