@@ -20,7 +20,7 @@ namespace mmad {
 namespace {
 
 constexpr int SN_T = 256;
-constexpr int SN_BM = 32;            // windows per tile
+constexpr int SN_BM_MAX = 64;        // windows per tile: 64 (thread tile 4 / 8 rows x 8 columns) or 32 (2 / 4 rows)
 constexpr int SN_W = 128;            // padded width of every layer
 constexpr int SN_LD = SN_W + 4;      // shared-memory row stride (floats): rows 16-byte aligned, 4-bank skew per row
 constexpr int SN_MAX_STEPS = 3 * MMAD_MAX_LAYERS;
@@ -41,18 +41,20 @@ struct SnPlan {
 };
 
 // one fused layer on R rows per thread: out[r][c] = epi(sum_k in[r][k] * Wt[k][c]).  `in` / `out`: shared tiles [rows][SN_LD].
-// Rows of thread (ty): r = rows_of(ty, i).  PASS_B: rows {2ty, 2ty+1} (x path) and {32 + 2ty, 32 + 2ty + 1} (xhat path).
-template <int R>
+// Rows of thread ty: the first RA = BM / 16 are windows RA * ty + i (x path); the next RA, if any, the same windows' xhat rows
+// (BM + RA * ty + i): a thread owns both paths of its windows, so pass B's diffs are register-local.
+// The accumulators are transformed in place and handed back in v.
+template <int R, int BM>
 __device__ __forceinline__ void sn_layer(const SnStep& st, const float* __restrict__ in, float* __restrict__ out, float slope,
                                          int tx, int ty, float (&v)[R][8]) {
-    float acc[R][8];
+    constexpr int RA = BM / 16;
 #pragma unroll
     for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
     int row[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) row[i] = (i < 2 ? 0 : SN_BM) + 2 * ty + (i & 1);
+    for (int i = 0; i < R; ++i) row[i] = (i < RA ? 0 : BM) + RA * ty + (i % RA);
     const float4* wt = reinterpret_cast<const float4*>(st.Wt);
 #pragma unroll 2
     for (int k4 = 0; k4 < st.K4; ++k4) {
@@ -66,34 +68,37 @@ __device__ __forceinline__ void sn_layer(const SnStep& st, const float* __restri
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
-                acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
-                acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
-                acc[i][4] = fmaf(av, w1.x, acc[i][4]); acc[i][5] = fmaf(av, w1.y, acc[i][5]);
-                acc[i][6] = fmaf(av, w1.z, acc[i][6]); acc[i][7] = fmaf(av, w1.w, acc[i][7]);
+                v[i][0] = fmaf(av, w0.x, v[i][0]); v[i][1] = fmaf(av, w0.y, v[i][1]);
+                v[i][2] = fmaf(av, w0.z, v[i][2]); v[i][3] = fmaf(av, w0.w, v[i][3]);
+                v[i][4] = fmaf(av, w1.x, v[i][4]); v[i][5] = fmaf(av, w1.y, v[i][5]);
+                v[i][6] = fmaf(av, w1.z, v[i][6]); v[i][7] = fmaf(av, w1.w, v[i][7]);
             }
         }
     }
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(st.bias) + tx), b1 = __ldg(reinterpret_cast<const float4*>(st.bias) + 16 + tx);
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float sc[8], sh[8];
     if (st.scale) {
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(st.scale) + tx), s1 = __ldg(reinterpret_cast<const float4*>(st.scale) + 16 + tx);
         const float4 h0 = __ldg(reinterpret_cast<const float4*>(st.shift) + tx), h1 = __ldg(reinterpret_cast<const float4*>(st.shift) + 16 + tx);
-        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
-    }
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float x = acc[i][j] + bb[j];
-            if (st.scale) {
+            for (int j = 0; j < 8; ++j) {
+                float x = v[i][j] + bb[j];
                 x = x > 0.f ? x : x * slope;
-                x = fmaf(x, sc[j], sh[j]);
+                v[i][j] = fmaf(x, sc[j], sh[j]);          // padded columns: zero weights, bias, scale, shift -> 0
             }
-            v[i][j] = x;            // padded columns: zero weights, zero bias, zero scale/shift -> 0
-        }
-        if (out) {
+    } else {
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] += bb[j];
+    }
+    if (out) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
             *reinterpret_cast<float4*>(out + row[i] * SN_LD + 4 * tx) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
             *reinterpret_cast<float4*>(out + row[i] * SN_LD + 64 + 4 * tx) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
         }
@@ -109,21 +114,23 @@ __device__ __forceinline__ float sn_half_warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(SN_T, 2)
+template <int BM>
+__global__ void __launch_bounds__(SN_T, BM == 32 ? 2 : 1)
 smallnet_chain_kernel(const SnPlan* __restrict__ P, const float* __restrict__ x, int ldx, int n, float* __restrict__ base_out,
                       float* __restrict__ sap_out) {
+    constexpr int RA = BM / 16;
     extern __shared__ __align__(16) float sn_smem[];
-    float* xs = sn_smem;                               // [32][SN_LD]   the tile's input rows (zero padded to 128 columns)
-    float* A0 = xs + SN_BM * SN_LD;                    // [64][SN_LD]   ping
-    float* A1 = A0 + 2 * SN_BM * SN_LD;                // [64][SN_LD]   pong
+    float* xs = sn_smem;                               // [BM][SN_LD]      the tile's input rows (zero padded to 128 columns)
+    float* A0 = xs + BM * SN_LD;                       // [2 BM][SN_LD]    ping
+    float* A1 = A0 + 2 * BM * SN_LD;                   // [2 BM][SN_LD]    pong
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int D = P->D, L = P->n_enc, Ld = P->n_dec;
     const float slope = P->slope;
-    const int tiles = (n + SN_BM - 1) / SN_BM;
+    const int tiles = (n + BM - 1) / BM;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int r0 = t * SN_BM;
+        const int r0 = t * BM;
         __syncthreads();                               // the previous tile's readers are done
-        for (int i = tid; i < SN_BM * (SN_W / 4); i += SN_T) {
+        for (int i = tid; i < BM * (SN_W / 4); i += SN_T) {
             const int r = i / (SN_W / 4), c = (i % (SN_W / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r0 + r < n) {
@@ -134,65 +141,64 @@ smallnet_chain_kernel(const SnPlan* __restrict__ P, const float* __restrict__ x,
             *reinterpret_cast<float4*>(xs + r * SN_LD + c) = v;
         }
         __syncthreads();
-        // ---- pass A: encoder and decoder on the 32 x rows ----
+        // ---- pass A: encoder and decoder on the BM x rows ----
         const float* cur = xs;
         float* nxt = A0;
-        float v2[2][8];
+        float va[RA][8];
         for (int l = 0; l < L; ++l) {
-            sn_layer<2>(P->enc[l], cur, nxt, slope, tx, ty, v2);
+            sn_layer<RA, BM>(P->enc[l], cur, nxt, slope, tx, ty, va);
             __syncthreads();
             cur = nxt; nxt = (nxt == A0) ? A1 : A0;
         }
         for (int l = 0; l < Ld; ++l) {
-            // the reconstruction goes to rows 32..63 of the tile that pass B starts from: [x | xhat]
-            float* out = (l == Ld - 1) ? nullptr : nxt;
-            sn_layer<2>(P->dec[l], cur, out, slope, tx, ty, v2);
+            float* out = (l == Ld - 1) ? nullptr : nxt;          // the reconstruction stays in registers
+            sn_layer<RA, BM>(P->dec[l], cur, out, slope, tx, ty, va);
             if (l < Ld - 1) { __syncthreads(); cur = nxt; nxt = (nxt == A0) ? A1 : A0; }
         }
-        // d_0 = xhat - x (thread-local: this thread's rows 2ty, 2ty+1, its 8 columns), base score, stacked tile for pass B
-        float base2[2], sap2[2] = {0.f, 0.f};
-        float* S = nxt;                                // free buffer: becomes the stacked [x | xhat] tile
+        // d_0 = xhat - x (thread-local: this thread's windows, its 8 columns), base score, stacked tile [x | xhat] for pass B
+        float base_r[RA], sap_r[RA];
+        float* S = nxt;                                // the free buffer
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int r = 2 * ty + i;
+        for (int i = 0; i < RA; ++i) {
+            const int r = RA * ty + i;
             const float4 x0 = *reinterpret_cast<const float4*>(xs + r * SN_LD + 4 * tx);
             const float4 x1 = *reinterpret_cast<const float4*>(xs + r * SN_LD + 64 + 4 * tx);
-            const float d[8] = {v2[i][0] - x0.x, v2[i][1] - x0.y, v2[i][2] - x0.z, v2[i][3] - x0.w,
-                                v2[i][4] - x1.x, v2[i][5] - x1.y, v2[i][6] - x1.z, v2[i][7] - x1.w};
+            const float d[8] = {va[i][0] - x0.x, va[i][1] - x0.y, va[i][2] - x0.z, va[i][3] - x0.w,
+                                va[i][4] - x1.x, va[i][5] - x1.y, va[i][6] - x1.z, va[i][7] - x1.w};
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) s = fmaf(d[j], d[j], s);
-            base2[i] = sn_half_warp_sum(s);
-            if (P->lo == 0) sap2[i] = base2[i];
+            base_r[i] = sn_half_warp_sum(s);
+            sap_r[i] = P->lo == 0 ? base_r[i] : 0.f;
             *reinterpret_cast<float4*>(S + r * SN_LD + 4 * tx) = x0;
             *reinterpret_cast<float4*>(S + r * SN_LD + 64 + 4 * tx) = x1;
-            *reinterpret_cast<float4*>(S + (SN_BM + r) * SN_LD + 4 * tx) = make_float4(v2[i][0], v2[i][1], v2[i][2], v2[i][3]);
-            *reinterpret_cast<float4*>(S + (SN_BM + r) * SN_LD + 64 + 4 * tx) = make_float4(v2[i][4], v2[i][5], v2[i][6], v2[i][7]);
+            *reinterpret_cast<float4*>(S + (BM + r) * SN_LD + 4 * tx) = make_float4(va[i][0], va[i][1], va[i][2], va[i][3]);
+            *reinterpret_cast<float4*>(S + (BM + r) * SN_LD + 64 + 4 * tx) = make_float4(va[i][4], va[i][5], va[i][6], va[i][7]);
         }
         __syncthreads();
         // ---- pass B: the encoder on [x | xhat], diffs between this thread's x rows and xhat rows ----
         cur = S; nxt = (S == A0) ? A1 : A0;
-        float v4[4][8];
+        float vb[2 * RA][8];
         for (int l = 1; l <= P->last; ++l) {
-            sn_layer<4>(P->enc[l - 1], cur, l == P->last ? nullptr : nxt, slope, tx, ty, v4);
+            sn_layer<2 * RA, BM>(P->enc[l - 1], cur, l == P->last ? nullptr : nxt, slope, tx, ty, vb);
             if (l >= P->lo && l < P->hi) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < RA; ++i) {
                     float s = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float d = v4[2 + i][j] - v4[i][j]; s = fmaf(d, d, s); }
-                    sap2[i] += sn_half_warp_sum(s);
+                    for (int j = 0; j < 8; ++j) { const float d = vb[RA + i][j] - vb[i][j]; s = fmaf(d, d, s); }
+                    sap_r[i] += sn_half_warp_sum(s);
                 }
             }
             if (l < P->last) { __syncthreads(); cur = nxt; nxt = (nxt == A0) ? A1 : A0; }
         }
         if (tx == 0) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int r = r0 + 2 * ty + i;
+            for (int i = 0; i < RA; ++i) {
+                const int r = r0 + RA * ty + i;
                 if (r < n) {
-                    if (base_out) base_out[r] = base2[i] * P->inv_base;
-                    if (sap_out) sap_out[r] = sap2[i] * P->inv_sap;
+                    if (base_out) base_out[r] = base_r[i] * P->inv_base;
+                    if (sap_out) sap_out[r] = sap_r[i] * P->inv_sap;
                 }
             }
         }
@@ -220,11 +226,11 @@ struct SmallNetState {
     SnPlan* d_plan = nullptr;
     float* d_pack = nullptr;       // transposed weights + padded vectors of every layer
     size_t pack_floats = 0;
-    int grid_max = 0;
+    int grid_max[2] = {0, 0};      // BM = 32, 64
     bool attr_set = false;
 };
 
-constexpr int kSnSmem = (SN_BM + 4 * SN_BM) * SN_LD * 4;    // xs + two stacked tiles = 84 480 B
+constexpr int sn_smem_bytes(int bm) { return 5 * bm * SN_LD * 4; }    // xs + two stacked tiles: 84 480 B (BM 32) / 168 960 B (BM 64)
 
 }  // namespace
 
@@ -303,12 +309,15 @@ int smallnet_prepare(mmad_t h, int lo, int hi, cudaStream_t s) {
     MMAD_CUDA_OK(cudaMemcpyAsync(S->d_plan, &P, sizeof P, cudaMemcpyHostToDevice, s));
     MMAD_CUDA_OK(cudaStreamSynchronize(s));       // P lives on this stack frame
     if (!S->attr_set) {
-        MMAD_CUDA_OK(cudaFuncSetAttribute(smallnet_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSnSmem));
+        MMAD_CUDA_OK(cudaFuncSetAttribute(smallnet_chain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sn_smem_bytes(32)));
+        MMAD_CUDA_OK(cudaFuncSetAttribute(smallnet_chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, sn_smem_bytes(64)));
         int dev = 0, sms = 148, per = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, smallnet_chain_kernel, SN_T, kSnSmem));
-        S->grid_max = sms * std::max(per, 1);
+        MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, smallnet_chain_kernel<32>, SN_T, sn_smem_bytes(32)));
+        S->grid_max[0] = sms * std::max(per, 1);
+        MMAD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, smallnet_chain_kernel<64>, SN_T, sn_smem_bytes(64)));
+        S->grid_max[1] = sms * std::max(per, 1);
         S->attr_set = true;
     }
     S->lo = lo; S->hi = hi;
@@ -330,9 +339,18 @@ int smallnet_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, f
         if (rc) return rc;
         S = static_cast<SmallNetState*>(handle_smallnet_get(h));
     }
-    const int tiles = (n + SN_BM - 1) / SN_BM;
-    const int grid = std::min(tiles, S->grid_max);
-    smallnet_chain_kernel<<<grid, SN_T, kSnSmem, s>>>(S->d_plan, d_x, ldx, n, d_base, d_sap);
+    // 64-window tiles (8 x 8 register tile in pass B: fewer weight loads per FMA) once they fill the SMs; 32-window tiles
+    // (two CTAs per SM) for shorter calls.  MMAD_SMALLNET_BM forces one for experiments.
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("MMAD_SMALLNET_BM"); force = e ? atoi(e) : 0; }
+    const bool big = force ? force == 64 : n >= 64 * S->grid_max[1];
+    if (big) {
+        const int grid = std::min((n + 63) / 64, S->grid_max[1]);
+        smallnet_chain_kernel<64><<<grid, SN_T, sn_smem_bytes(64), s>>>(S->d_plan, d_x, ldx, n, d_base, d_sap);
+    } else {
+        const int grid = std::min((n + 31) / 32, S->grid_max[0]);
+        smallnet_chain_kernel<32><<<grid, SN_T, sn_smem_bytes(32), s>>>(S->d_plan, d_x, ldx, n, d_base, d_sap);
+    }
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

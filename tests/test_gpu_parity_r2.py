@@ -357,7 +357,7 @@ def test_smallnet_fused_chain_matches_oracle(D, btl, nl, precision):
         np.testing.assert_allclose(o["sap"].cpu().numpy(), RO.sap_score(ref), rtol=2e-5)
         np.testing.assert_allclose(o["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=2e-5)
         if n == 257:
-            for lo, hi in ((0, 1), (1, 2), (2, nl), (nl, nl + 1), (1, nl + 1)):
+            for lo, hi in ((0, 1), (1, 2), (1, nl), (nl, nl + 1), (1, nl + 1)):
                 s = eng.score(xd, lo, hi)
                 np.testing.assert_allclose(s["sap"].cpu().numpy(), RO.sap_score(ref, lo, hi), rtol=2e-5)
                 np.testing.assert_allclose(s["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=2e-5)
