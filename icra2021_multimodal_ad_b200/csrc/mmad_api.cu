@@ -843,9 +843,11 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     // F16F8 NAP: the fit's variances carry this mode's rounding noise in the near-null directions, so scoring keeps the
     // same arithmetic at every batch size
     if (h->desc.precision == MMAD_PREC_F16F8 && d_nap) h->skinny = false;
-    // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29): base / SAP scores from ONE
-    // fused kernel, exact fp32 whatever the handle's precision mode (smallnet.cu)
-    if (n > 0 && !d_nap && !d_diffs && h->smallnet && !h->prof && smallnet_enabled() && smallnet_fits(h) && d_x && (ldx % 4 == 0) &&
+    // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29) in the fp32 mode: base / SAP
+    // scores from ONE fused exact-fp32 kernel (smallnet.cu): 65 / 48 M windows/s at D = 64 / 128 against 29 / 27 M for the
+    // per-layer fp32 kernels.  The tensor-core modes keep their per-layer kernels (93 / 92 M windows/s in f16x3).
+    if (n > 0 && !d_nap && !d_diffs && h->smallnet && h->desc.precision == MMAD_PREC_FP32 && !h->prof && smallnet_enabled() &&
+        smallnet_fits(h) && d_x && (ldx % 4 == 0) &&
         ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) && !check_range(h, lo, hi)) {
         rc = smallnet_score(h, d_x, ldx, n, lo, hi, d_base, d_sap, (cudaStream_t)stream);
         if (rc != MMAD_E_UNSUPPORTED) { h->skinny = false; return rc; }      // (plan not built while the stream is capturing)
@@ -1141,7 +1143,7 @@ int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, in
         if (!exec) {
             cudaStream_t cs = handle_capture_stream(h);
             if (!cs) return MMAD_E_CUDA;
-            if (!on && h->smallnet && smallnet_enabled() && smallnet_fits(h)) {      // its plan cannot be built inside a capture
+            if (!on && h->smallnet && h->desc.precision == MMAD_PREC_FP32 && smallnet_enabled() && smallnet_fits(h)) {      // its plan cannot be built inside a capture
                 rc = smallnet_prepare(h, lo, hi, s);
                 if (rc) return rc;
             }

@@ -81,8 +81,8 @@ int mmad_set_precision(mmad_t h, int precision);   /* invalidates an installed N
  *                     (first-order correction of the truncating fp32 accumulation); 0 = off
  *   "nap_passes"      F16X3 NAP rotation: 3 = full split (default), 2 = whitening rows rounded to fp16, 0 = default
  *   "require_pinned"  1: mmad_score_host returns MMAD_E_ARG for pageable bulk input instead of accepting it
- *   "smallnet"        0: models whose widths are all <= 128 use the per-layer kernels of the handle's precision mode
- *                     instead of the fused whole-chain fp32 kernel (default 1)
+ *   "smallnet"        0: FP32-mode models whose widths are all <= 128 use the per-layer kernels instead of the fused
+ *                     whole-chain kernel (default 1)
  * Unknown names return MMAD_E_ARG. */
 int mmad_set_option(mmad_t h, const char* name, double value);
 
