@@ -111,6 +111,7 @@ struct mmad_handle {
     unsigned long long weights_gen = 0;   // incremented by every mmad_set_layer
     void* stream_state = nullptr;         // one-launch realtime kernel (stream.cu)
     void* smallnet_state = nullptr;       // fused chain of the per-modality models (smallnet.cu)
+    void* peer_state = nullptr;           // NVLink peer buffers of the BatchNorm-statistics exchange (peer.cu)
     bool smallnet = true;                 // mmad_set_option "smallnet"
 };
 
@@ -516,6 +517,8 @@ LayerF32 handle_layer_f32(mmad_t h, int module, int index) {
 }
 unsigned long long handle_weights_gen(mmad_t h) { return h->weights_gen; }
 void* handle_stream_get(mmad_t h) { return h->stream_state; }
+void* handle_peer_get(mmad_t h) { return h->peer_state; }
+void handle_peer_set(mmad_t h, void* state) { h->peer_state = state; }
 void* handle_smallnet_get(mmad_t h) { return h->smallnet_state; }
 void handle_smallnet_set(mmad_t h, void* state) { h->smallnet_state = state; }
 void handle_stream_set(mmad_t h, void* state) { h->stream_state = state; }
@@ -598,6 +601,7 @@ int mmad_create(const mmad_desc_t* d, mmad_t* out) {
 
 int mmad_destroy(mmad_t h) {
     if (!h) return MMAD_OK;
+    mmad_peer_close(h);
     mmad_comm_destroy(h);
     stream_state_free(h->stream_state);
     h->stream_state = nullptr;

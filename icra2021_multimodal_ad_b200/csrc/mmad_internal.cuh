@@ -162,6 +162,14 @@ void handle_graph_clear(mmad_t h);
 // second stream + fork/join events of a handle (independent branches of a launch sequence); 0 on success
 int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
 
+// NVLink peer-memory exchange of small fp64 vectors (peer.cu)
+void* handle_peer_get(mmad_t h);
+void handle_peer_set(mmad_t h, void* state);
+void peer_state_free(void* state);
+bool peer_ready(mmad_t h);
+int peer_max_doubles();
+int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s);
+
 // NCCL communicator of a handle (comm.cu)
 void handle_comm(mmad_t h, void** comm, int* world);
 void handle_set_comm(mmad_t h, void* comm, int world, int rank);

@@ -679,22 +679,35 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             MMAD_LAUNCHED();
         }
     }
-    // Data parallel with the handle's communicator: every layer's gradients (W, b, gamma, beta -- contiguous in a flat
-    // gradient buffer) are all-reduced right behind its dW GEMM on the second stream, overlapping the rest of backward.
+    // Data parallel with the handle's communicator: the gradients are all-reduced in two buckets on the second stream -- the
+    // decoder's parameters (one contiguous block of the flat gradient buffer) as soon as the decoder's backward pass is done,
+    // overlapping the encoder's backward pass; the encoder's at the end.  (One all-reduce per LAYER was measured slower than a
+    // single flat one: ten medium collectives cost more latency than they hide.)
     const bool grad_ar = !allreduce && comm_p && comm_world > 1 && handle_grad_allreduce(h);
-    auto layer_grad_allreduce = [&](const mmad_train_layer_t& L, const Ref& r, cudaStream_t st) -> int {
-        const float* ptrs[4] = {L.gW, L.gb, r.bn ? L.ggamma : nullptr, r.bn ? L.gbeta : nullptr};
-        const size_t cnts[4] = {(size_t)r.N * r.K, (size_t)r.N, (size_t)r.N, (size_t)r.N};
-        uintptr_t lo = ~(uintptr_t)0, hi = 0; size_t sum = 0; int n = 0;
-        for (int i = 0; i < 4; ++i) if (ptrs[i]) {
-            const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptrs[i]);
-            lo = std::min(lo, a0); hi = std::max(hi, a0 + cnts[i] * 4); sum += cnts[i] * 4; ++n;
+    auto module_grad_allreduce = [&](int m, cudaStream_t st) -> int {
+        const mmad_train_layer_t* Ls = m == 0 ? enc : dec;
+        const int n = m == 0 ? d.n_enc : d.n_dec;
+        const int* w = m == 0 ? d.enc_widths : d.dec_widths;
+        uintptr_t lo = ~(uintptr_t)0, hi = 0; size_t sum = 0; int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            const bool bn = i < n - 1;
+            const float* ptrs[4] = {Ls[i].gW, Ls[i].gb, bn ? Ls[i].ggamma : nullptr, bn ? Ls[i].gbeta : nullptr};
+            const size_t cnts[4] = {(size_t)w[i + 1] * w[i], (size_t)w[i + 1], (size_t)w[i + 1], (size_t)w[i + 1]};
+            for (int k = 0; k < 4; ++k) if (ptrs[k]) {
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptrs[k]);
+                lo = std::min(lo, a0); hi = std::max(hi, a0 + cnts[k] * 4); sum += cnts[k] * 4; ++cnt;
+            }
         }
-        if (hi - lo <= sum + 12 * (size_t)n)      // one contiguous block (alignment padding only)
+        if (hi - lo <= sum + 12 * (size_t)cnt)      // one contiguous block (alignment padding only)
             return comm_allreduce(h, reinterpret_cast<void*>(lo), (long long)((hi - lo) / 4), false, st);
-        for (int i = 0; i < 4; ++i) if (ptrs[i]) {
-            const int rc = comm_allreduce(h, const_cast<float*>(ptrs[i]), (long long)cnts[i], false, st);
-            if (rc) return rc;
+        for (int i = 0; i < n; ++i) {               // scattered parameters: tensor by tensor
+            const bool bn = i < n - 1;
+            float* ptrs[4] = {Ls[i].gW, Ls[i].gb, bn ? Ls[i].ggamma : nullptr, bn ? Ls[i].gbeta : nullptr};
+            const size_t cnts[4] = {(size_t)w[i + 1] * w[i], (size_t)w[i + 1], (size_t)w[i + 1], (size_t)w[i + 1]};
+            for (int k = 0; k < 4; ++k) if (ptrs[k]) {
+                const int rc = comm_allreduce(h, ptrs[k], (long long)cnts[k], false, st);
+                if (rc) return rc;
+            }
         }
         return MMAD_OK;
     };
@@ -758,7 +771,9 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                     forked = true;
                 }
                 rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e, sw);
-                if (!rc && grad_ar) rc = layer_grad_allreduce(L, r, sw);
+                // the module's last weight gradient is queued: its bucket follows on the same stream (the fork event above is
+                // behind every bias / BatchNorm gradient of the module, which are computed on the main stream)
+                if (!rc && grad_ar && r.i == 0) rc = module_grad_allreduce(r.m, sw);
             } else {
                 GemmShape g;
                 g.M = r.N; g.N = r.K; g.K = B;
@@ -766,7 +781,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 g.B = r.in.f; g.ldb = r.in.ld; g.transB = true;
                 e.acc_scale = gemm_scale;
                 rc = gemm_simt(g, e, s);
-                if (!rc && grad_ar) rc = layer_grad_allreduce(L, r, s);
+                if (!rc && grad_ar && r.i == 0) rc = module_grad_allreduce(r.m, s);
             }
             if (rc) return rc;
         }

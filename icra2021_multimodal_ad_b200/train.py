@@ -121,14 +121,21 @@ def train_state(model) -> TrainState:
     return st
 
 
-def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_grads: bool = False):
+def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_grads: bool = True, peer: Optional[bool] = None):
     """Make BatchNorm batch statistics global over ``group`` (N-GPU data parallel == 1 GPU on the
     concatenated batch); gradients are combined by ``allreduce_gradients``.
 
     native (default: env MMAD_PY_ALLREDUCE != 1): the library opens its own NCCL communicator
     (``mmad_comm_init``; the unique id travels through ``torch.distributed``) and enqueues the collectives
     itself, so the data-parallel step is one CUDA-graph replay.  Otherwise ``torch.distributed.all_reduce`` is
-    called back from inside the step (works with any backend)."""
+    called back from inside the step (works with any backend).
+
+    peer (default: env MMAD_NO_PEER != 1): the 32 BatchNorm-statistics exchanges of a step (<= 2 x 1408 doubles each,
+    strictly serialised with the layer chain) run as one-kernel exchanges over NVLink peer memory (``mmad_peer_*``: every
+    rank maps every other rank's buffer through cudaIpc) instead of ncclAllReduce.  Falls back to NCCL if the GPUs cannot
+    map each other.
+    overlap_grads (default on): the gradients are all-reduced inside the captured step in two buckets on the second stream,
+    the decoder's while the encoder's backward pass still runs; ``allreduce_gradients`` is then a no-op."""
     import os
     import torch.distributed as dist
     st = train_state(model)
@@ -150,10 +157,32 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
         raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
         with torch.cuda.device(dev):
             check(lib().mmad_comm_init(eng._h, raw, dist.get_rank(group), st.world))
-            # overlap_grads: every layer's gradients are all-reduced behind its dW GEMM inside the captured step.
-            # Measured on 2 B200 at B = 256: 1.38 ms/step against 1.21 ms with ONE flat all-reduce after the step
-            # (ten medium collectives cost more latency than they hide for a 41 MB model), hence off by default.
             check(lib().mmad_comm_set_grad_allreduce(eng._h, 1 if overlap_grads else 0))
+            if peer is None:
+                peer = os.environ.get("MMAD_NO_PEER", "0") != "1"
+            st.peer = False
+            if peer:
+                hb = (C.c_ubyte * 64)()
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+                try:
+                    check(lib().mmad_peer_create(eng._h, hb))
+                except _lib.MmadError:
+                    ok.zero_()
+                mine = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
+                allh = [torch.empty_like(mine) for _ in range(st.world)]
+                dist.all_gather(allh, mine, group=group)
+                if int(ok.item()):
+                    try:
+                        raw = (C.c_ubyte * (64 * st.world))(*torch.cat(allh).cpu().tolist())
+                        check(lib().mmad_peer_open(eng._h, raw, dist.get_rank(group), st.world))
+                    except _lib.MmadError:
+                        ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks or none (a mixed set would deadlock)
+                if int(ok.item()):
+                    st.peer = True
+                else:
+                    check(lib().mmad_peer_close(eng._h))
+                dist.barrier(group)
         st.native = True
         st.native_handle = eng._h.value      # the communicator lives in THIS library handle
         st.grads_in_step = bool(overlap_grads)

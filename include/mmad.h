@@ -275,11 +275,24 @@ int mmad_comm_unique_id(unsigned char* h_id);
 int mmad_comm_init(mmad_t h, const unsigned char* h_id, int rank, int world);
 int mmad_comm_destroy(mmad_t h);
 int mmad_comm_world(mmad_t h);
-/* on: mmad_train_fwd_bwd also SUM-all-reduces every layer's gradients (W, b, gamma, beta) right behind that layer's
- * weight-gradient GEMM on its second stream, overlapping the rest of the backward pass (needs a communicator). */
+/* on: mmad_train_fwd_bwd also SUM-all-reduces the gradients in TWO buckets on its second stream -- the decoder's as soon
+ * as the decoder's backward pass is done (overlapping the encoder's), the encoder's at the end of the step (needs a
+ * communicator; the parameter gradients of a module must form one contiguous block, as the host layer's flat buffer does). */
 int mmad_comm_set_grad_allreduce(mmad_t h, int on);
 int mmad_comm_allreduce_f32(mmad_t h, float* d_buf, long long count, void* stream);
 int mmad_comm_allreduce_f64(mmad_t h, double* d_buf, long long count, void* stream);
+
+/* Latency-bound exchange of small fp64 vectors (the BatchNorm statistics of a data-parallel step: 32 strictly serialised
+ * all-reduces of <= 2 x 1408 doubles per step) over NVLink peer memory instead of ncclAllReduce: every rank creates a
+ * buffer (mmad_peer_create returns its 64-byte cudaIpc handle), the host layer gathers the handles of all ranks of the
+ * node (rank order) and every rank maps them (mmad_peer_open; call a barrier afterwards).  From then on
+ * mmad_comm_allreduce_f64 / the in-step exchanges of at most 4096 doubles run as ONE kernel (push (data, sequence)
+ * pairs to every peer, poll, add in rank order -- identical bits on every rank), also inside captured CUDA graphs. */
+#define MMAD_IPC_HANDLE_BYTES 64
+int mmad_peer_create(mmad_t h, unsigned char* h_handle);
+int mmad_peer_open(mmad_t h, const unsigned char* h_handles, int rank, int world);
+int mmad_peer_close(mmad_t h);
+int mmad_peer_allreduce_f64(mmad_t h, double* d_buf, long long count, void* stream);
 
 /* ---- multimodal feature extractor in front of the autoencoder ----
  * utils/data_loaders.py:152-229 (HSR_Net.forward) / 601-674 (Multisensory_module.forward): per sample

@@ -83,6 +83,26 @@ def _dp_worker(rank, world, port, q):
         lo, hi = P.shard_range(len(x), rank, world)
         losses = [P.data_parallel_step(model, opt, x[lo:hi]) for _ in range(3)]
         trained = {k: v.cpu() for k, v in model.state_dict().items()}
+        # the NVLink peer-memory exchange behind the BatchNorm statistics (csrc/peer.cu): against NCCL, every size class,
+        # many back-to-back exchanges (both buffer sets, sequence numbers), identical bits on both ranks
+        from icra2021_multimodal_ad_b200 import train as T
+        from icra2021_multimodal_ad_b200._lib import check, lib
+        st = T.train_state(model)
+        peer_ok = bool(getattr(st, "peer", False))
+        peer_err = 0.0
+        if peer_ok:
+            h = model.handle_engine()._h
+            g = torch.Generator(device="cuda").manual_seed(100 + rank)
+            for it in range(60):
+                n = (1, 7, 100, 2816, 4096)[it % 5]
+                v = torch.randn(n, dtype=torch.float64, device="cuda", generator=g) * 10 ** (it % 7 - 3)
+                want = v.clone()
+                dist.all_reduce(want)
+                check(lib().mmad_peer_allreduce_f64(h, v.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+                peer_err = max(peer_err, float(((v - want).abs() / want.abs().clamp_min(1e-300)).max()))
+                other = v.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(other, v)            # bit-identical on every rank
         # sharded scoring + NAP fit over both ranks (fresh identical weights, well-conditioned selection [0:1])
         model.load_state_dict(sd)
         eng = model.eval().engine()
@@ -92,7 +112,7 @@ def _dp_worker(rank, world, port, q):
         xs, _ = synth_windows(101, D, 11)
         sc = P.score_sharded(model, xs, 0, 1, nap=True)
         if rank == 0:
-            q.put(dict(losses=losses, sd=trained,
+            q.put(dict(losses=losses, sd=trained, peer_ok=peer_ok, peer_err=peer_err,
                        nap=sc["nap"].cpu(), sap=sc["sap"].cpu()))
     finally:
         dist.destroy_process_group()
@@ -117,6 +137,8 @@ def test_two_gpu_data_parallel_equals_one_gpu_on_the_concatenated_batch():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    assert got["peer_ok"], "the NVLink peer-memory exchange did not come up on this box"
+    assert got["peer_err"] < 1e-14
     D, btl, nl = 128, 100, 5
     cfg = argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision="fp32")
     x, _ = synth_windows(96, D, 9, anomaly_rate=0.0)
