@@ -349,8 +349,9 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
     model = get_model(cfg)
     model.load_state_dict(synth_state_dict(D, BTL, NL, 0, enc_out=2 * BTL if vib else None))
     opt = Adam(model.parameters(), lr=1e-3)
+    st = None
     if world > 1:
-        T.set_data_parallel(model)
+        st = T.set_data_parallel(model)
     eng = types.SimpleNamespace(model=model, optimizer=opt, config=cfg)
     xh, _ = synth_windows(batch, D, 1234 + int(os.environ.get("RANK", "0")), anomaly_rate=0.0)
     xh = xh.pin_memory()
@@ -396,8 +397,11 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
             "hbm_floor_ms": step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3, "frac_of_hbm_floor": step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3 / ms_dev,
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
                     "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16", "f16f8": "tcgen05 f16x3 split"}[precision],
-            "graph": True, "collectives": None if world == 1 else
-            "library-owned communicator: BatchNorm statistics all-reduced inside the captured step, flat gradient once per step"}
+            "graph": True, "collectives": None if world == 1 else {
+                "bn_statistics": "one-kernel NVLink peer-memory exchange per BatchNorm layer and direction (csrc/peer.cu)" if getattr(st, "peer", False)
+                else "ncclAllReduce per BatchNorm layer and direction",
+                "gradients": "two NCCL all-reduces inside the captured step (decoder bucket overlaps the encoder backward)"
+                if getattr(st, "grads_in_step", False) else "one flat NCCL all-reduce after the step"}}
 
 
 def bench_stream(eng, batches=(1, 8, 10, 64), calls=400, warm=60):
