@@ -230,6 +230,9 @@ def timed_nap_fit(eng, xtr_dev, world):
     fit = eng.nap_fit(xtr_dev, 0, NL + 1, distributed=world > 1, phases=ph)
     torch.cuda.synchronize()
     ph["total_s"] = time.perf_counter() - t0
+    ph["factor"] = fit["factor"]
+    ph["triangular_rows"] = int(fit["tri_rows"])
+    ph["rows_K"] = int(fit["vt"].shape[0])
     return fit, ph
 
 

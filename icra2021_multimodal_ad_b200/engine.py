@@ -261,7 +261,7 @@ class Engine:
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
                 batch_rows: int = 16384, distributed: Optional[bool] = None,
-                restandardize: bool = True, factor: str = "hybrid", phases: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                restandardize: bool = True, factor: str = "hybrid", phases: Optional[dict] = None, tau: float = 1e-3) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
@@ -310,7 +310,7 @@ class Engine:
                 check(lib().mmad_tri_unpack(tri.data_ptr(), dsel, gram.data_ptr(), _stream()))
             del tri
         mark("exchange_s")
-        fit = nap_fit_from_stats(mu, gram, N, factor=factor)
+        fit = nap_fit_from_stats(mu, gram, N, factor=factor, tau=tau)
         del gram
         mark("eig_factor_s")
         self.nap_set_fit(lo, hi, fit["mu"], fit["vt"], fit["var"], fit["mu2"])
