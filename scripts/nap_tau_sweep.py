@@ -22,7 +22,7 @@ y = yte.numpy().astype(bool)
 truth = RO.nap_score_fp64(RO.concat_diffs(RO.get_diffs(xtr, sd)), RO.concat_diffs(RO.get_diffs(xte, sd)))
 ref = g["nap"]["score"].numpy().astype(np.float64)
 print("reference: err %.3f rho %.4f auroc %.4f" % (np.median(np.abs(ref - truth) / truth), spearmanr(ref, truth).correlation, g["nap"]["metrics"][0]))
-for prec in ("f16x3", "fp32"):
+for prec in (() if os.environ.get("ONLY_C") else ("f16x3", "fp32")):
     m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=prec)).eval()
     m.load_state_dict(sd)
     eng = m.engine()
@@ -43,7 +43,7 @@ xf = xs.repeat(8, 1)
 xf = (xf + 1e-3 * torch.randn(xf.shape, generator=torch.Generator().manual_seed(0))).clamp_(0, 1).cuda()
 xb, _ = synth_windows(8192, D, 1236)
 xb = xb.repeat(10, 1)[:75776].contiguous().cuda()
-for tau in (1e-2, 1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 0.0):
+for tau in (() if os.environ.get("ONLY_C") else (1e-2, 1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 0.0)):
     fit = eng.nap_fit(xf, 0, nl + 1, distributed=False, factor="hybrid", tau=tau)
     for _ in range(3):
         eng.score(xb, 0, nl + 1, nap=True)
@@ -55,3 +55,25 @@ for tau in (1e-2, 1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 0.0):
     e1.record(); torch.cuda.synchronize()
     lam = None
     print("bench model tau %.0e: triangular rows %d / %d  %.2f ms/step" % (tau, fit["tri_rows"], fit["vt"].shape[0], e0.elapsed_time(e1) / 5), flush=True)
+
+# (c) the protocol on bench.py's TRAINED model: oracle fp32 NAP (the reference's algorithm) and the fp64 value on the oracle's diffs
+xtr2, _ = synth_windows(6144, D, 41, anomaly_rate=0.0)
+xte2, yte2 = synth_windows(512, D, 43, anomaly_rate=0.15)
+y2 = yte2.numpy().astype(bool)
+dtr, dte = RO.get_diffs(xtr2, sdb), RO.get_diffs(xte2, sdb)
+ctr, cte = RO.concat_diffs(dtr), RO.concat_diffs(dte)
+truth2 = RO.nap_score_fp64(ctr, cte)
+ref2 = RO.NapFit(ctr).score(cte).astype(np.float64)
+print("trained model, oracle (reference algorithm, fp32): err %.3f rho %.4f auroc %.4f | fp64 auroc %.4f" % (
+    np.median(np.abs(ref2 - truth2) / truth2), spearmanr(ref2, truth2).correlation, M.get_auc_roc(ref2.astype(np.float32), y2),
+    M.get_auc_roc(truth2.astype(np.float32), y2)), flush=True)
+for prec in ("f16x3", "fp32"):
+    m = get_model(argparse.Namespace(input_size=D, btl_size=btl, n_layers=nl, gpu_id=0, precision=prec)).eval()
+    m.load_state_dict(sdb)
+    eng = m.engine()
+    for factor, tau in (("hybrid", 1e-3), ("hybrid", 1e-5), ("hybrid", 1e-6), ("triangular", 0.0), ("eigen", 0.0)):
+        fit = eng.nap_fit(xtr2.cuda(), 0, nl + 1, distributed=False, factor=factor, tau=tau)
+        new = eng.score(xte2.cuda(), 0, nl + 1, base=False, sap=False, nap=True)["nap"].cpu().numpy().astype(np.float64)
+        print("trained %s %s tau %.0e: triangular rows %d / %d  err %.3f rho %.4f auroc %.4f" % (
+            prec, factor, tau, fit["tri_rows"], fit["vt"].shape[0], np.median(np.abs(new - truth2) / truth2),
+            spearmanr(new, truth2).correlation, M.get_auc_roc(new.astype(np.float32), y2)), flush=True)
