@@ -261,7 +261,7 @@ class Engine:
 
     def nap_fit(self, x_train: torch.Tensor, lo: int = 0, hi: Optional[int] = None, group=None,
                 batch_rows: int = 16384, distributed: Optional[bool] = None,
-                restandardize: bool = True, factor: str = "hybrid", phases: Optional[dict] = None, tau: float = 1e-3) -> Dict[str, torch.Tensor]:
+                restandardize: bool = True, factor: str = "hybrid", phases: Optional[dict] = None, tau: float = 1e-5) -> Dict[str, torch.Tensor]:
         """utils/normalize.py:47-70 + 20-34 on device, from statistics instead of an SVD of the
         N x D' matrix:  mu = mean(d);  G = (d-mu)^T (d-mu)  (fp64)  = V diag(lambda) V^T;
         var_j = lambda_j / (N-1)  (== diag(np.cov) of the rotated data); K = min(N, D').
@@ -360,7 +360,7 @@ class Engine:
         self.nap_fit_state = {k: st[k] for k in ("mu", "vt", "var", "mu2", "n", "factor", "tri_rows", "lo", "hi", "precision")}
 
 
-def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "hybrid", tau: float = 1e-3) -> Dict[str, torch.Tensor]:
+def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, factor: str = "hybrid", tau: float = 1e-5) -> Dict[str, torch.Tensor]:
     """Eigendecomposition of the centred Gram matrix (fp64, cuSOLVER syevd through
     torch.linalg.eigh -- a library call, not on the hot path) -> (mu, V^T, var, mu2).
 
@@ -370,13 +370,17 @@ def nap_fit_from_stats(mu: torch.Tensor, gram: torch.Tensor, n_total: int, facto
     triangular factor R of the whitening matrix diag(var^-1/2) V^T = Q R (fp64 Householder QR): half of R is
     zero, so the scoring GEMM does half the products.  Rows are normalised to unit max (the scale goes into
     ``var``) so they split cleanly into fp16 pairs.
-    factor="hybrid" (default): triangular factor of the WELL-CONDITIONED part of the spectrum (singular values
-    >= tau * the largest) followed by the plain eigenvector rows of the weak directions.  Every row of a triangular
-    factor carries the gain of the weakest direction it spans, so on a rank-deficient selection (all layers, SURVEY
-    F5: ~770 of 5482 directions at the fp32 noise floor) rounding noise of size eps * |d| / sigma_min lands in EVERY
-    output; the eigenvector form confines it to the weak outputs.  Measured at D = 1728, all layers (rank agreement
-    with the fp64 value): eigen 0.97, triangular 0.86, reference 0.97.  Well-conditioned selections have no weak
-    part and keep the full triangular factor (half the MMA work)."""
+    factor="hybrid" (default): triangular factor of the part of the spectrum ABOVE the rounding-noise floor (singular
+    values >= tau * the largest, tau = 1e-5) followed by the plain eigenvector rows of the directions below it.  Every
+    row of a triangular factor carries the gain of the weakest direction it spans, so on a rank-deficient selection
+    (all layers, SURVEY F5: 770 of the 5482 singular values of a random-init model, 1570 of a trained one, sit at the
+    fp32 noise floor, 1e-8 of the largest) the noise-floor directions' gain lands in EVERY output; the eigenvector form
+    confines it to their own outputs, whose variance the Standardizer refit then normalises like the reference does.
+    Measured at D = 1728, all layers, f16x3 (scripts/nap_tau_sweep.py; rank agreement with the fp64 value / AUROC):
+    reference golden model -- reference 0.974 / 0.760, eigen = hybrid at every tau in [1e-5, 1e-2] 0.970 / 0.755,
+    triangular 0.861 / 0.777; trained model -- reference algorithm 0.954 / 0.794, eigen = hybrid 0.943 / 0.795,
+    triangular 0.925 / 0.775.  Well-conditioned selections have nothing below the floor and keep the full triangular
+    factor (half the MMA work)."""
     lam, V = torch.linalg.eigh(gram)            # ascending
     # near-null directions (SURVEY F5) can come out slightly negative; floor at fp64 resolution of the
     # largest eigenvalue so that var stays positive like the reference's np.cov diagonal
