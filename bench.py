@@ -239,7 +239,7 @@ def timed_nap_fit(eng, xtr_dev, world):
 # ---------------------------------------------------------------------------------------
 # scoring measurement of one precision mode
 # ---------------------------------------------------------------------------------------
-def measure_scoring(eng, precision, x_dev, x_host_np, want_nap, steps, warmup, world, dev, local, L, B, detailed):
+def measure_scoring(eng, precision, x_dev, x_host_np, want_nap, steps, warmup, world, dev, local, L, B, detailed, nap_work=0.5):
     import torch.distributed as dist
     from icra2021_multimodal_ad_b200 import _lib
 
@@ -306,7 +306,7 @@ def measure_scoring(eng, precision, x_dev, x_host_np, want_nap, steps, warmup, w
         # tensor work per product in fp16-pass units: f16x3 three fp16 MMAs; f16f8 one fp16 MMA + one fp8 MMA over twice the
         # contraction length at twice the rate (= one more unit); the triangular NAP factor executes half of the rotation
         mma_passes = {"f16x3": 3, "f16f8": 2}.get(precision, 1)
-        executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT / 2 if want_nap else 0))
+        executed_per_window = mma_passes * (FLOP_SAP + (FLOP_NAP_ROT * nap_work if want_nap else 0))
         executed_tf = value / world * executed_per_window / 1e12 if precision != "fp32" else None
         res["roofline"] = {
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -315,10 +315,12 @@ def measure_scoring(eng, precision, x_dev, x_host_np, want_nap, steps, warmup, w
             "launches_timed": int(gemm_launches), "gemm_share_of_step": gemm_ms / psteps / (ms / steps),
             "executed_mma_tflops": executed_tf, "executed_frac_of_peak": executed_tf / peak_tf if executed_tf and peak_tf else None,
             "mode_cap_frac": {"f16x3": 1 / 3, "f16f8": 1 / 2}.get(precision),
+            "nap_rotation_work_executed": nap_work,
             "note": "achieved counts ONE product per MAC of the reference's dense algorithm (SURVEY 8d); f16x3 issues 3 fp16 MMAs per "
                     "product, so dense work is capped at peak/3 (f16f8: one fp16 + one double-length fp8 MMA = 2 units, cap peak/2); the "
-                    "triangular NAP factor executes half of the rotation, which is why achieved may exceed the dense cap; "
-                    "executed_frac_of_peak is the share of the tensor pipe's peak actually issued"}
+                    "triangular block of the NAP factor skips the products left of its diagonal (nap_rotation_work_executed = share of "
+                    "the dense rotation actually issued), which is why achieved may exceed the dense cap; executed_frac_of_peak is the "
+                    "share of the tensor pipe's peak actually issued"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host input, scores back on host) ----
     for _ in range(max(1, warmup // 2)):
@@ -623,7 +625,11 @@ def main():
     x_dev = x_host.to(dev)
     xh_np = x_host.numpy()
 
-    primary, out = measure_scoring(eng, precision, x_dev, xh_np, want_nap, args.steps, args.warmup, world, dev, local, L, B, True)
+    def nap_work(ph):      # share of the dense D' x K rotation the tensor cores execute: rows of the triangular block skip k < row
+        t, k = ph.get("triangular_rows", 0), max(ph.get("rows_K", 1), 1)
+        return (t * (1.0 - t / (2.0 * sum(widths(D)))) + (k - t)) / k
+    primary, out = measure_scoring(eng, precision, x_dev, xh_np, want_nap, args.steps, args.warmup, world, dev, local, L, B, True,
+                                   nap_work(fit_ph) if want_nap else 0.5)
 
     extras = {}
 
