@@ -602,7 +602,12 @@ def main():
     precision = args.precision
     if precision == "auto":
         precision = os.environ.get("MMAD_DEFAULT_PRECISION", DEFAULT_PRECISION)
-    sd = trained_state_dict(local)              # identical on every rank (same seeds, deterministic kernels)
+    sd = trained_state_dict(local)
+    if world > 1:       # every rank scores THE SAME model (a checkpoint in real use): the train step's split-K atomics are not
+        for k in sd:    # bit-reproducible across GPUs, and 20 Adam steps turn that into 1e-3 differences of single weights
+            t = sd[k].to(dev)
+            dist.broadcast(t, src=0)
+            sd[k] = t.cpu()
     cfg = argparse.Namespace(input_size=D, btl_size=BTL, n_layers=NL, gpu_id=local, precision=precision)
     model = get_model(cfg).eval()
     model.load_state_dict(sd)

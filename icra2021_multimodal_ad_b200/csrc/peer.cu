@@ -4,7 +4,8 @@
 // normalised -- 16 forward and 16 backward exchanges of <= 2 x 1408 doubles, strictly serialised with the layer chain.
 // Through ncclAllReduce each of them costs ~15-20 us at 8 ranks (protocol set-up dominates 22 KB), 0.5 ms per step; the step
 // itself is 0.8 ms.  Here every rank owns a buffer that all peers map (cudaIpc), and ONE small kernel per exchange
-//   1. pushes its vector into its slot of EVERY rank's buffer as 8-byte (32 data bits, sequence number) pairs -- an 8-byte
+//   1. pushes its vector into its slot of EVERY rank's buffer (one CTA per destination) as 8-byte (32 data bits, sequence
+//      number) pairs -- an 8-byte
 //      store is single-copy atomic over NVLink, so the flag travels with the data and no fence or separate signal is needed
 //      (the low-latency protocol of collective libraries);
 //   2. polls its own buffer until every rank's pairs carry this exchange's sequence number;
@@ -31,7 +32,8 @@ struct PeerPtrs {
 struct PeerState {
     PeerPtrs p;
     uint2* local = nullptr;
-    unsigned long long* d_seq = nullptr;
+    unsigned long long* d_seq = nullptr;     // [0]: exchange sequence number, [1]: CTA completion counter (as unsigned int)
+    double* d_out = nullptr;                 // sums before they are copied back in place
     bool open = false;
     void* mapped[kPeerMaxWorld] = {nullptr};
 };
@@ -45,26 +47,29 @@ __device__ __forceinline__ void peer_st(uint2* p, uint32_t data, uint32_t seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
 }
 
+// grid = world CTAs: CTA r pushes this rank's vector to rank r; the CTAs then share the polling / summation of the elements.
+// One CTA for everything was push-bound at 8 ranks (45 000 remote 8-byte stores through one SM).
 __global__ void __launch_bounds__(kPeerThreads)
-peer_allreduce_f64_kernel(const PeerPtrs P, double* __restrict__ buf, int count, unsigned long long* __restrict__ seq_ctr) {
-    const unsigned long long seq = *seq_ctr;          // every thread reads it before thread 0 advances it (barrier below)
+peer_allreduce_f64_kernel(const PeerPtrs P, double* __restrict__ buf, double* __restrict__ out, int count,
+                          unsigned long long* __restrict__ seq_ctr, unsigned int* __restrict__ done_ctr) {
+    const unsigned long long seq = *seq_ctr;          // every CTA reads it before the last one to finish advances it
     const uint32_t tag = (uint32_t)seq + 1u;          // never 0 (the buffers start zeroed)
     const size_t set = (size_t)(seq & 1) * P.world * (2 * kPeerMaxDoubles);
     const int world = P.world, rank = P.rank;
-    // 1. push
-    for (int i = threadIdx.x; i < count; i += kPeerThreads) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
-        const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
-        const size_t off = set + (size_t)rank * (2 * kPeerMaxDoubles) + 2 * (size_t)i;
-        for (int r = 0; r < world; ++r) {
-            peer_st(P.buf[r] + off, lo, tag);
-            peer_st(P.buf[r] + off + 1, hi, tag);
+    // 1. push to peer blockIdx.x (one destination per CTA)
+    for (int r = blockIdx.x; r < world; r += gridDim.x) {
+        uint2* dst = P.buf[r] + set + (size_t)rank * (2 * kPeerMaxDoubles);
+        for (int i = threadIdx.x; i < count; i += kPeerThreads) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
+            peer_st(dst + 2 * (size_t)i, (uint32_t)bits, tag);
+            peer_st(dst + 2 * (size_t)i + 1, (uint32_t)(bits >> 32), tag);
         }
     }
-    // 2. + 3. poll the local buffer, add in rank order
+    // 2. + 3. poll the local buffer, add in rank order: elements are dealt round-robin to the CTAs.  The sums go to `out`
+    // (not in place: other CTAs may still be pushing `buf`) and are copied back by the last CTA to finish.
     const uint2* mine = P.buf[rank] + set;
     const long long t0 = clock64();
-    for (int i = threadIdx.x; i < count; i += kPeerThreads) {
+    for (int i = blockIdx.x * kPeerThreads + threadIdx.x; i < count; i += gridDim.x * kPeerThreads) {
         double sum = 0.0;
         for (int r = 0; r < world; ++r) {
             const uint2* q = mine + (size_t)r * (2 * kPeerMaxDoubles) + 2 * (size_t)i;
@@ -79,10 +84,20 @@ peer_allreduce_f64_kernel(const PeerPtrs P, double* __restrict__ buf, int count,
             }
             sum += __longlong_as_double((long long)(((unsigned long long)b.x << 32) | a.x));
         }
-        buf[i] = sum;
+        out[i] = sum;
+    }
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done_ctr, 1u) + 1u == gridDim.x;
+        if (s_last) __threadfence();
     }
     __syncthreads();
-    if (threadIdx.x == 0) *seq_ctr = seq + 1;
+    if (!s_last) return;
+    for (int i = threadIdx.x; i < count; i += kPeerThreads) buf[i] = __ldcg(out + i);
+    __syncthreads();
+    if (threadIdx.x == 0) { *done_ctr = 0; *seq_ctr = seq + 1; }
 }
 
 }  // namespace
@@ -91,7 +106,7 @@ void peer_state_free(void* p) {
     PeerState* S = static_cast<PeerState*>(p);
     if (!S) return;
     for (int r = 0; r < kPeerMaxWorld; ++r) if (S->mapped[r]) cudaIpcCloseMemHandle(S->mapped[r]);
-    cudaFree(S->local); cudaFree(S->d_seq);
+    cudaFree(S->local); cudaFree(S->d_seq); cudaFree(S->d_out);
     delete S;
 }
 
@@ -107,7 +122,8 @@ int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s)
     if (!S || !S->open) { set_error("peer buffers are not open"); return MMAD_E_STATE; }
     if (count <= 0) return MMAD_OK;
     if (count > kPeerMaxDoubles) { set_error("peer all-reduce: %lld doubles > %d", count, kPeerMaxDoubles); return MMAD_E_ARG; }
-    peer_allreduce_f64_kernel<<<1, kPeerThreads, 0, s>>>(S->p, d_buf, (int)count, S->d_seq);
+    peer_allreduce_f64_kernel<<<S->p.world, kPeerThreads, 0, s>>>(S->p, d_buf, S->d_out, (int)count, S->d_seq,
+                                                                  reinterpret_cast<unsigned int*>(S->d_seq + 1));
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
@@ -128,8 +144,9 @@ int mmad_peer_create(mmad_t h, unsigned char* h_handle) {
     const size_t bytes = (size_t)2 * kPeerMaxWorld * (2 * kPeerMaxDoubles) * sizeof(uint2);       // 2 MB
     MMAD_CUDA_OK(cudaMalloc(&S->local, bytes));
     MMAD_CUDA_OK(cudaMemset(S->local, 0, bytes));
-    MMAD_CUDA_OK(cudaMalloc(&S->d_seq, 8));
-    MMAD_CUDA_OK(cudaMemset(S->d_seq, 0, 8));
+    MMAD_CUDA_OK(cudaMalloc(&S->d_seq, 16));
+    MMAD_CUDA_OK(cudaMemset(S->d_seq, 0, 16));
+    MMAD_CUDA_OK(cudaMalloc(&S->d_out, (size_t)kPeerMaxDoubles * 8));
     MMAD_CUDA_OK(cudaDeviceSynchronize());
     cudaIpcMemHandle_t hd;
     MMAD_CUDA_OK(cudaIpcGetMemHandle(&hd, S->local));
