@@ -121,7 +121,7 @@ def train_state(model) -> TrainState:
     return st
 
 
-def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_grads: bool = True, peer: Optional[bool] = None):
+def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_grads: bool = False, peer: Optional[bool] = None):
     """Make BatchNorm batch statistics global over ``group`` (N-GPU data parallel == 1 GPU on the
     concatenated batch); gradients are combined by ``allreduce_gradients``.
 
@@ -134,8 +134,10 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
     strictly serialised with the layer chain) run as one-kernel exchanges over NVLink peer memory (``mmad_peer_*``: every
     rank maps every other rank's buffer through cudaIpc) instead of ncclAllReduce.  Falls back to NCCL if the GPUs cannot
     map each other.
-    overlap_grads (default on): the gradients are all-reduced inside the captured step in two buckets on the second stream,
-    the decoder's while the encoder's backward pass still runs; ``allreduce_gradients`` is then a no-op."""
+    overlap_grads (default off): the gradients are all-reduced inside the captured step in two buckets on the second
+    stream, the decoder's while the encoder's backward pass still runs; ``allreduce_gradients`` is then a no-op.  Measured
+    at B = 256 per GPU (scripts/dp_ablation.py): no better than ONE flat all-reduce after the step at 2 GPUs (0.987 vs
+    0.998 ms) and worse at 8 (1.232 vs 1.168 ms) -- the overlapped collective takes SMs from a chain of 15-us GEMMs."""
     import os
     import torch.distributed as dist
     st = train_state(model)
