@@ -254,11 +254,37 @@ __global__ void __launch_bounds__(kCT) bn_bwd_apply_kernel(const float* __restri
 }
 
 // ---- small-batch single-GPU variants: ONE launch per BatchNorm layer and direction ---------------------------------
-// When one CTA can walk all B rows of its 128 columns (B <= kFusedRows) and no cross-rank exchange sits between the
-// statistics and their use, statistics + apply run in one kernel: pass 1 accumulates (fp64, same order as the two-kernel
-// path: warp w rows w, w+8, ..; cross-warp sum in warp order), pass 2 re-reads the L2-hot rows.  No atomics, no zeroed
-// statistic buffers, 16 launches fewer per step (0.80 -> 0.6x ms at B = 256).
+// When no cross-rank exchange sits between the statistics and their use and the batch is small (B <= kFusedRows), statistics
+// + apply run in one kernel.  A CTA owns only 32 columns and ALL rows (N = 1402 -> 44 CTAs; with 128 columns per CTA the 11
+// CTAs were latency bound and the step got slower): lane = (row within a group of 4) x (float4 column quad), the 8 warps
+// take 32 rows per iteration, 8 iterations' loads in flight.  Pass 1 accumulates in fp64, pass 2 re-reads the L2-hot rows.
+// No atomics, no zeroed statistic buffers, deterministic, 16 launches fewer per step.
 constexpr int kFusedRows = 1024;
+constexpr int kFC = 32;       // columns per CTA
+
+template <int NS>
+__device__ __forceinline__ void fused_col_reduce(const double (&acc)[NS][4], double* sm, double (&tot)[NS]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double v = acc[s][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 8) sm[(warp * NS + s) * kFC + cq * 4 + j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < kFC) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCT / 32; ++w) t += sm[(w * NS + s) * kFC + threadIdx.x];
+            tot[s] = t;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope, float eps,
                                                            float momentum, const float* __restrict__ gamma,
@@ -267,14 +293,14 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
                                                            float* __restrict__ mean_out, float* __restrict__ inv_out,
                                                            float* __restrict__ out, int ldo, __half* __restrict__ oh,
                                                            __half* __restrict__ ol) {
-    __shared__ double sm[(kCT / 32) * 2 * kCB];
-    __shared__ float s_mean[kCB], s_inv[kCB], s_g[kCB], s_b[kCB];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c0 = blockIdx.x * kCB + lane * 4;
+    __shared__ double sm[(kCT / 32) * 2 * kFC];
+    __shared__ float s_mean[kFC], s_inv[kFC], s_g[kFC], s_b[kFC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7, rl = lane >> 3;
+    const int c0 = blockIdx.x * kFC + cq * 4;
     double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
     if (c0 < N) {
-#pragma unroll 4
-        for (int r = warp; r < B; r += kCT / 32) {
+#pragma unroll 8
+        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
             const float4 v = ld4(pre + (size_t)r * ld + c0);
             const float a[4] = {lrelu(v.x, slope), lrelu(v.y, slope), lrelu(v.z, slope), lrelu(v.w, slope)};
 #pragma unroll
@@ -282,9 +308,9 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
         }
     }
     double tot[2];
-    cta_col_reduce<2>(acc, sm, tot);
-    if (threadIdx.x < kCB) {
-        const int c = blockIdx.x * kCB + threadIdx.x;
+    fused_col_reduce<2>(acc, sm, tot);
+    if (threadIdx.x < kFC) {
+        const int c = blockIdx.x * kFC + threadIdx.x;
         float m = 0.f, iv = 0.f, g = 0.f, b = 0.f;
         if (c < N) {
             const double Bg = (double)B;
@@ -309,9 +335,9 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
     if (c0 >= N) return;
     float m[4], iv[4], g[4], b[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { m[j] = s_mean[lane * 4 + j]; iv[j] = s_inv[lane * 4 + j]; g[j] = s_g[lane * 4 + j]; b[j] = s_b[lane * 4 + j]; }
-#pragma unroll 4
-    for (int r = warp; r < B; r += kCT / 32) {
+    for (int j = 0; j < 4; ++j) { m[j] = s_mean[cq * 4 + j]; iv[j] = s_inv[cq * 4 + j]; g[j] = s_g[cq * 4 + j]; b[j] = s_b[cq * 4 + j]; }
+#pragma unroll 8
+    for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
         const float4 v = ld4(pre + (size_t)r * ld + c0);
         const float p4[4] = {v.x, v.y, v.z, v.w};
         float o[4];
@@ -329,10 +355,10 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
                                                            __half* __restrict__ gh, __half* __restrict__ gl, float twin_scale,
                                                            float* __restrict__ gb, float* __restrict__ ggamma,
                                                            float* __restrict__ gbeta) {
-    __shared__ double sm[(kCT / 32) * 2 * kCB];
-    __shared__ float s_a1[kCB], s_a2[kCB];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c0 = blockIdx.x * kCB + lane * 4;
+    __shared__ double sm[(kCT / 32) * 2 * kFC];
+    __shared__ float s_a1[kFC], s_a2[kFC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7, rl = lane >> 3;
+    const int c0 = blockIdx.x * kFC + cq * 4;
     float m[4], iv[4], k[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -344,7 +370,7 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
     double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
     if (c0 < N) {
 #pragma unroll 4
-        for (int r = warp; r < B; r += kCT / 32) {
+        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
             const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
             const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
             const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
@@ -358,9 +384,9 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
         }
     }
     double tot[2];
-    cta_col_reduce<2>(acc, sm, tot);
-    if (threadIdx.x < kCB) {
-        const int c = blockIdx.x * kCB + threadIdx.x;
+    fused_col_reduce<2>(acc, sm, tot);
+    if (threadIdx.x < kFC) {
+        const int c = blockIdx.x * kFC + threadIdx.x;
         float a1 = 0.f, a2 = 0.f;
         if (c < N) {
             a1 = (float)(tot[0] / (double)B);
@@ -375,9 +401,9 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
     if (c0 < N) {
         float a1[4], a2[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a1[j] = s_a1[lane * 4 + j]; a2[j] = s_a2[lane * 4 + j]; }
+        for (int j = 0; j < 4; ++j) { a1[j] = s_a1[cq * 4 + j]; a2[j] = s_a2[cq * 4 + j]; }
 #pragma unroll 4
-        for (int r = warp; r < B; r += kCT / 32) {
+        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
             const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
             const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
             const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
@@ -396,9 +422,9 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
         }
     }
     double tot2[1];
-    cta_col_reduce<1>(acc2, sm, tot2);
-    const int c = blockIdx.x * kCB + threadIdx.x;
-    if (threadIdx.x < kCB && c < N) gb[c] = (float)tot2[0];
+    fused_col_reduce<1>(acc2, sm, tot2);
+    const int c = blockIdx.x * kFC + threadIdx.x;
+    if (threadIdx.x < kFC && c < N) gb[c] = (float)tot2[0];
 }
 
 // gb[c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer; gb zeroed by the caller)
@@ -802,8 +828,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* mean = (float*)(ws + p.mean[m][i]);
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
-                if (!dist && B <= kFusedRows) {       // one launch: a CTA walks all rows of its 128 columns
-                    bn_fwd_fused_kernel<<<(N + kCB - 1) / kCB, kCT, 0, s>>>(pre, Np, B, N, slope, d.bn_eps, bn_momentum, L.gamma, L.beta,
+                if (!dist && B <= kFusedRows) {       // one launch: a CTA walks all rows of its 32 columns
+                    bn_fwd_fused_kernel<<<(N + kFC - 1) / kFC, kCT, 0, s>>>(pre, Np, B, N, slope, d.bn_eps, bn_momentum, L.gamma, L.beta,
                                                                             L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
                                                                             tc ? nullptr : out, Np, oh, ol);
                     MMAD_LAUNCHED();
@@ -890,7 +916,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
             if (!dist && B <= kFusedRows) {
-                bn_bwd_fused_kernel<<<(r.N + kCB - 1) / kCB, kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma,
+                bn_bwd_fused_kernel<<<(r.N + kFC - 1) / kFC, kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma,
                                                                           tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta);
                 MMAD_LAUNCHED();
             } else {
