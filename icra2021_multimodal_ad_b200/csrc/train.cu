@@ -253,180 +253,6 @@ __global__ void __launch_bounds__(kCT) bn_bwd_apply_kernel(const float* __restri
     }
 }
 
-// ---- small-batch single-GPU variants: ONE launch per BatchNorm layer and direction ---------------------------------
-// When no cross-rank exchange sits between the statistics and their use and the batch is small (B <= kFusedRows), statistics
-// + apply run in one kernel.  A CTA owns only 32 columns and ALL rows (N = 1402 -> 44 CTAs; with 128 columns per CTA the 11
-// CTAs were latency bound and the step got slower): lane = (row within a group of 4) x (float4 column quad), the 8 warps
-// take 32 rows per iteration, 8 iterations' loads in flight.  Pass 1 accumulates in fp64, pass 2 re-reads the L2-hot rows.
-// No atomics, no zeroed statistic buffers, deterministic, 16 launches fewer per step.
-constexpr int kFusedRows = 1024;
-constexpr int kFC = 32;       // columns per CTA
-
-template <int NS>
-__device__ __forceinline__ void fused_col_reduce(const double (&acc)[NS][4], double* sm, double (&tot)[NS]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7;
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double v = acc[s][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 8) sm[(warp * NS + s) * kFC + cq * 4 + j] = v;
-        }
-    __syncthreads();
-    if (threadIdx.x < kFC) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < kCT / 32; ++w) t += sm[(w * NS + s) * kFC + threadIdx.x];
-            tot[s] = t;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope, float eps,
-                                                           float momentum, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ run_mean,
-                                                           float* __restrict__ run_var, long long* __restrict__ nbt,
-                                                           float* __restrict__ mean_out, float* __restrict__ inv_out,
-                                                           float* __restrict__ out, int ldo, __half* __restrict__ oh,
-                                                           __half* __restrict__ ol) {
-    __shared__ double sm[(kCT / 32) * 2 * kFC];
-    __shared__ float s_mean[kFC], s_inv[kFC], s_g[kFC], s_b[kFC];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7, rl = lane >> 3;
-    const int c0 = blockIdx.x * kFC + cq * 4;
-    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
-    if (c0 < N) {
-#pragma unroll 8
-        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
-            const float4 v = ld4(pre + (size_t)r * ld + c0);
-            const float a[4] = {lrelu(v.x, slope), lrelu(v.y, slope), lrelu(v.z, slope), lrelu(v.w, slope)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { acc[0][j] += (double)a[j]; acc[1][j] = fma((double)a[j], (double)a[j], acc[1][j]); }
-        }
-    }
-    double tot[2];
-    fused_col_reduce<2>(acc, sm, tot);
-    if (threadIdx.x < kFC) {
-        const int c = blockIdx.x * kFC + threadIdx.x;
-        float m = 0.f, iv = 0.f, g = 0.f, b = 0.f;
-        if (c < N) {
-            const double Bg = (double)B;
-            const double md = tot[0] / Bg;
-            double var_b = tot[1] / Bg - md * md;
-            if (var_b < 0.0) var_b = 0.0;
-            m = (float)md;
-            iv = (float)(1.0 / sqrt(var_b + (double)eps));
-            g = gamma[c]; b = beta[c];
-            mean_out[c] = m;
-            inv_out[c] = iv;
-            if (run_mean) {
-                const double unb = Bg > 1.0 ? var_b * (Bg / (Bg - 1.0)) : var_b;
-                run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
-                run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
-            }
-            if (c == 0 && nbt) *nbt += 1;
-        }
-        s_mean[threadIdx.x] = m; s_inv[threadIdx.x] = iv; s_g[threadIdx.x] = g; s_b[threadIdx.x] = b;
-    }
-    __syncthreads();
-    if (c0 >= N) return;
-    float m[4], iv[4], g[4], b[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { m[j] = s_mean[cq * 4 + j]; iv[j] = s_inv[cq * 4 + j]; g[j] = s_g[cq * 4 + j]; b[j] = s_b[cq * 4 + j]; }
-#pragma unroll 8
-    for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
-        const float4 v = ld4(pre + (size_t)r * ld + c0);
-        const float p4[4] = {v.x, v.y, v.z, v.w};
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = (c0 + j < N) ? fmaf((lrelu(p4[j], slope) - m[j]) * iv[j], g[j], b[j]) : 0.f;
-        if (out) *reinterpret_cast<float4*>(out + (size_t)r * ldo + c0) = make_float4(o[0], o[1], o[2], o[3]);
-        if (oh) split4_store(o, 1.f, oh, ol, (size_t)r * ldo + c0);
-    }
-}
-
-__global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre,
-                                                           int ld, int B, int N, float slope, float gscale,
-                                                           const float* __restrict__ mean, const float* __restrict__ inv,
-                                                           const float* __restrict__ gamma, float* __restrict__ gpre, int ldo,
-                                                           __half* __restrict__ gh, __half* __restrict__ gl, float twin_scale,
-                                                           float* __restrict__ gb, float* __restrict__ ggamma,
-                                                           float* __restrict__ gbeta) {
-    __shared__ double sm[(kCT / 32) * 2 * kFC];
-    __shared__ float s_a1[kFC], s_a2[kFC];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = lane & 7, rl = lane >> 3;
-    const int c0 = blockIdx.x * kFC + cq * 4;
-    float m[4], iv[4], k[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool ok = c0 + j < N;
-        m[j] = ok ? mean[c0 + j] : 0.f;
-        iv[j] = ok ? inv[c0 + j] : 0.f;
-        k[j] = ok ? gamma[c0 + j] * iv[j] : 0.f;
-    }
-    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
-    if (c0 < N) {
-#pragma unroll 4
-        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
-            const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
-            const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
-            const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
-            const float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xh = (lrelu(pv[j], slope) - m[j]) * iv[j];
-                acc[0][j] += (double)gv[j];
-                acc[1][j] = fma((double)gv[j], (double)xh, acc[1][j]);
-            }
-        }
-    }
-    double tot[2];
-    fused_col_reduce<2>(acc, sm, tot);
-    if (threadIdx.x < kFC) {
-        const int c = blockIdx.x * kFC + threadIdx.x;
-        float a1 = 0.f, a2 = 0.f;
-        if (c < N) {
-            a1 = (float)(tot[0] / (double)B);
-            a2 = (float)(tot[1] / (double)B);
-            gbeta[c] = (float)tot[0];
-            ggamma[c] = (float)tot[1];
-        }
-        s_a1[threadIdx.x] = a1; s_a2[threadIdx.x] = a2;
-    }
-    __syncthreads();             // also: every warp is done with sm before it is reused below
-    double acc2[1][4] = {{0.0, 0.0, 0.0, 0.0}};
-    if (c0 < N) {
-        float a1[4], a2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { a1[j] = s_a1[cq * 4 + j]; a2[j] = s_a2[cq * 4 + j]; }
-#pragma unroll 4
-        for (int r = warp * 4 + rl; r < B; r += kCT / 8) {
-            const float4 gv4 = ld4(g + (size_t)r * ldg + c0);
-            const float4 pv4 = ld4(pre + (size_t)r * ld + c0);
-            const float gv[4] = {gv4.x * gscale, gv4.y * gscale, gv4.z * gscale, gv4.w * gscale};
-            const float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-            float ga[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xh = (lrelu(pv[j], slope) - m[j]) * iv[j];
-                float t = k[j] * (gv[j] - a1[j] - xh * a2[j]);
-                t = pv[j] > 0.f ? t : t * slope;
-                ga[j] = (c0 + j < N) ? t : 0.f;
-                acc2[0][j] += (double)ga[j];
-            }
-            if (gpre) *reinterpret_cast<float4*>(gpre + (size_t)r * ldo + c0) = make_float4(ga[0], ga[1], ga[2], ga[3]);
-            if (gh) split4_store(ga, twin_scale, gh, gl, (size_t)r * ldo + c0);
-        }
-    }
-    double tot2[1];
-    fused_col_reduce<1>(acc2, sm, tot2);
-    const int c = blockIdx.x * kFC + threadIdx.x;
-    if (threadIdx.x < kFC && c < N) gb[c] = (float)tot2[0];
-}
-
 // gb[c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer; gb zeroed by the caller)
 __global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale,
                                                              float* __restrict__ gb, int RS) {
@@ -828,23 +654,16 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* mean = (float*)(ws + p.mean[m][i]);
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
-                if (!dist && B <= kFusedRows) {       // one launch: a CTA walks all rows of its 32 columns
-                    bn_fwd_fused_kernel<<<(N + kFC - 1) / kFC, kCT, 0, s>>>(pre, Np, B, N, slope, d.bn_eps, bn_momentum, L.gamma, L.beta,
-                                                                            L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
-                                                                            tc ? nullptr : out, Np, oh, ol);
-                    MMAD_LAUNCHED();
-                } else {
-                    bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
-                    MMAD_LAUNCHED();
-                    if (dist) {
-                        rc = stats_allreduce(st, 2LL * Np);
-                        if (rc) return rc;
-                    }
-                    bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
-                                                                       L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
-                                                                       tc ? nullptr : out, Np, oh, ol, row_slab(B));
-                    MMAD_LAUNCHED();
+                bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
+                MMAD_LAUNCHED();
+                if (dist) {
+                    rc = stats_allreduce(st, 2LL * Np);
+                    if (rc) return rc;
                 }
+                bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
+                                                                   L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
+                                                                   tc ? nullptr : out, Np, oh, ol, row_slab(B));
+                MMAD_LAUNCHED();
                 cur = Mat{out, oh, ol, Np};
             } else {
                 cur = Mat{pre, oh, ol, Np};
@@ -915,25 +734,19 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             __half* goh = tc ? (__half*)(ws + p.gth[idx]) : nullptr;
             __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
-            if (!dist && B <= kFusedRows) {
-                bn_bwd_fused_kernel<<<(r.N + kFC - 1) / kFC, kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma,
-                                                                          tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta);
+            bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
+                                                                  L.gb, row_slab(B));
+            MMAD_LAUNCHED();
+            if (dist) {    // parameter gradients from the LOCAL sums, then the statistics are combined
+                bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
                 MMAD_LAUNCHED();
-            } else {
-                bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
-                                                                      L.gb, row_slab(B));
-                MMAD_LAUNCHED();
-                if (dist) {    // parameter gradients from the LOCAL sums, then the statistics are combined
-                    bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
-                    MMAD_LAUNCHED();
-                    int rc = stats_allreduce(stb, 2LL * r.Np);
-                    if (rc) return rc;
-                }
-                bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
-                                                                     r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
-                                                                     L.gbeta, dist ? 0 : 1, row_slab(B));
-                MMAD_LAUNCHED();
+                int rc = stats_allreduce(stb, 2LL * r.Np);
+                if (rc) return rc;
             }
+            bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
+                                                                 r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
+                                                                 L.gbeta, dist ? 0 : 1, row_slab(B));
+            MMAD_LAUNCHED();
             gpre = Mat{go, goh, gol, p.maxNp};
             gi ^= 1;
             gemm_scale = 1.f;
