@@ -52,7 +52,8 @@ struct StPlan {
     float* xf; float* fbase;
     size_t bufsz;
     int ld;
-    float* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2
+    uint2* partial;    // [n_diffs][grid][ST_MAX_ROWS] per-CTA row sums of d^2 as (value, sequence) pairs
+    int wmax4;         // largest weight slice of a CTA (float4): the pair protocol keeps TWO slices in flight
     int nact[MMAD_MAX_LAYERS + 2];   // CTAs that own columns of diff l
     StStep step[ST_MAX_STEPS];
 };
@@ -107,15 +108,13 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 // All polls are bounded: a protocol bug traps instead of hanging the device.
 template <int NB, bool LL>
 __global__ void __launch_bounds__(ST_THREADS, 1)
-stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, float* out_host,
-                    unsigned long long* flag_host, unsigned long long seq, unsigned long long* bar, unsigned long long bar_base,
-                    unsigned long long bar2_base, unsigned long long* dbg) {
+stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_src, int rows, uint2* out_host,
+                    unsigned long long seq, unsigned long long* bar, unsigned long long bar2_base, unsigned long long* dbg) {
     extern __shared__ __align__(16) float st_smem[];
     __shared__ float s_red[ST_KQ][NB][ST_CPC];
     __shared__ float s_sq[NB][ST_CPC];
     __shared__ float s_vec[3][ST_CPC];        // bias, BN scale, BN shift of this CTA's columns
     __shared__ float s_fin[MMAD_MAX_LAYERS + 2][ST_MAX_ROWS];
-    __shared__ int s_last;
     auto stamp = [&](int i) {                 // MMAD_STREAM_DEBUG: CTA 0's wall clock at the phase boundaries
         if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
             unsigned long long t;
@@ -129,7 +128,10 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     const int n_steps = P->n_steps;
     const float slope = P->slope;
     const uint32_t seq32 = (uint32_t)seq;
-    unsigned long long arrivals = bar2_base;      // barrier protocol: bar[1] counts the arrivals of every barrier of every call
+    unsigned long long arrivals = bar2_base;      // barrier protocol: *bar counts the arrivals of every barrier of every call
+    // pair protocol: two weight slices in flight (slice s in buffer s & 1, the activation tile behind both); barrier protocol:
+    // one slice, the activation tile right behind it
+    const int wmax4 = P->wmax4;
 
     auto prefetch_weights = [&](int s) -> uint32_t {    // cp.async of this CTA's weight slice; returns its float4 extent
         const StStep& st = P->step[s];
@@ -137,7 +139,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
         const int n4 = ncols * st.K4;
         const float4* src = reinterpret_cast<const float4*>(st.W) + (size_t)c_lo * st.K4;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st_smem);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st_smem) + (LL ? (uint32_t)(s & 1) * (uint32_t)wmax4 * 16u : 0u);
         for (int i = tid; i < n4; i += ST_THREADS) st_cp16(dst + i * 16, src + i);
         st_cp_commit();
         return (uint32_t)(st.cpc * st.K4);
@@ -152,6 +154,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         return v ? __ldg(v + c) : 0.f;
     };
     uint32_t w4 = prefetch_weights(0);
+    if (LL && n_steps > 1) prefetch_weights(1);
     float vpre = prefetch_vec(0);
 
     // ---- stage the input rows from the caller's mapped host buffer (once, by the whole grid) ----
@@ -172,7 +175,7 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
             xd[(size_t)r * ld4 + c] = __ldcv(xs + i);
         }
         arrivals += grid;
-        grid_barrier(bar + 1, arrivals);
+        grid_barrier(bar, arrivals);
     }
     stamp(1);
 
@@ -182,8 +185,8 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
         const int c_lo = cta * st.cpc;
         int ncols = st.N - c_lo; if (ncols > st.cpc) ncols = st.cpc; if (ncols < 0) ncols = 0;
         if (tid < 3 * ST_CPC) s_vec[tid / ST_CPC][tid % ST_CPC] = vpre;      // visible after the __syncthreads below
-        const float4* wsm = reinterpret_cast<const float4*>(st_smem);
-        float* asm_f = st_smem + 4 * (size_t)w4;
+        const float4* wsm = reinterpret_cast<const float4*>(st_smem) + (LL ? (size_t)(s & 1) * wmax4 : 0);
+        float* asm_f = st_smem + 4 * (size_t)(LL ? 2 * wmax4 : w4);
         const float4* asm4 = reinterpret_cast<const float4*>(asm_f);
         const int cg = warp & (ST_CG - 1), kq = warp >> 2;
         const int cl0 = cg * ST_CW;
@@ -242,7 +245,10 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
                 }
                 st_cp_commit();
             }
-            st_cp_wait_all();                 // this CTA's weight slice (issued one step earlier)
+            // this CTA's weight slice: issued one step earlier (barrier protocol) / two steps earlier, with the next one still
+            // allowed in flight (pair protocol)
+            if (LL && s + 1 < n_steps) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else st_cp_wait_all();
             __syncthreads();
             if (nj > 0) {
                 float acc[NB][ST_CW];
@@ -307,40 +313,49 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
             if (st.diff >= 0 && tid < nb) {
                 float t = 0.f;
                 for (int cl = 0; cl < ncols; ++cl) t += s_sq[tid][cl];
-                P->partial[((size_t)st.diff * grid + cta) * ST_MAX_ROWS + r0 + tid] = t;
+                st_pair(P->partial + ((size_t)st.diff * grid + cta) * ST_MAX_ROWS + r0 + tid, t, seq32);
             }
         }
         if (s + 1 < n_steps) {
             __syncthreads();            // everybody is done reading the current slice and activation tile
-            w4 = prefetch_weights(s + 1);          // travels while this CTA waits for the others
+            if constexpr (LL) {
+                if (s + 2 < n_steps) prefetch_weights(s + 2);     // into the buffer this step just released
+            } else {
+                w4 = prefetch_weights(s + 1);      // travels while this CTA waits for the others
+            }
             vpre = prefetch_vec(s + 1);
             if constexpr (!LL) {
                 arrivals += grid;
-                grid_barrier(bar + 1, arrivals);
+                grid_barrier(bar, arrivals);
             }
         }
         stamp(2 + s);
     }
 
-    // ---- the last CTA to finish adds the per-CTA partial sums (fixed order) and rings the doorbell ----
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(bar, 1ULL);
-        s_last = (old + 1 == bar_base + grid) ? 1 : 0;
-        if (s_last) __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
+    // ---- CTA 0 collects the per-CTA partial sums -- (value, sequence) pairs again: no counter, no fence -- adds them in a fixed
+    // order and writes the scores to the caller's mapped memory as pairs too: the host polls the score pairs themselves ----
+    if (cta != 0) return;
     const int nd = P->n_diffs;
+    const long long tf = clock64();
     for (int l = warp; l < nd; l += ST_THREADS / 32) {          // warp l: diff l, lanes split the CTAs (<= 8 loads in flight each)
         const int na = P->nact[l];
         for (int r = 0; r < rows; ++r) {
             float t[8];
+            unsigned pending = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = lane + 32 * j;
-                t[j] = c < na ? __ldcg(P->partial + ((size_t)l * grid + c) * ST_MAX_ROWS + r) : 0.f;
+            for (int j = 0; j < 8; ++j) { t[j] = 0.f; if (lane + 32 * j < na) pending |= 1u << j; }
+            while (pending) {
+                uint2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (pending & (1u << j)) v[j] = ld_pair(P->partial + ((size_t)l * grid + lane + 32 * j) * ST_MAX_ROWS + r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if ((pending & (1u << j)) && v[j].y == seq32) { t[j] = __uint_as_float(v[j].x); pending &= ~(1u << j); }
+                if (pending && clock64() - tf > 2000000000LL) {
+                    printf("mmad stream kernel: partial sums of diff %d never arrived (lane %d)\n", l, lane);
+                    __trap();
+                }
             }
             float v = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
             v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -355,15 +370,12 @@ stream_chain_kernel(const StPlan* __restrict__ P, const float* __restrict__ x_sr
     if (tid < rows) {
         float sap = 0.f;
         for (int l = P->lo; l < P->hi; ++l) sap += s_fin[l][tid];
-        out_host[tid] = s_fin[0][tid] * P->inv_base;
-        out_host[ST_MAX_ROWS + tid] = sap * P->inv_sap;
+        st_pair(out_host + tid, s_fin[0][tid] * P->inv_base, seq32);
+        st_pair(out_host + ST_MAX_ROWS + tid, sap * P->inv_sap, seq32);
     }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(flag_host) = seq;
-        __threadfence_system();
-        if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[1 + n_steps] = t; }
+    if (dbg) {
+        __syncthreads();
+        if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[1 + n_steps] = t; }
     }
 }
 
@@ -377,11 +389,11 @@ struct StreamState {
     uint2* d_act = nullptr;              // one pair buffer per step output (nothing is reused inside a call)
     float* d_xf = nullptr;               // the same as plain floats (flag protocol)
     float* d_actf = nullptr;
-    float* d_partial = nullptr;
+    uint2* d_partial = nullptr;
     unsigned long long* d_bar = nullptr;
     float* h_in = nullptr;  float* d_in = nullptr;      // pinned + mapped input [64, D]
-    float* h_out = nullptr; float* d_out = nullptr;     // pinned + mapped scores [2][64] + flag
-    unsigned long long seq = 0, bar_base = 0, bar2_base = 0;
+    uint2* h_out = nullptr; uint2* d_out = nullptr;     // pinned + mapped scores [2][64] as (value, sequence) pairs
+    unsigned long long seq = 0, bar2_base = 0;
     unsigned long long* d_dbg = nullptr;  // MMAD_STREAM_DEBUG=1: per-phase globaltimer stamps of CTA 0
     unsigned long long weights_gen = 0;
     cudaStream_t stream = nullptr;
@@ -410,9 +422,8 @@ const void* stream_kernel(int idx) {
 }
 
 int launch(StreamState* S, int idx, int rows) {
-    unsigned long long* flag = reinterpret_cast<unsigned long long*>(S->d_out + 2 * ST_MAX_ROWS);
-    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, (void*)&flag, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar_base,
-                    (void*)&S->bar2_base, (void*)&S->d_dbg};
+    void* args[] = {(void*)&S->d_plan, (void*)&S->d_in, (void*)&rows, (void*)&S->d_out, (void*)&S->seq, (void*)&S->d_bar, (void*)&S->bar2_base,
+                    (void*)&S->d_dbg};
     MMAD_CUDA_OK(cudaLaunchCooperativeKernel(stream_kernel(idx), dim3(S->grid), dim3(ST_THREADS), args, S->smem[idx], S->stream));
     return MMAD_OK;
 }
@@ -448,11 +459,11 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         S->D = D;
         MMAD_CUDA_OK(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
         MMAD_CUDA_OK(cudaMalloc(&S->d_plan, sizeof(StPlan)));
-        MMAD_CUDA_OK(cudaMalloc(&S->d_bar, 16));
-        MMAD_CUDA_OK(cudaMemset(S->d_bar, 0, 16));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_bar, 8));
+        MMAD_CUDA_OK(cudaMemset(S->d_bar, 0, 8));
         MMAD_CUDA_OK(cudaHostAlloc(&S->h_in, (size_t)ST_MAX_ROWS * D * 4, cudaHostAllocMapped));
-        MMAD_CUDA_OK(cudaHostAlloc(&S->h_out, (size_t)(2 * ST_MAX_ROWS + 4) * 4, cudaHostAllocMapped));
-        memset(S->h_out, 0, (size_t)(2 * ST_MAX_ROWS + 4) * 4);
+        MMAD_CUDA_OK(cudaHostAlloc(&S->h_out, (size_t)2 * ST_MAX_ROWS * sizeof(uint2), cudaHostAllocMapped));
+        memset(S->h_out, 0, (size_t)2 * ST_MAX_ROWS * sizeof(uint2));
         MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_in, S->h_in, 0));
         MMAD_CUDA_OK(cudaHostGetDevicePointer((void**)&S->d_out, S->h_out, 0));
         const char* dbg = getenv("MMAD_STREAM_DEBUG");
@@ -476,7 +487,8 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     if (!S->d_act) {
         MMAD_CUDA_OK(cudaMalloc(&S->d_act, buf * n_buf * 8));
         MMAD_CUDA_OK(cudaMalloc(&S->d_x, buf * 8));
-        MMAD_CUDA_OK(cudaMalloc(&S->d_partial, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
+        MMAD_CUDA_OK(cudaMalloc(&S->d_partial, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 8));
+        MMAD_CUDA_OK(cudaMemset(S->d_partial, 0, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 8));
         MMAD_CUDA_OK(cudaMemset(S->d_act, 0, buf * n_buf * 8));       // sequence 0 is never used by a call
         MMAD_CUDA_OK(cudaMemset(S->d_x, 0, buf * 8));
         MMAD_CUDA_OK(cudaMalloc(&S->d_actf, buf * n_buf * 4));
@@ -484,7 +496,6 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     }
     MMAD_CUDA_OK(cudaMemset(S->d_actf, 0, buf * n_buf * 4));          // padding columns of the float buffers stay zero for ever
     MMAD_CUDA_OK(cudaMemset(S->d_xf, 0, buf * 4));
-    MMAD_CUDA_OK(cudaMemset(S->d_partial, 0, (size_t)(L + 1) * S->grid * ST_MAX_ROWS * 4));
     // buffers: 0..L-1 enc(x) (the diff references), L..L+Ld-1 decoder, then enc(xhat)
     StPlan P;
     memset(&P, 0, sizeof P);
@@ -500,7 +511,7 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
     P.inv_sap = 1.f / dsel;
     int ns = 0;
     size_t need[5] = {0, 0, 0, 0, 0};
-    int prev_nprod = 0;
+    int prev_nprod = 0, wmax4 = 0, kpmax = 0;
     auto add = [&](const LayerF32& Lr, int ibuf, int obuf, int rbuf, int diff) {
         StStep& st = P.step[ns++];
         st.W = Lr.W; st.bias = Lr.bias; st.scale = Lr.has_bn ? Lr.scale : nullptr; st.shift = Lr.has_bn ? Lr.shift : nullptr;
@@ -510,7 +521,9 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
         st.diff = diff;
         prev_nprod = (Lr.N + st.cpc - 1) / st.cpc;
         if (diff >= 0) P.nact[diff] = prev_nprod;
-        for (int i = 0; i < 5; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + kNbOf[i]) * Lr.Kp * 4);
+        wmax4 = std::max(wmax4, st.cpc * st.K4);
+        kpmax = std::max(kpmax, Lr.Kp);
+        for (int i = 2; i < 5; ++i) need[i] = std::max(need[i], (size_t)(st.cpc + kNbOf[i]) * Lr.Kp * 4);
     };
     int cur = -1;
     for (int l = 0; l < L; ++l) { add(enc[l], cur, l, -2, -1); cur = l; }
@@ -528,6 +541,8 @@ static int stream_prepare(mmad_t h, int lo, int hi) {
             cur = out;
         }
     }
+    P.wmax4 = wmax4;
+    for (int i = 0; i < 2; ++i) need[i] = (size_t)2 * wmax4 * 16 + (size_t)kNbOf[i] * kpmax * 4;      // pair protocol: two slices + the tile
     P.n_steps = ns;          // diffs beyond `last` have no producers: nact == 0, their sum is 0
     S->n_steps = ns;
     MMAD_CUDA_OK(cudaMemcpy(S->d_plan, &P, sizeof P, cudaMemcpyHostToDevice));
@@ -568,19 +583,27 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
     rc = launch(S, idx, rows);
     if (rc) return rc;
     MMAD_LAUNCHED();
-    S->bar_base += (unsigned long long)S->grid;          // one arrival per CTA and call (the last one finalises)
     if (idx >= 2) S->bar2_base += (unsigned long long)S->grid * (unsigned long long)S->n_steps;   // staging + n_steps - 1 barriers
-    // the doorbell: the kernel's last store is the sequence number, written after the scores (system-scope fences)
-    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(S->h_out + 2 * ST_MAX_ROWS);
+    // the doorbell: every score arrives as an 8-byte (value, sequence) pair in mapped pinned memory; a pair that carries this
+    // call's number is final (single-copy atomic store), so the host polls the scores themselves
+    const uint32_t seq32 = (uint32_t)S->seq;
+    volatile uint2* hp = S->h_out;
+    auto arrived = [&]() {
+        for (int r = rows - 1; r >= 0; --r)
+            if (hp[r].y != seq32 || hp[ST_MAX_ROWS + r].y != seq32) return false;
+        return true;
+    };
     const auto t0 = std::chrono::steady_clock::now();
     unsigned spins = 0;
-    while (*flag != S->seq) {
+    bool ok = arrived();
+    while (!ok) {
         __builtin_ia32_pause();
-        if ((++spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) break;
+        ok = arrived();
+        if (!ok && (++spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) break;
     }
-    if (*flag != S->seq) {        // never rang: fetch the launch / execution error
+    if (!ok) {        // never rang: fetch the launch / execution error
         cudaError_t e = cudaStreamSynchronize(S->stream);
-        if (e != cudaSuccess || *flag != S->seq) {
+        if (e != cudaSuccess || !arrived()) {
             S->ok = false;
             set_error("stream kernel did not complete: %s", cudaGetErrorString(e));
             return MMAD_E_CUDA;
@@ -597,8 +620,10 @@ int stream_score(mmad_t h, const float* h_x, int ldx, int rows, int lo, int hi, 
         for (int i = 0; i < S->n_steps; ++i) fprintf(stderr, " %.1f", (t[2 + i] - t[1 + i]) / 1e3);
         fprintf(stderr, "\n");
     }
-    if (h_base) memcpy(h_base, S->h_out, (size_t)rows * 4);
-    if (h_sap) memcpy(h_sap, S->h_out + ST_MAX_ROWS, (size_t)rows * 4);
+    for (int r = 0; r < rows; ++r) {
+        if (h_base) memcpy(h_base + r, (const void*)&S->h_out[r].x, 4);
+        if (h_sap) memcpy(h_sap + r, (const void*)&S->h_out[ST_MAX_ROWS + r].x, 4);
+    }
     return MMAD_OK;
 }
 
