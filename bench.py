@@ -425,6 +425,18 @@ def bench_stream(eng, batches=(1, 8, 10, 64), calls=400, warm=60):
         ts = np.sort(np.asarray(ts)) * 1e6
         out[str(b)] = {"p50_us": float(ts[len(ts) // 2]), "p99_us": float(ts[int(len(ts) * 0.99)]),
                        "p50_us_per_window": float(ts[len(ts) // 2] / b)}
+        # the same call at the C ABI (what a C / C++ caller of mmad_score_host pays): arguments converted once
+        from icra2021_multimodal_ad_b200._lib import lib
+        fn = lib().mmad_score_host
+        ob, os_ = np.empty(b, dtype=np.float32), np.empty(b, dtype=np.float32)
+        a = (eng._h, C.c_void_p(x.ctypes.data), D, C.c_longlong(b), 0, NL + 1, C.c_void_p(ob.ctypes.data), C.c_void_p(os_.ctypes.data), None)
+        tc = []
+        for _ in range(calls):
+            t0 = time.perf_counter()
+            fn(*a)
+            tc.append(time.perf_counter() - t0)
+        tc = np.sort(np.asarray(tc)) * 1e6
+        out[str(b)]["p50_us_c_abi"] = float(tc[len(tc) // 2])
     return out
 
 
