@@ -740,6 +740,7 @@ int mmad_concat_width(mmad_t h, int lo, int hi) {
 
 int mmad_ae_forward(mmad_t h, const float* d_x, int ldx, int n, float* d_xhat, float* d_z, void* d_ws,
                     size_t ws_bytes, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_ae_forward");
     int rc = check_ready(h);
     if (rc) return rc;
     if (n == 0) return MMAD_OK;
@@ -840,6 +841,7 @@ static int score_impl(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi
 
 int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float* d_nap,
                float* d_diffs, void* d_ws, size_t ws_bytes, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_score");
     int rc = check_ready(h);
     if (rc) return rc;
     // <= 64 rows (the realtime caller): exact-fp32 weight-streaming kernels on all SMs instead of one 128-row tile
@@ -915,6 +917,7 @@ static int score_impl(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi
 
 int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, double* d_sum, void* d_ws,
                             size_t ws_bytes, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_nap_accumulate_sum");
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
@@ -942,6 +945,7 @@ int mmad_nap_accumulate_sum(mmad_t h, const float* d_x, int ldx, int n, int lo, 
 
 int mmad_nap_accumulate_gram(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, const float* d_mu,
                              double* d_gram, void* d_ws, size_t ws_bytes, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_nap_accumulate_gram");
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
@@ -1030,6 +1034,7 @@ int mmad_nap_set_standardizer(mmad_t h, const float* d_var, const float* d_mu2, 
 
 int mmad_nap_rotate_stats(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, double* d_rsum, double* d_rsq,
                           void* d_ws, size_t ws_bytes, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_nap_rotate_stats");
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;
@@ -1065,6 +1070,7 @@ int mmad_nap_rotate_stats(mmad_t h, const float* d_x, int ldx, int n, int lo, in
 // Host-buffer scoring: double-buffered H2D / compute / D2H over two internal streams.
 int mmad_score_host(mmad_t h, const float* h_x, int ldx, long long n, int lo, int hi, float* h_base, float* h_sap,
                     float* h_nap) {
+    mmad::NvtxScope nvtx_("mmad_score_host");
     int rc = check_ready(h);
     if (rc) return rc;
     if ((rc = check_range(h, lo, hi))) return rc;

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler injects itself
+
 #include "../../include/mmad.h"
 
 namespace mmad {
@@ -26,6 +28,14 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
             return MMAD_E_CUDA;                                                         \
         }                                                                               \
     } while (0)
+
+// NVTX range around an entry point of the C ABI (nsys / ncu --nvtx show the path's phases by name)
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+    NvtxScope(const NvtxScope&) = delete;
+    NvtxScope& operator=(const NvtxScope&) = delete;
+};
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }

@@ -835,6 +835,7 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
                        const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, const float* d_eps, float beta_kl,
                        float bn_momentum, float* d_loss, void* d_ws, size_t ws_bytes, mmad_allreduce_fn allreduce,
                        void* allreduce_ctx, void* stream) {
+    mmad::NvtxScope nvtx_("mmad_train_fwd_bwd");
     if (!h || !d_x || !enc || !dec || !d_loss || !d_ws) { set_error("null argument"); return MMAD_E_ARG; }
     const mmad_desc_t& d = *handle_desc(h);
     const int D = d.enc_widths[0];
@@ -916,6 +917,7 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
 int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads, float* const* h_m, float* const* h_v,
                    const long long* h_numel, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
                    void* stream) {
+    mmad::NvtxScope nvtx_("mmad_adam_step");
     if (n_tensors < 0 || (n_tensors > 0 && (!h_params || !h_grads || !h_m || !h_v || !h_numel)) || step < 1) {
         set_error("bad argument"); return MMAD_E_ARG;
     }
