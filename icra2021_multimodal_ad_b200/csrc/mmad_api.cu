@@ -515,6 +515,12 @@ LayerF32 handle_layer_f32(mmad_t h, int module, int index) {
     const Layer& L = (module == 0 ? h->enc : h->dec)[index];
     return LayerF32{L.K, L.N, L.Kp, L.Np, L.has_bn, L.W, L.bias, L.scale, L.shift};
 }
+int handle_layer_tcmaps(mmad_t h, int module, int index, CUtensorMap* wh, CUtensorMap* wl, float* wscale) {
+    const Layer& L = (module == 0 ? h->enc : h->dec)[index];
+    if (!L.tc_ready) return 1;
+    *wh = L.tcB2.hi; *wl = L.tcB2.lo; *wscale = L.wscale;
+    return 0;
+}
 unsigned long long handle_weights_gen(mmad_t h) { return h->weights_gen; }
 void* handle_stream_get(mmad_t h) { return h->stream_state; }
 void* handle_peer_get(mmad_t h) { return h->peer_state; }
@@ -857,6 +863,14 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
         ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) && !check_range(h, lo, hi)) {
         rc = smallnet_score(h, d_x, ldx, n, lo, hi, d_base, d_sap, (cudaStream_t)stream);
         if (rc != MMAD_E_UNSUPPORTED) { h->skinny = false; return rc; }      // (plan not built while the stream is capturing)
+    }
+    // ... and in the F16X3 mode from ONE fused tensor-core kernel (smallnet_tc.cu): weights and activations in shared memory,
+    // accumulators in TMEM, nothing but x and the scores in HBM.  Calls of <= 64 rows keep the exact-fp32 small-batch kernels.
+    if (n > 64 && !d_nap && !d_diffs && h->smallnet && h->desc.precision == MMAD_PREC_F16X3 && !h->prof && smallnet_enabled() &&
+        smallnet_fits(h) && tc_available() && d_x && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) &&
+        !check_range(h, lo, hi)) {
+        rc = smallnet_tc_score(h, d_x, ldx, n, lo, hi, d_base, d_sap, (float)h->acc_comp, (cudaStream_t)stream);
+        if (rc != MMAD_E_UNSUPPORTED) { h->skinny = false; return rc; }
     }
     rc = score_impl(h, d_x, ldx, n, lo, hi, d_base, d_sap, d_nap, d_diffs, d_ws, ws_bytes, stream);
     h->skinny = false;

@@ -160,6 +160,10 @@ void handle_smallnet_set(mmad_t h, void* state);
 void smallnet_state_free(void* state);
 bool smallnet_enabled();                              // MMAD_NO_SMALLNET=1 disables
 bool smallnet_fits(mmad_t h);
+// tensor-core variant (smallnet_tc.cu): TMA maps of a layer's fp16 twins (box 64 halfs x 128 rows) and their scale
+int handle_layer_tcmaps(mmad_t h, int module, int index, CUtensorMap* wh, CUtensorMap* wl, float* wscale);
+int smallnet_tc_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, float acc_comp,
+                      cudaStream_t s);
 int smallnet_prepare(mmad_t h, int lo, int hi, cudaStream_t s);     // (re)builds the packed plan; synchronises s
 int smallnet_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float* d_base, float* d_sap, cudaStream_t s);
 

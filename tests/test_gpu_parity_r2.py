@@ -339,24 +339,26 @@ def test_realtime_detecter_test_call(D, btl, nl, tmp_path):
 @pytest.mark.parametrize("precision", ["fp32", "f16x3"])
 @pytest.mark.parametrize("D,btl,nl", [(64, 100, 5), (128, 100, 5), (93, 10, 3), (48, 100, 5), (128, 128, 2)])
 def test_smallnet_fused_chain_matches_oracle(D, btl, nl, precision):
-    """Per-modality models (utils/data_loaders.py:16-29: force_torque 64, mic 128; every width <= 128): in the fp32 mode
-    base and SAP come from ONE fused kernel per call (rows must be 16-byte aligned: D % 4 == 0); the tensor-core modes and
-    unaligned widths keep the per-layer kernels.  Against the oracle, against the per-layer kernels (mmad_set_option
+    """Per-modality models (utils/data_loaders.py:16-29: force_torque 64, mic 128; every width <= 128): base and SAP come
+    from ONE fused kernel per call -- CUDA cores in the fp32 mode (smallnet.cu), tensor cores with weights and activations
+    in shared memory and accumulators in TMEM in the f16x3 mode (smallnet_tc.cu, calls of more than 64 rows); rows must be
+    16-byte aligned (D % 4 == 0), other cases keep the per-layer kernels.  Against the oracle, against the per-layer kernels (mmad_set_option
     smallnet = 0), every layer selection, ragged row counts, odd widths."""
     from icra2021_multimodal_ad_b200._lib import lib
     from oracle import rapp_oracle as RO
     sd = synth_state_dict(D, btl, nl, 13)
     eng = _model(D, btl, nl, sd, precision).engine()
-    fused = precision == "fp32" and D % 4 == 0
     tol = 2e-5 if precision == "fp32" else 1e-4
-    for n in (1, 31, 32, 33, 257, 20011):
+    for n in (1, 31, 32, 33, 127, 128, 129, 257, 20011):
+        # fp32: the fused CUDA-core kernel at every row count; f16x3: the fused tensor-core kernel above 64 rows
+        fused = D % 4 == 0 and (precision == "fp32" or n > 64)
         x, _ = synth_windows(n, D, 300 + n)
         ref = RO.get_diffs(x, sd)
         xd = x.cuda()
         eng.score(xd, 0, nl + 1)
         l0 = lib().mmad_launch_count()
         o = eng.score(xd, 0, nl + 1)
-        assert (lib().mmad_launch_count() - l0 == 1) == fused
+        assert (lib().mmad_launch_count() - l0 == 1) == fused, (n, precision)
         np.testing.assert_allclose(o["sap"].cpu().numpy(), RO.sap_score(ref), rtol=tol)
         np.testing.assert_allclose(o["base"].cpu().numpy(), RO.recon_score(ref[0]), rtol=tol)
         if n == 257:
