@@ -3,13 +3,15 @@
 // held in shared memory, the layer chain is fused per batch tile, and tcgen05 tensor cores are used ... for the dense
 // batch x width GEMMs".
 //
-// One CTA (128 threads) owns a tile of 128 windows and walks ALL layers; nothing but x and the two scores touches HBM:
+// One CTA (512 threads) owns a tile of 128 windows and walks ALL layers; nothing but x and the two scores touches HBM:
 //   * activations live in shared memory as fp16 hi/lo twins in the K-major, 128-byte-swizzled layout tcgen05.mma reads
 //     (the epilogue writes that layout directly: 16-byte chunk j of row r goes to chunk j ^ (r & 7));
 //   * one layer's weights (hi/lo twins of 256 W, <= 64 KB) sit in shared memory, fetched by TMA; the NEXT layer's weights are
 //     requested as soon as the current layer's MMAs have completed, so the fetch hides behind the epilogue;
-//   * the accumulators sit in TMEM (2 x 128 columns); thread t owns row t: tcgen05.ld hands it its accumulator row, it applies
-//     bias / LeakyReLU / BatchNorm, splits the result into the next layer's fp16 pair and writes it back into the tile in place;
+//   * the accumulators sit in TMEM (2 x 128 columns); four threads share a row (32 columns each; with ONE thread per row the
+//     four warps of the CTA ran at one warp per scheduler and the epilogue's dependent-issue latency was the whole kernel):
+//     tcgen05.ld hands a thread its piece of the accumulator row, it applies bias / LeakyReLU / BatchNorm, splits the result
+//     into the next layer's fp16 pair and writes it back into the tile in place;
 //   * pass A (enc, dec) runs on the x tile; pass B runs the encoder on the x tile AND the xhat tile with the same weights
 //     (reconstruction_aggregation.py:25-27 does exactly that), so the diff d_l = enc_l(xhat) - enc_l(x) is formed from two fp32
 //     accumulator rows in registers -- no stash -- and its squares are summed per row by the thread that owns the row.
@@ -23,11 +25,11 @@ using namespace tc;
 
 namespace {
 
-constexpr int SNT_THREADS = 128;
+constexpr int SNT_THREADS = 512;            // 16 warps: row = 32 * (warp % 4) + lane (the TMEM lanes a warp may read), column block = warp / 4
 constexpr int SNT_MAX_LAYERS = 8;
 constexpr int SNT_TILE = 16384;                 // one [128 rows x 64 halfs] swizzled box
 constexpr int SNT_ACT = 4 * SNT_TILE;           // hi kb0, hi kb1, lo kb0, lo kb1
-constexpr int SNT_SMEM = 3 * SNT_ACT + 2048 + 1024;      // x tile, xhat tile, weights + vectors/barriers (1.6 KB) + alignment
+constexpr int SNT_SMEM = 3 * SNT_ACT + 4096 + 1024;      // x tile, xhat tile, weights + vectors / row partials / barriers (3.6 KB) + alignment
 
 struct alignas(64) SntLayer {
     CUtensorMap wh, wl;          // hi / lo twins of 256 W, [N rows, Kp] K-major, box 64 halfs x 128 rows
@@ -74,10 +76,13 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
     uint8_t* tQ = smem + SNT_ACT;               // x tile of pass B
     uint8_t* tW = smem + 2 * SNT_ACT;           // weights of the current layer: Wh kb0, Wh kb1, Wl kb0, Wl kb1
     float* s_vec = reinterpret_cast<float*>(smem + 3 * SNT_ACT);         // [3][128] bias, scale, shift of the current layer
-    uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_vec + 3 * 128);      // weights landed
+    float* s_sq = s_vec + 3 * 128;                                       // [4][128] row partial sums of d^2 per column block
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_sq + 4 * 128);       // weights landed
     uint64_t* bar_mma = bar_w + 1;                                       // this step's MMAs completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = (warp & 3) * 32 + (tid & 31);       // this thread's row of the tile == its TMEM lane
+    const int q = warp >> 2;                            // its block of 32 columns
 
     if (tid == 0) {
         mbar_init(smem_u32(bar_w), 1);
@@ -92,7 +97,7 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes; thread t <-> lane t
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's 32 TMEM lanes
 
     const int L = P.n_enc, Ld = P.n_dec, D = P.D;
     const int steps_a = L + Ld, n_steps = steps_a + P.last;
@@ -185,18 +190,18 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
                 if (s + 1 < n_steps) fetch_weights(s + 1);
                 else if (t + (int)gridDim.x < tiles) fetch_weights(0);
             }
-            // ---- epilogue: thread `tid` owns row `tid` ----
+            // ---- epilogue: thread (row, q) owns columns [32 q, 32 q + 32) of its row ----
             const int kp_next = ((Ly.N + 63) / 64) * 64;
             const bool write_p = pass_b ? (l_b < P.last) : true;         // pass B's last layer feeds nothing
             const bool is_xhat = !pass_b && s == steps_a - 1;
+            const int c0 = q * 32;
             float sq = 0.f;
-            for (int c0 = 0; c0 < kp_next; c0 += 32) {
+            if (c0 < kp_next) {
                 uint32_t v0[32], v1[32];
                 if (c0 < n_eff) {
                     tmem_ld32(taddr + c0, v0);
                     if (pass_b) tmem_ld32(taddr + 128 + c0, v1);
                 }
-                float y0[32], y1[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int c = c0 + i;
@@ -212,40 +217,44 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
                             sq = fmaf(d, d, sq);
                         }
                     }
-                    y0[i] = a0; y1[i] = a1;
+                    v0[i] = __float_as_uint(a0); v1[i] = __float_as_uint(a1);
                 }
-                if (is_xhat && r0 + tid < n) {           // d_0 = xhat - x against the fp32 input
-                    const float* xr = x + (size_t)(r0 + tid) * ldx;
+                if (is_xhat && r0 + row < n) {           // d_0 = xhat - x against the fp32 input
+                    const float* xr = x + (size_t)(r0 + row) * ldx;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int c = c0 + i;
-                        if (c < D) { const float d = y0[i] - __ldg(xr + c); sq = fmaf(d, d, sq); }
+                        if (c < D) { const float d = __uint_as_float(v0[i]) - __ldg(xr + c); sq = fmaf(d, d, sq); }
                     }
                 }
                 if (write_p) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int k8 = 0; k8 < 4; ++k8) {
                         float o[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = y0[q * 8 + j];
-                        snt_store8(pass_b ? tQ : tP, tid, (c0 >> 3) + q, o);
+                        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v0[k8 * 8 + j]);
+                        snt_store8(pass_b ? tQ : tP, row, (c0 >> 3) + k8, o);
                         if (pass_b) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = y1[q * 8 + j];
-                            snt_store8(tP, tid, (c0 >> 3) + q, o);
+                            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v1[k8 * 8 + j]);
+                            snt_store8(tP, row, (c0 >> 3) + k8, o);
                         }
                     }
                 }
             }
-            if (is_xhat) { base_sum = sq; if (P.lo == 0) sap_sum += sq; }
-            if (pass_b && l_b >= P.lo && l_b < P.hi) sap_sum += sq;
+            s_sq[q * 128 + row] = sq;
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
+            if (q == 0) {                                // the row's four column blocks, fixed order
+                const float t4 = ((s_sq[row] + s_sq[128 + row]) + s_sq[256 + row]) + s_sq[384 + row];
+                if (is_xhat) { base_sum = t4; if (P.lo == 0) sap_sum += t4; }
+                if (pass_b && l_b >= P.lo && l_b < P.hi) sap_sum += t4;
+            }
         }
-        if (r0 + tid < n) {
-            if (base_out) base_out[r0 + tid] = base_sum * P.inv_base;
-            if (sap_out) sap_out[r0 + tid] = sap_sum * P.inv_sap;
+        if (q == 0 && r0 + row < n) {
+            if (base_out) base_out[r0 + row] = base_sum * P.inv_base;
+            if (sap_out) sap_out[r0 + row] = sap_sum * P.inv_sap;
         }
     }
     tc_fence_before();
