@@ -29,7 +29,7 @@ constexpr int SNT_THREADS = 512;            // 16 warps: row = 32 * (warp % 4) +
 constexpr int SNT_MAX_LAYERS = 8;
 constexpr int SNT_TILE = 16384;                 // one [128 rows x 64 halfs] swizzled box
 constexpr int SNT_ACT = 4 * SNT_TILE;           // hi kb0, hi kb1, lo kb0, lo kb1
-constexpr int SNT_SMEM = 3 * SNT_ACT + 4096 + 1024;      // x tile, xhat tile, weights + vectors / row partials / barriers (3.6 KB) + alignment
+constexpr int SNT_SMEM = 3 * SNT_ACT + 6144 + 1024;      // x tile, xhat tile, weights + vectors (3 KB) / row partials (2 KB) / barriers + alignment
 
 struct alignas(64) SntLayer {
     CUtensorMap wh, wl;          // hi / lo twins of 256 W, [N rows, Kp] K-major, box 64 halfs x 128 rows
@@ -42,8 +42,14 @@ struct SntParams {
     SntLayer enc[SNT_MAX_LAYERS], dec[SNT_MAX_LAYERS];
     int n_enc, n_dec, D, lo, hi, last;
     float inv_base, inv_sap, slope;
+    unsigned long long* dbg;     // MMAD_SNT_DEBUG=1: %globaltimer stamps of CTA 0's first tile, 6 per step
 };
 
+__device__ __forceinline__ unsigned long long snt_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `ch` (8 halfs) of row `row` inside an activation tile half (hi or lo)
@@ -51,8 +57,17 @@ __device__ __forceinline__ uint32_t snt_chunk_off(int row, int ch) {
     return (uint32_t)((ch >> 3) * SNT_TILE + row * 128 + (((ch & 7) ^ (row & 7)) << 4));
 }
 
-// eight values -> hi / lo halves, written as one 16-byte chunk each
-__device__ __forceinline__ void snt_store8(uint8_t* tile, int row, int ch, const float (&y)[8]) {
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
+// eight values -> hi / lo halves, written as one 16-byte chunk each (`tile` is a shared-space address)
+__device__ __forceinline__ void snt_store8(uint32_t tile, int row, int ch, const float (&y)[8]) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -62,9 +77,55 @@ __device__ __forceinline__ void snt_store8(uint8_t* tile, int row, int ch, const
         h[i] = *reinterpret_cast<const uint32_t*>(&hh);
         l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    const uint32_t off = snt_chunk_off(row, ch);
-    *reinterpret_cast<uint4*>(tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(tile + 2 * SNT_TILE + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    const uint32_t off = tile + snt_chunk_off(row, ch);
+    sts128(off, h[0], h[1], h[2], h[3]);
+    sts128(off + 2 * SNT_TILE, l[0], l[1], l[2], l[3]);
+}
+
+// the eight values of a chunk back as hi + lo
+__device__ __forceinline__ void snt_load8(uint32_t tile, int row, int ch, float (&y)[8]) {
+    const uint32_t off = tile + snt_chunk_off(row, ch);
+    const uint4 h = lds128u(off), l = lds128u(off + 2 * SNT_TILE);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&ll[i]));
+        y[2 * i] = a.x + c.x; y[2 * i + 1] = a.y + c.y;
+    }
+}
+
+// bias / LeakyReLU / BatchNorm of 32 accumulator columns in place; `sv` = shared address of the layer's vectors at column c0.
+// Columns past the layer's width come out as exact zeros without a test: their weights, bias, scale and shift are all zero.
+template <bool BN>
+__device__ __forceinline__ void snt_transform(uint32_t (&v)[32], uint32_t sv, float mul, float slope) {
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 b = lds128(sv + i4 * 16);
+        float a[4] = {fmaf(__uint_as_float(v[4 * i4]), mul, b.x), fmaf(__uint_as_float(v[4 * i4 + 1]), mul, b.y),
+                      fmaf(__uint_as_float(v[4 * i4 + 2]), mul, b.z), fmaf(__uint_as_float(v[4 * i4 + 3]), mul, b.w)};
+        if (BN) {
+            const float4 sc = lds128(sv + 512 + i4 * 16), sh = lds128(sv + 1024 + i4 * 16);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[j] = a[j] > 0.f ? a[j] : a[j] * slope;
+                a[j] = fmaf(a[j], scv[j], shv[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[4 * i4 + j] = __float_as_uint(a[j]);
+    }
+}
+
+__device__ __forceinline__ void snt_store32(uint32_t tile, int row, int c0, const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int k8 = 0; k8 < 4; ++k8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[k8 * 8 + j]);
+        snt_store8(tile, row, (c0 >> 3) + k8, o);
+    }
 }
 
 __global__ void __launch_bounds__(SNT_THREADS, 1)
@@ -72,21 +133,26 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
                    float* __restrict__ sap_out) {
     extern __shared__ uint8_t snt_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(snt_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tP = smem;                         // x tile, then the activations of pass A in place, finally xhat
-    uint8_t* tQ = smem + SNT_ACT;               // x tile of pass B
-    uint8_t* tW = smem + 2 * SNT_ACT;           // weights of the current layer: Wh kb0, Wh kb1, Wl kb0, Wl kb1
-    float* s_vec = reinterpret_cast<float*>(smem + 3 * SNT_ACT);         // [3][128] bias, scale, shift of the current layer
-    float* s_sq = s_vec + 3 * 128;                                       // [4][128] row partial sums of d^2 per column block
-    uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_sq + 4 * 128);       // weights landed
-    uint64_t* bar_mma = bar_w + 1;                                       // this step's MMAs completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t tP = sb;                       // x tile, then the activations of pass A in place, finally xhat
+    const uint32_t tQ = sb + SNT_ACT;             // x again: compared with xhat, then the x path of pass B in place
+    const uint32_t tW = sb + 2 * SNT_ACT;         // weights of the current layer: Wh kb0, Wh kb1, Wl kb0, Wl kb1
+    const uint32_t s_vec = sb + 3 * SNT_ACT;      // [2 buffers][bias, scale, shift][128]: this step's and the next step's vectors
+    float* s_sq = reinterpret_cast<float*>(smem + 3 * SNT_ACT + 2 * 3 * 128 * 4);      // [4][128] row partial sums of d^2 per column block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sq + 4 * 128);
+    const uint32_t bar_w = smem_u32(bars);        // weights landed
+    const uint32_t bar_mma = smem_u32(bars + 1);  // accumulator 0 complete
+    const uint32_t bar_mma2 = smem_u32(bars + 2); // pass B: accumulator 1 complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = (warp & 3) * 32 + (tid & 31);       // this thread's row of the tile == its TMEM lane
     const int q = warp >> 2;                            // its block of 32 columns
+    const int c0 = q * 32;
 
     if (tid == 0) {
-        mbar_init(smem_u32(bar_w), 1);
-        mbar_init(smem_u32(bar_mma), 1);
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_mma2, 1);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -97,30 +163,46 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's 32 TMEM lanes
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c0;     // this warp's 32 TMEM lanes, this thread's columns
 
     const int L = P.n_enc, Ld = P.n_dec, D = P.D;
     const int steps_a = L + Ld, n_steps = steps_a + P.last;
+    const float slope = P.slope;
     auto layer_of = [&](int s) -> const SntLayer& { return s < L ? P.enc[s] : (s < steps_a ? P.dec[s - L] : P.enc[s - steps_a]); };
     auto fetch_weights = [&](int s) {           // thread 0: TMA of step s's weight twins into tW
         const SntLayer& Ly = layer_of(s);
-        const uint32_t fb = smem_u32(bar_w);
-        mbar_expect_tx(fb, (uint32_t)(2 * Ly.num_kb * SNT_TILE));
-        for (int kb = 0; kb < Ly.num_kb; ++kb) {
-            tma_load_2d(smem_u32(tW + kb * SNT_TILE), &Ly.wh, fb, kb * 64, 0);
-            tma_load_2d(smem_u32(tW + 2 * SNT_TILE + kb * SNT_TILE), &Ly.wl, fb, kb * 64, 0);
+        const int nkb = Ly.num_kb;
+        mbar_expect_tx(bar_w, (uint32_t)(2 * nkb * SNT_TILE));
+        for (int kb = 0; kb < nkb; ++kb) {
+            tma_load_2d(tW + kb * SNT_TILE, &Ly.wh, bar_w, kb * 64, 0);
+            tma_load_2d(tW + 2 * SNT_TILE + kb * SNT_TILE, &Ly.wl, bar_w, kb * 64, 0);
         }
     };
-    // x rows of the tile -> fp16 hi / lo twins in the swizzled layout (coalesced 32-byte reads, zero padding to 64 / 128 columns)
-    auto load_x = [&](uint8_t* tile, int r0) {
+    // threads 128..255: the epilogue vectors of step s into buffer `buf` (zero past the layer's width)
+    auto fetch_vectors = [&](int s, int buf) {
+        const SntLayer& Ly = layer_of(s);
+        const int c = tid - 128;
+        const bool ok = c < Ly.N;
+        const float* sc = Ly.scale;
+        const float b = ok ? __ldg(Ly.bias + c) : 0.f;
+        const float a = (ok && sc) ? __ldg(sc + c) : 0.f;
+        const float h = (ok && sc) ? __ldg(Ly.shift + c) : 0.f;
+        const uint32_t dst = s_vec + buf * 1536 + c * 4;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(b) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 512), "f"(a) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 1024), "f"(h) : "memory");
+    };
+    // x rows of the tile -> fp16 hi / lo twins in the swizzled layout, into BOTH tiles (coalesced 32-byte reads, zero padding
+    // to 64 / 128 columns)
+    auto load_x = [&](int r0) {
         const int nch = ((D + 63) / 64) * 8;        // 16-byte chunks per row
         for (int i = tid; i < 128 * nch; i += SNT_THREADS) {
-            const int row = i / nch, ch = i - row * nch;
+            const int r = i / nch, ch = i - r * nch;
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            if (r0 + row < n) {
-                const float* src = x + (size_t)(r0 + row) * ldx + ch * 8;
+            if (r0 + r < n) {
+                const float* src = x + (size_t)(r0 + r) * ldx + ch * 8;
                 if (ch * 8 + 7 < D) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
                     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -129,49 +211,47 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
                     for (int j = 0; j < 8; ++j) if (ch * 8 + j < D) v[j] = __ldg(src + j);
                 }
             }
-            snt_store8(tile, row, ch, v);
+            snt_store8(tP, r, ch, v);
+            snt_store8(tQ, r, ch, v);
         }
     };
 
-    uint32_t g = 0;                              // global step counter: phase of both barriers
+    uint32_t g = 0, gb = 0;                      // step counter (phase of bar_w / bar_mma), pass-B step counter (phase of bar_mma2)
     const int tiles = (n + 127) / 128;
-    if (tid == 0 && (int)blockIdx.x < tiles) fetch_weights(0);
+    if ((int)blockIdx.x < tiles) {
+        if (tid == 0) fetch_weights(0);
+        if (warp >= 4 && warp < 8) fetch_vectors(0, 0);
+    }
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int r0 = t * 128;
-        load_x(tP, r0);
+        load_x(r0);
         fence_proxy_async();
         __syncthreads();
         float base_sum = 0.f, sap_sum = 0.f;
         for (int s = 0; s < n_steps; ++s, ++g) {
             const SntLayer& Ly = layer_of(s);
+            const int N = Ly.N, num_kb = Ly.num_kb;
+            const float mul = Ly.acc_mul;
+            const bool bn = Ly.scale != nullptr;
+            const bool stamp = P.dbg && tid == 0 && t == 0;
+            if (stamp) P.dbg[6 * s] = snt_now();
             const bool pass_b = s >= steps_a;
             const int l_b = s - steps_a + 1;                 // pass B: index of the diff this step produces
-            if (s == steps_a) {                              // pass B starts: x again (L2-hot) next to xhat
-                load_x(tQ, r0);
-                fence_proxy_async();
-            }
-            // this layer's epilogue vectors
-            if (tid < 128) {
-                const bool ok = tid < Ly.N;
-                s_vec[tid] = ok ? __ldg(Ly.bias + tid) : 0.f;
-                s_vec[128 + tid] = (ok && Ly.scale) ? __ldg(Ly.scale + tid) : 0.f;
-                s_vec[256 + tid] = (ok && Ly.scale) ? __ldg(Ly.shift + tid) : 0.f;
-            }
-            __syncthreads();
-            const int n_eff = (Ly.N + 15) & ~15;
+            const int n_eff = (N + 31) & ~31;                // MMA width: whole 32-column blocks (weight rows past N are zero)
             if (tid == 0) {
-                mbar_wait(smem_u32(bar_w), g & 1);
+                mbar_wait(bar_w, g & 1);
                 tc_fence_after();
                 const uint32_t idesc = make_idesc(n_eff, false, false);
                 for (int a = 0; a < (pass_b ? 2 : 1); ++a) {
-                    // pass A: P -> acc0.  pass B: Q (x path) -> acc0, P (xhat path) -> acc1
-                    const uint8_t* src = pass_b ? (a == 0 ? tQ : tP) : tP;
+                    // pass A: P -> acc0.  pass B: Q (x path) -> acc0, then P (xhat path) -> acc1, each with its own barrier so
+                    // that the epilogue of the x path runs under the MMAs of the xhat path
+                    const uint32_t src = pass_b ? (a == 0 ? tQ : tP) : tP;
                     const uint32_t d_tmem = tmem_base + a * 128;
-                    for (int kb = 0; kb < Ly.num_kb; ++kb) {
-                        const uint64_t dAh = make_smem_desc<false>(smem_u32(src + kb * SNT_TILE));
-                        const uint64_t dAl = make_smem_desc<false>(smem_u32(src + 2 * SNT_TILE + kb * SNT_TILE));
-                        const uint64_t dBh = make_smem_desc<false>(smem_u32(tW + kb * SNT_TILE));
-                        const uint64_t dBl = make_smem_desc<false>(smem_u32(tW + 2 * SNT_TILE + kb * SNT_TILE));
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        const uint64_t dAh = make_smem_desc<false>(src + kb * SNT_TILE);
+                        const uint64_t dAl = make_smem_desc<false>(src + 2 * SNT_TILE + kb * SNT_TILE);
+                        const uint64_t dBh = make_smem_desc<false>(tW + kb * SNT_TILE);
+                        const uint64_t dBl = make_smem_desc<false>(tW + 2 * SNT_TILE + kb * SNT_TILE);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -180,72 +260,77 @@ smallnet_tc_kernel(const __grid_constant__ SntParams P, const float* __restrict_
                             umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
                         }
                     }
+                    umma_commit(a == 0 ? bar_mma : bar_mma2);
                 }
-                umma_commit(smem_u32(bar_mma));
+                if (stamp) P.dbg[6 * s + 1] = snt_now();
             }
-            mbar_wait(smem_u32(bar_mma), g & 1);
+            // the NEXT step's vectors travel under this step's MMAs (the other buffer was last read one step ago)
+            if (warp >= 4 && warp < 8) {
+                if (s + 1 < n_steps) fetch_vectors(s + 1, (g + 1) & 1);
+                else if (t + (int)gridDim.x < tiles) fetch_vectors(0, (g + 1) & 1);
+            }
+            const uint32_t sv = s_vec + (g & 1) * 1536 + c0 * 4;
+            const int kp_next = ((N + 63) / 64) * 64;
+            const bool write_p = pass_b ? (l_b < P.last) : true;         // pass B's last layer feeds nothing
+            const bool is_xhat = !pass_b && s == steps_a - 1;
+            const bool active = c0 < kp_next;                            // warp-uniform
+            float sq = 0.f;
+            uint32_t v0[32];
+            // ---- epilogue, accumulator 0: thread (row, q) owns columns [32 q, 32 q + 32) of its row ----
+            mbar_wait(bar_mma, g & 1);
             tc_fence_after();
-            // the weight buffer is free: the next step's weights (or the next tile's first layer) travel during the epilogue
-            if (tid == 0) {
+            if (stamp) P.dbg[6 * s + 2] = snt_now();
+            if (!pass_b && tid == 0) {           // the weight buffer is free: the next weights travel during the epilogue
                 if (s + 1 < n_steps) fetch_weights(s + 1);
                 else if (t + (int)gridDim.x < tiles) fetch_weights(0);
             }
-            // ---- epilogue: thread (row, q) owns columns [32 q, 32 q + 32) of its row ----
-            const int kp_next = ((Ly.N + 63) / 64) * 64;
-            const bool write_p = pass_b ? (l_b < P.last) : true;         // pass B's last layer feeds nothing
-            const bool is_xhat = !pass_b && s == steps_a - 1;
-            const int c0 = q * 32;
-            float sq = 0.f;
-            if (c0 < kp_next) {
-                uint32_t v0[32], v1[32];
-                if (c0 < n_eff) {
-                    tmem_ld32(taddr + c0, v0);
-                    if (pass_b) tmem_ld32(taddr + 128 + c0, v1);
-                }
+            if (active) {
+                if (c0 < n_eff) tmem_ld32(taddr, v0);
+                else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = c0 + i;
-                    float a0 = 0.f, a1 = 0.f;
-                    if (c < Ly.N) {
-                        const float b = s_vec[c], sc = s_vec[128 + c], sh = s_vec[256 + c];
-                        a0 = fmaf(__uint_as_float(v0[i]), Ly.acc_mul, b);
-                        if (Ly.scale) { a0 = a0 > 0.f ? a0 : a0 * P.slope; a0 = fmaf(a0, sc, sh); }
-                        if (pass_b) {
-                            a1 = fmaf(__uint_as_float(v1[i]), Ly.acc_mul, b);
-                            if (Ly.scale) { a1 = a1 > 0.f ? a1 : a1 * P.slope; a1 = fmaf(a1, sc, sh); }
-                            const float d = a1 - a0;
-                            sq = fmaf(d, d, sq);
-                        }
-                    }
-                    v0[i] = __float_as_uint(a0); v1[i] = __float_as_uint(a1);
+                    for (int i = 0; i < 32; ++i) v0[i] = 0u;
                 }
-                if (is_xhat && r0 + row < n) {           // d_0 = xhat - x against the fp32 input
-                    const float* xr = x + (size_t)(r0 + row) * ldx;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = c0 + i;
-                        if (c < D) { const float d = __uint_as_float(v0[i]) - __ldg(xr + c); sq = fmaf(d, d, sq); }
-                    }
-                }
-                if (write_p) {
+                if (bn) snt_transform<true>(v0, sv, mul, slope); else snt_transform<false>(v0, sv, mul, slope);
+                if (is_xhat) {                   // d_0 = xhat - x (x as the hi + lo pair the first layer multiplied)
 #pragma unroll
                     for (int k8 = 0; k8 < 4; ++k8) {
-                        float o[8];
+                        float xv[8];
+                        snt_load8(tQ, row, (c0 >> 3) + k8, xv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v0[k8 * 8 + j]);
-                        snt_store8(pass_b ? tQ : tP, row, (c0 >> 3) + k8, o);
-                        if (pass_b) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v1[k8 * 8 + j]);
-                            snt_store8(tP, row, (c0 >> 3) + k8, o);
-                        }
+                        for (int j = 0; j < 8; ++j) { const float d = __uint_as_float(v0[k8 * 8 + j]) - xv[j]; sq = fmaf(d, d, sq); }
                     }
                 }
+                if (write_p) snt_store32(pass_b ? tQ : tP, row, c0, v0);
+            }
+            if (stamp) P.dbg[6 * s + 3] = snt_now();
+            // ---- pass B, accumulator 1: the xhat path and the diff ----
+            if (pass_b) {
+                mbar_wait(bar_mma2, gb & 1);
+                tc_fence_after();
+                if (tid == 0) {
+                    if (s + 1 < n_steps) fetch_weights(s + 1);
+                    else if (t + (int)gridDim.x < tiles) fetch_weights(0);
+                }
+                if (active) {
+                    uint32_t v1[32];
+                    if (c0 < n_eff) tmem_ld32(taddr + 128, v1);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v1[i] = 0u;
+                    }
+                    if (bn) snt_transform<true>(v1, sv, mul, slope); else snt_transform<false>(v1, sv, mul, slope);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(v1[i]) - __uint_as_float(v0[i]); sq = fmaf(d, d, sq); }
+                    if (write_p) snt_store32(tP, row, c0, v1);
+                }
+                ++gb;
             }
             s_sq[q * 128 + row] = sq;
+            if (stamp) P.dbg[6 * s + 4] = snt_now();
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
+            if (stamp) P.dbg[6 * s + 5] = snt_now();
             if (q == 0) {                                // the row's four column blocks, fixed order
                 const float t4 = ((s_sq[row] + s_sq[128 + row]) + s_sq[256 + row]) + s_sq[384 + row];
                 if (is_xhat) { base_sum = t4; if (P.lo == 0) sap_sum += t4; }
@@ -302,9 +387,29 @@ int smallnet_tc_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = (n + 127) / 128;
+    static const bool debug = getenv("MMAD_SNT_DEBUG") != nullptr;
+    static int debug_left = 3;
+    const bool dbg = debug && debug_left > 0;
+    if (dbg) {
+        MMAD_CUDA_OK(cudaMallocManaged(&P.dbg, 6 * 32 * sizeof(unsigned long long)));
+        memset(P.dbg, 0, 6 * 32 * sizeof(unsigned long long));
+    }
     smallnet_tc_kernel<<<std::min(tiles, sms), SNT_THREADS, SNT_SMEM, s>>>(P, d_x, ldx, n, d_base, d_sap);
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
+    if (dbg) {
+        MMAD_CUDA_OK(cudaStreamSynchronize(s));
+        const int steps = P.n_enc + P.n_dec + P.last;
+        fprintf(stderr, "smallnet_tc D=%d n=%d: per step ns [mma issue, acc0 wait, epilogue 0, epilogue 1, end sync]\n", P.D, n);
+        for (int i = 0; i < steps; ++i) {
+            const unsigned long long* q = P.dbg + 6 * i;
+            fprintf(stderr, "  step %2d: %5llu %5llu %5llu %5llu %5llu   total %llu\n", i, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3],
+                    q[5] - q[4], (i + 1 < steps ? q[6] : q[5]) - q[0]);
+        }
+        fprintf(stderr, "  tile total %llu ns\n", P.dbg[6 * (steps - 1) + 5] - P.dbg[0]);
+        cudaFree(P.dbg);
+        --debug_left;
+    }
     return MMAD_OK;
 }
 
