@@ -33,7 +33,17 @@ struct TcParams {
     int tiles_m, tiles_n;
     int tri;             // leading rows of B that are upper triangular (B[n,k] = 0 for k < n): tiles inside skip the k-blocks left of their first row
     int splits;          // split-K factor (plain epilogue only): work item = (tile, split), atomically accumulated
+    int dbg;             // MMAD_TC_DEBUG=1: CTA 0 leaves %globaltimer stamps in g_tc_stamps
 };
+
+__device__ unsigned long long g_tc_stamps[16];       // 0-7: phases of CTA 0; 8-15: end of the first tile's epilogue per epilogue warp
+__device__ __forceinline__ void tc_stamp(const TcParams& p, int i) {
+    if (p.dbg && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tc_stamps[i] = t;
+    }
+}
 
 // ---- the kernel ---------------------------------------------------------------------------------
 template <int PASSES, bool A_MN, bool B_MN, int BN>
@@ -59,6 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (threadIdx.x == 0) tc_stamp(p, 0);
     const int num_kb = (p.K + BK - 1) / BK;
     const int num_tiles = p.tiles_m * p.tiles_n * p.splits;     // work items: tile-major, split fastest
     // k-block range of split sp: [sp * num_kb / splits, (sp + 1) * num_kb / splits)  (host guarantees splits <= num_kb)
@@ -83,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tc_stamp(p, 1);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -123,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         if (PASSES == 3) load_b(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapBl);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (w == (int)blockIdx.x && kb == kb_lo) tc_stamp(p, 2);
                 }
             }
         }
@@ -144,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(smem_u32(&full[stage]), phase);
                     tc_fence_after();
+                    if (w == (int)blockIdx.x && kb == kb_lo) tc_stamp(p, 3);
                     const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
                     const uint64_t dAh = make_smem_desc<A_MN>(st);
                     const uint64_t dBh = make_smem_desc<B_MN>(st + A_TILE_BYTES);
@@ -169,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                         }
                     }
                     umma_commit(smem_u32(&empty[stage]));                        // frees the smem stage when the MMAs retire
-                    if (kb == kb_hi - 1) umma_commit(smem_u32(&acc_full[acc])); // accumulator complete
+                    if (kb == kb_hi - 1) { umma_commit(smem_u32(&acc_full[acc])); if (w == (int)blockIdx.x) tc_stamp(p, 4); }   // accumulator complete
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -181,8 +195,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int half = (warp - 2) >> 2;       // column half of the tile this warp drains (BN = 128: half 1 idles)
         const int et = threadIdx.x - 64;        // 0..255
         float4* stg = s_stage + (warp - 2) * STG_FLOAT4;
-        const int col_lo = BN == 256 ? half * 128 : 0;
-        const int col_hi = BN == 256 ? col_lo + 128 : (half == 0 ? 128 : 0);
+        // BN = 128: both warps of a lane quarter share the tile's columns 64 / 64 unless the row partial sums are wanted
+        // (their slots are 128 columns wide: one writer per slot)
+        const bool split128 = BN == 128 && e.rowpart == nullptr;
+        const int col_lo = BN == 256 ? half * 128 : (split128 ? half * 64 : 0);
+        const int col_hi = BN == 256 ? col_lo + 128 : (split128 ? col_lo + 64 : (half == 0 ? 128 : 0));
         int acc = 0; uint32_t acc_phase = 0;
         EpiVec vec;
         if (et < BN && (int)blockIdx.x < num_tiles)
@@ -201,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             }
             mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
             tc_fence_after();
+            if (threadIdx.x == 64 && w == (int)blockIdx.x) tc_stamp(p, 5);
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             float sq[8];
@@ -210,6 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc]));
             if (col_hi > col_lo && n0 + col_lo < p.N) epi_rowpart(e, p.M, row_base, (n0 + col_lo) / ROWPART_COLS, lane, sq);
+            if (threadIdx.x == 64 && w == (int)blockIdx.x) tc_stamp(p, 6);
+            if (lane == 0 && w == (int)blockIdx.x) tc_stamp(p, 6 + warp);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -220,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
+    if (threadIdx.x == 0) tc_stamp(p, 7);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -326,6 +347,10 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (K + BK - 1) / BK;
     p.splits = 1;
+    const bool debug = getenv("MMAD_TC_DEBUG") != nullptr;     // read per call: a profiling script switches it on after warm-up
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (debug) cudaStreamIsCapturing(s, &cap);
+    p.dbg = debug && cap == cudaStreamCaptureStatusNone;
     p.tri = e.b_upper_tri;     // leading rows of B that are upper triangular (tiles entirely inside skip k-blocks left of them)
     if (!p.tri && e.plain && e.split_k_ok) {
         // split-K when it fills the machine better: cost ~ waves x k-blocks per item; ties go to fewer splits
@@ -367,6 +392,18 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
 #undef MMAD_TC_LAUNCH
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
+    if (p.dbg) {
+        static unsigned long long last_end = 0;
+        unsigned long long t[16];
+        MMAD_CUDA_OK(cudaStreamSynchronize(s));
+        MMAD_CUDA_OK(cudaMemcpyFromSymbol(t, g_tc_stamps, sizeof t));
+        fprintf(stderr, "gemm_tc M=%d N=%d K=%d passes=%d A_mn=%d B_mn=%d bn=%d splits=%d grid=%d plain=%d: prologue %llu, first TMA issued +%llu, first stage "
+                "landed +%llu, last MMA issued +%llu, accumulator ready +%llu, epilogue +%llu, exit +%llu = %llu ns\n", M, N, K, passes, (int)A.mn,
+                (int)B.mn, bn, p.splits, grid, (int)e.plain, t[1] - t[0], t[2] - t[1], t[3] - t[1], t[4] - t[1], t[5] - t[1], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
+        fprintf(stderr, "    epilogue warps 2-9 done at +%llu %llu %llu %llu | %llu %llu %llu %llu after the accumulator\n", t[8] - t[5], t[9] - t[5],
+                t[10] - t[5], t[11] - t[5], t[12] - t[5], t[13] - t[5], t[14] - t[5], t[15] - t[5]);
+        last_end = t[7];
+    }
     return MMAD_OK;
 }
 

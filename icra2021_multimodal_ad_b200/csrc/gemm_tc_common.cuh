@@ -186,43 +186,104 @@ __device__ __forceinline__ void store_f8_twin(uint8_t* row, int col, float v0, f
     *reinterpret_cast<uint2*>(row + 2 * col) = t;
 }
 
-// plain store mode (rows of Y need not be 16-byte aligned: parameter-gradient tensors [N, K]): 16-column pieces,
-// half-warp <-> one row, lane <-> column: two coalesced 64-byte row segments per instruction
+__device__ __forceinline__ uint32_t stg_off32(int row16, int j8) { return (uint32_t)(row16 * 8 + (j8 ^ (row16 & 7))) * 16u; }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
+
+// plain store mode (pre-activations of the BatchNorm layers, dX, parameter gradients; with split-K the partial sums are added
+// atomically).  A train step runs ONE tile per CTA, so this epilogue is not hidden behind the next tile's MMAs: it is written
+// for latency -- 32-column blocks (one tcgen05.ld each), the transposed block re-read with every load of a phase independent
+// of the others, 16-byte stores / red.v4 when the rows of Y are 16-byte aligned.  (The first version walked 16-column pieces
+// with a dependent load -> store chain per row pair: 6-8 us per tile, 60 % of every training GEMM.)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+    return r;
+}
+
 template <int BN>
 __device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
                                                float4* stg, const float* s_mul, const float* s_bias, int lane, int col_lo,
                                                int col_hi) {
     int n_cols = N - n0; if (n_cols > BN) n_cols = BN;
-    int c_end = (n_cols + 15) & ~15;
+    int c_end = (n_cols + 31) & ~31;
     if (c_end > col_hi) c_end = col_hi;
-    for (int c0 = col_lo; c0 < c_end; c0 += 16) {
-        {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(e.Y) & 15) == 0) && (e.ldy % 4 == 0);
+    const bool atomic = splits > 1;
+    const uint32_t stg_s = smem_u32(stg), mul_s = smem_u32(s_mul), bias_s = smem_u32(s_bias);
+    for (int c0 = col_lo; c0 < c_end; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        if (vec_ok) {
+            // lane = (row in a group of 4, float4 column): 4 rows x 128 contiguous bytes per instruction
+            const int rsub = lane >> 3, cg = lane & 7;
+            const int cc = c0 + cg * 4, gc = n0 + cc;
+            const float4 mul = lds128(mul_s + cc * 4), bia = lds128(bias_s + cc * 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                stg[stg_slot(lane, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
-        __syncwarp();
-        const int c = c0 + (lane & 15);
-        const int gc = n0 + c;
-        const int rpar = lane >> 4;
-        if (gc < N) {
-            const float mulc = s_mul[c], biac = s_bias[c];
-            const float* stf = reinterpret_cast<const float*>(stg);
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int rl = i * 2 + rpar;
-                const int r = row_base + rl;
-                const float val = fmaf(stf[stg_slot(rl, (lane & 15) >> 2) * 4 + (lane & 3)], mulc, biac);
-                if (r < M) {
-                    if (splits > 1) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);   // split-K partial sums
+            for (int ph = 0; ph < 2; ++ph) {
+                if ((lane >> 4) == ph) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sts128(stg_s + stg_off32(lane & 15, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+                float4 a[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) a[it] = lds128(stg_s + stg_off32(it * 4 + rsub, cg));
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = row_base + ph * 16 + it * 4 + rsub;
+                    if (r >= M || gc >= N) continue;
+                    const float x0 = fmaf(a[it].x, mul.x, bia.x), x1 = fmaf(a[it].y, mul.y, bia.y);
+                    const float x2 = fmaf(a[it].z, mul.z, bia.z), x3 = fmaf(a[it].w, mul.w, bia.w);
+                    float* dst = e.Y + (size_t)r * e.ldy + gc;
+                    if (gc + 3 < N) {
+                        if (atomic) red_add_v4(dst, x0, x1, x2, x3);
+                        else *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+                    } else {
+                        const float xs[3] = {x0, x1, x2};
+                        for (int j = 0; j < 3 && gc + j < N; ++j) {
+                            if (atomic) atomicAdd(dst + j, xs[j]); else dst[j] = xs[j];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        } else {
+            // rows of Y are only 4-byte aligned (parameter gradients [N, K] with odd K): lane = column, one row per instruction
+            const int gc = n0 + c0 + lane;
+            const float mulc = lds32(mul_s + (c0 + lane) * 4), biac = lds32(bias_s + (c0 + lane) * 4);
+            const uint32_t rd = stg_s + (uint32_t)(lane & 3) * 4u;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                if ((lane >> 4) == ph) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sts128(stg_s + stg_off32(lane & 15, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+                float a[16];
+#pragma unroll
+                for (int rl = 0; rl < 16; ++rl) a[rl] = lds32(rd + stg_off32(rl, lane >> 2));
+#pragma unroll
+                for (int rl = 0; rl < 16; ++rl) {
+                    const int r = row_base + ph * 16 + rl;
+                    if (r >= M || gc >= N) continue;
+                    const float val = fmaf(a[rl], mulc, biac);
+                    if (atomic) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);
                     else e.Y[(size_t)r * e.ldy + gc] = val;
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
 }
 
@@ -234,16 +295,6 @@ __device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, 
 // selects, row pointers advanced by constant strides -- the epilogue is issue-bound (two warps per scheduler), so the
 // instruction count of this loop is what paces the chain layers once the MMA work drops to two passes.
 // sq[ph * 4 + it] returns this lane's partial row sum of squares for row row_base + ph*16 + it*4 + lane/8.
-__device__ __forceinline__ uint32_t stg_off32(int row16, int j8) { return (uint32_t)(row16 * 8 + (j8 ^ (row16 & 7))) * 16u; }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
-    return r;
-}
-
 struct EpiPtrs {     // per-lane pointers at (row_base + lane/8, n0 + 4 * (lane%8)); null when the output is absent
     float* Y; float* pre; float* dout; const float* ref;
     __half* Yh; uint8_t* Yl; __half* Dh; uint8_t* Dl;

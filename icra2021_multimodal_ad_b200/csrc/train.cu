@@ -253,6 +253,180 @@ __global__ void __launch_bounds__(kCT) bn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// ---- one-kernel BatchNorm for small batches (B <= 512, single rank) -----------------------------------------------
+// At B = 256 the statistics kernel and the apply kernel are each pure latency (launch + one L2 round trip + a reduction:
+// 4 - 7 us for 1.4 MB), four of them per BatchNorm layer.  Columns are independent, so a CTA that owns 16 columns over ALL
+// rows can do both: every thread keeps its RPT rows x 4 columns in registers (all loads in flight at once), the column sums
+// are reduced through shuffles (row lanes of a warp) and shared memory (warps) in a fixed order -- no atomics, no zeroed
+// accumulators -- and the normalised values are written from the registers.  Thread t: column quad t & 3, rows t >> 2 + 64 i.
+constexpr int kFB = 16;       // columns per CTA of the fused kernels
+
+template <int NS>
+__device__ __forceinline__ void fused_col_reduce(double (&s)[NS][4], double* sm /* [8][NS][kFB] */, double (&tot)[NS][4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = threadIdx.x & 3;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double v = s[k][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) sm[(warp * NS + k) * kFB + lane * 4 + j] = v;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCT / 32; ++w) t += sm[(w * NS + k) * kFB + cq * 4 + j];
+            tot[k][j] = t;
+        }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope, float eps,
+                                                           float momentum, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ run_mean,
+                                                           float* __restrict__ run_var, long long* __restrict__ nbt,
+                                                           float* __restrict__ mean_out, float* __restrict__ inv_out,
+                                                           float* __restrict__ out, int ldo, __half* __restrict__ oh,
+                                                           __half* __restrict__ ol) {
+    __shared__ double sm[(kCT / 32) * 2 * kFB];
+    const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
+    const int c0 = blockIdx.x * kFB + cq * 4;
+    const bool col_ok = c0 < N;
+    float a[RPT][4];
+    double s[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rl + 64 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && r < B) v = ld4(pre + (size_t)r * ld + c0);
+        a[i][0] = lrelu(v.x, slope); a[i][1] = lrelu(v.y, slope); a[i][2] = lrelu(v.z, slope); a[i][3] = lrelu(v.w, slope);
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[0][j] += (double)a[i][j]; s[1][j] = fma((double)a[i][j], (double)a[i][j], s[1][j]); }
+    double tot[2][4];
+    fused_col_reduce<2>(s, sm, tot);
+    if (!col_ok) return;
+    const double Bg = (double)B;
+    float m[4], iv[4], g[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        const bool ok = c < N;
+        const double md = tot[0][j] / Bg;
+        double var_b = tot[1][j] / Bg - md * md;
+        if (var_b < 0.0) var_b = 0.0;
+        m[j] = (float)md;
+        iv[j] = (float)(1.0 / sqrt(var_b + (double)eps));
+        g[j] = ok ? gamma[c] : 0.f; b[j] = ok ? beta[c] : 0.f;
+        if (ok && rl == 0) {
+            mean_out[c] = m[j];
+            inv_out[c] = iv[j];
+            if (run_mean) {
+                const double unb = Bg > 1.0 ? var_b * (Bg / (Bg - 1.0)) : var_b;
+                run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m[j];
+                run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+            }
+            if (c == 0 && nbt) *nbt += 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rl + 64 * i;
+        if (r >= B) continue;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (c0 + j < N) ? fmaf((a[i][j] - m[j]) * iv[j], g[j], b[j]) : 0.f;
+        if (out) *reinterpret_cast<float4*>(out + (size_t)r * ldo + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (oh) split4_store(o, 1.f, oh, ol, (size_t)r * ldo + c0);
+    }
+}
+
+// backward twin: s1 = sum g, s2 = sum g xhat, g_pre = gamma inv (g - s1/B - xhat s2/B) lrelu'(pre), gb = sum g_pre,
+// ggamma = s2, gbeta = s1 -- everything bn_bwd_reduce_kernel + bn_bwd_apply_kernel produce, from one read of g and pre
+template <int RPT>
+__global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre, int ld,
+                                                           int B, int N, float slope, float gscale, const float* __restrict__ mean,
+                                                           const float* __restrict__ inv, const float* __restrict__ gamma,
+                                                           float* __restrict__ gpre, int ldo, __half* __restrict__ gh,
+                                                           __half* __restrict__ gl, float twin_scale, float* __restrict__ gb,
+                                                           float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    __shared__ double sm[(kCT / 32) * 2 * kFB];
+    const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
+    const int c0 = blockIdx.x * kFB + cq * 4;
+    const bool col_ok = c0 < N;
+    float m[4], iv[4], k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = col_ok && c0 + j < N;
+        m[j] = ok ? mean[c0 + j] : 0.f;
+        iv[j] = ok ? inv[c0 + j] : 0.f;
+        k[j] = ok ? gamma[c0 + j] * iv[j] : 0.f;
+    }
+    float gv[RPT][4], xh[RPT][4];
+    unsigned pos[RPT];                   // bit j: pre > 0
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rl + 64 * i;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && r < B) { g4 = ld4(g + (size_t)r * ldg + c0); p4 = ld4(pre + (size_t)r * ld + c0); }
+        const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+        gv[i][0] = g4.x * gscale; gv[i][1] = g4.y * gscale; gv[i][2] = g4.z * gscale; gv[i][3] = g4.w * gscale;
+        pos[i] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            xh[i][j] = (lrelu(pv[j], slope) - m[j]) * iv[j];
+            pos[i] |= (pv[j] > 0.f ? 1u : 0u) << j;
+        }
+    }
+    double s[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        if (rl + 64 * i >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[0][j] += (double)gv[i][j]; s[1][j] = fma((double)gv[i][j], (double)xh[i][j], s[1][j]); }
+    }
+    double tot[2][4];
+    fused_col_reduce<2>(s, sm, tot);
+    const double Bg = (double)B;
+    float a1[4], a2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a1[j] = (float)(tot[0][j] / Bg); a2[j] = (float)(tot[1][j] / Bg);
+        if (col_ok && c0 + j < N && rl == 0) { gbeta[c0 + j] = (float)tot[0][j]; ggamma[c0 + j] = (float)tot[1][j]; }
+    }
+    double acc[1][4] = {{0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rl + 64 * i;
+        if (r >= B || !col_ok) continue;
+        float ga[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = k[j] * (gv[i][j] - a1[j] - xh[i][j] * a2[j]);
+            t = ((pos[i] >> j) & 1u) ? t : t * slope;
+            ga[j] = (c0 + j < N) ? t : 0.f;
+            acc[0][j] += (double)ga[j];
+        }
+        if (gpre) *reinterpret_cast<float4*>(gpre + (size_t)r * ldo + c0) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        if (gh) split4_store(ga, twin_scale, gh, gl, (size_t)r * ldo + c0);
+    }
+    __syncthreads();                     // the first reduction's partials have been read by everyone
+    double tb[1][4];
+    fused_col_reduce<1>(acc, sm, tb);
+    if (col_ok && rl == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c0 + j < N) gb[c0 + j] = (float)tb[0][j];
+    }
+}
+
 // gb[c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer; gb zeroed by the caller)
 __global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale,
                                                              float* __restrict__ gb, int RS) {
@@ -523,7 +697,10 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     const double Bg = (double)global_batch;
     const float slope = d.lrelu_slope;
     constexpr float GS = 16.f;       // gradients are scaled by 2^4 before the fp16 hi/lo split
-    MMAD_CUDA_OK(cudaMemsetAsync(ws + p.st_all, 0, p.st_bytes, s));
+    // one-kernel BatchNorm (statistics + apply) when one rank holds the whole batch and it fits the register tile
+    static const bool no_fuse_bn = getenv("MMAD_NO_FUSED_BN") != nullptr;
+    const bool fuse_bn = !dist && B >= 128 && B <= 512 && global_batch == (long long)B && !no_fuse_bn;   // below 128 rows the two-kernel form measured faster
+    if (!fuse_bn) MMAD_CUDA_OK(cudaMemsetAsync(ws + p.st_all, 0, p.st_bytes, s));
     MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
 
     // an activation / gradient matrix: fp32 and (tensor-core modes) fp16 hi/lo twins, same leading dimension
@@ -654,16 +831,24 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* mean = (float*)(ws + p.mean[m][i]);
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
-                bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
-                MMAD_LAUNCHED();
-                if (dist) {
-                    rc = stats_allreduce(st, 2LL * Np);
-                    if (rc) return rc;
+                if (fuse_bn) {
+#define MMAD_BN_FWD(R) bn_fwd_fused_kernel<R><<<(N + kFB - 1) / kFB, kCT, 0, s>>>(pre, Np, B, N, slope, d.bn_eps, bn_momentum, L.gamma, L.beta, \
+                           L.run_mean, L.run_var, L.num_batches_tracked, mean, inv, tc ? nullptr : out, Np, oh, ol)
+                    if (B <= 64) MMAD_BN_FWD(1); else if (B <= 128) MMAD_BN_FWD(2); else if (B <= 256) MMAD_BN_FWD(4); else MMAD_BN_FWD(8);
+#undef MMAD_BN_FWD
+                    MMAD_LAUNCHED();
+                } else {
+                    bn_fwd_stats_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, row_slab(B));
+                    MMAD_LAUNCHED();
+                    if (dist) {
+                        rc = stats_allreduce(st, 2LL * Np);
+                        if (rc) return rc;
+                    }
+                    bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
+                                                                       L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
+                                                                       tc ? nullptr : out, Np, oh, ol, row_slab(B));
+                    MMAD_LAUNCHED();
                 }
-                bn_fwd_apply_kernel<<<col_grid(N, B), kCT, 0, s>>>(pre, Np, B, N, slope, st, Np, Bg, d.bn_eps, bn_momentum, L.gamma,
-                                                                   L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv,
-                                                                   tc ? nullptr : out, Np, oh, ol, row_slab(B));
-                MMAD_LAUNCHED();
                 cur = Mat{out, oh, ol, Np};
             } else {
                 cur = Mat{pre, oh, ol, Np};
@@ -734,19 +919,27 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             __half* goh = tc ? (__half*)(ws + p.gth[idx]) : nullptr;
             __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
-            bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
-                                                                  L.gb, row_slab(B));
-            MMAD_LAUNCHED();
-            if (dist) {    // parameter gradients from the LOCAL sums, then the statistics are combined
-                bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
+            if (fuse_bn) {
+#define MMAD_BN_BWD(R) bn_bwd_fused_kernel<R><<<(r.N + kFB - 1) / kFB, kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, \
+                           tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta)
+                if (B <= 64) MMAD_BN_BWD(1); else if (B <= 128) MMAD_BN_BWD(2); else if (B <= 256) MMAD_BN_BWD(4); else MMAD_BN_BWD(8);
+#undef MMAD_BN_BWD
                 MMAD_LAUNCHED();
-                int rc = stats_allreduce(stb, 2LL * r.Np);
-                if (rc) return rc;
+            } else {
+                bn_bwd_reduce_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, stb, r.Np,
+                                                                      L.gb, row_slab(B));
+                MMAD_LAUNCHED();
+                if (dist) {    // parameter gradients from the LOCAL sums, then the statistics are combined
+                    bn_bwd_param_kernel<<<(r.N + 127) / 128, 128, 0, s>>>(stb, r.Np, r.N, L.ggamma, L.gbeta);
+                    MMAD_LAUNCHED();
+                    int rc = stats_allreduce(stb, 2LL * r.Np);
+                    if (rc) return rc;
+                }
+                bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
+                                                                     r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
+                                                                     L.gbeta, dist ? 0 : 1, row_slab(B));
+                MMAD_LAUNCHED();
             }
-            bn_bwd_apply_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, stb,
-                                                                 r.Np, Bg, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma,
-                                                                 L.gbeta, dist ? 0 : 1, row_slab(B));
-            MMAD_LAUNCHED();
             gpre = Mat{go, goh, gol, p.maxNp};
             gi ^= 1;
             gemm_scale = 1.f;
