@@ -427,6 +427,60 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
     }
 }
 
+// ---- follow-ups of the bare Linear layers at small batch --------------------------------------------------------
+// With one tile per CTA the GEMM's fused epilogue is all exposed latency (12 us for the loss epilogue of the output layer on
+// 28 CTAs with no split-K); a plain split-K GEMM plus one of these small kernels is half of that.
+// fp16 hi / lo twins of scale * src[:, :cols] (zero padded to ldh columns... up to cols_p)
+__global__ void __launch_bounds__(256) twin_split_kernel(const float* __restrict__ src, int lds, int B, int cols, int cols_p, float scale,
+                                                         __half* __restrict__ h, __half* __restrict__ l, int ldh) {
+    const int q4 = cols_p >> 2;
+    const size_t total = (size_t)B * q4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / q4), c = (int)(i % q4) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 3 < cols) {
+            const float4 t = ld4(src + (size_t)r * lds + c);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (c + j < cols) v[j] = src[(size_t)r * lds + c + j];
+        }
+        split4_store(v, scale, h, l, (size_t)r * ldh + c);
+    }
+}
+
+// output layer: d = xhat - x (fp32, zero padded to cols_p), twins of twin_scale * d, rowsum[r] = sum_c d^2.
+// One row per 128 threads.
+__global__ void __launch_bounds__(256) loss_diff_kernel(const float* __restrict__ xhat, int ldx, const float* __restrict__ ref, int ldref,
+                                                        int B, int cols, int cols_p, float* __restrict__ dout, int ldd,
+                                                        __half* __restrict__ dh, __half* __restrict__ dl, int lddh, float twin_scale,
+                                                        float* __restrict__ rowsum) {
+    __shared__ float s_part[8];
+    const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int r = blockIdx.x * 2 + half;
+    float sq = 0.f;
+    if (r < B) {
+        for (int c = t * 4; c < cols_p; c += 512) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c + 3 < cols) {
+                const float4 a = ld4(xhat + (size_t)r * ldx + c), b = ld4(ref + (size_t)r * ldref + c);
+                d[0] = a.x - b.x; d[1] = a.y - b.y; d[2] = a.z - b.z; d[3] = a.w - b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c + j < cols) d[j] = xhat[(size_t)r * ldx + c + j] - ref[(size_t)r * ldref + c + j];
+            }
+            sq = fmaf(d[0], d[0], fmaf(d[1], d[1], fmaf(d[2], d[2], fmaf(d[3], d[3], sq))));
+            *reinterpret_cast<float4*>(dout + (size_t)r * ldd + c) = make_float4(d[0], d[1], d[2], d[3]);
+            if (dh) split4_store(d, twin_scale, dh, dl, (size_t)r * lddh + c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (t == 0 && r < B) rowsum[r] = ((s_part[half * 4] + s_part[half * 4 + 1]) + s_part[half * 4 + 2]) + s_part[half * 4 + 3];
+}
+
 // gb[c] += scale * sum_r g[r,c]   (bias gradient of a bare Linear layer; gb zeroed by the caller)
 __global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale,
                                                              float* __restrict__ gb, int RS) {
@@ -543,7 +597,24 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamA
                        reinterpret_cast<uintptr_t>(v)) & 15) == 0;
     if (vec) {      // 16-byte accesses: four independent element updates per thread per iteration
         const long long end4 = base + ((end - base) & ~3LL);
-        for (long long i = base + threadIdx.x * 4LL; i < end4; i += blockDim.x * 4LL) {
+        // two groups per thread per trip, all eight loads issued before the first update: the kernel is one pass over
+        // 7 x 4 bytes per parameter and lives on the number of bytes in flight
+        const long long stride = blockDim.x * 4LL;
+        long long i = base + threadIdx.x * 4LL;
+        for (; i + stride < end4; i += 2 * stride) {
+            float4 pv0 = *reinterpret_cast<const float4*>(p + i), pv1 = *reinterpret_cast<const float4*>(p + i + stride);
+            const float4 gr0 = *reinterpret_cast<const float4*>(g + i), gr1 = *reinterpret_cast<const float4*>(g + i + stride);
+            float4 mv0 = *reinterpret_cast<const float4*>(m + i), mv1 = *reinterpret_cast<const float4*>(m + i + stride);
+            float4 vv0 = *reinterpret_cast<const float4*>(v + i), vv1 = *reinterpret_cast<const float4*>(v + i + stride);
+            pv0.x = upd(pv0.x, gr0.x, mv0.x, vv0.x); pv0.y = upd(pv0.y, gr0.y, mv0.y, vv0.y);
+            pv0.z = upd(pv0.z, gr0.z, mv0.z, vv0.z); pv0.w = upd(pv0.w, gr0.w, mv0.w, vv0.w);
+            pv1.x = upd(pv1.x, gr1.x, mv1.x, vv1.x); pv1.y = upd(pv1.y, gr1.y, mv1.y, vv1.y);
+            pv1.z = upd(pv1.z, gr1.z, mv1.z, vv1.z); pv1.w = upd(pv1.w, gr1.w, mv1.w, vv1.w);
+            *reinterpret_cast<float4*>(m + i) = mv0; *reinterpret_cast<float4*>(m + i + stride) = mv1;
+            *reinterpret_cast<float4*>(v + i) = vv0; *reinterpret_cast<float4*>(v + i + stride) = vv1;
+            *reinterpret_cast<float4*>(p + i) = pv0; *reinterpret_cast<float4*>(p + i + stride) = pv1;
+        }
+        for (; i < end4; i += stride) {
             float4 pv = *reinterpret_cast<const float4*>(p + i);
             const float4 gr = *reinterpret_cast<const float4*>(g + i);
             float4 mv = *reinterpret_cast<const float4*>(m + i);
@@ -701,6 +772,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     static const bool no_fuse_bn = getenv("MMAD_NO_FUSED_BN") != nullptr;
     const bool fuse_bn = !dist && B >= 128 && B <= 512 && global_batch == (long long)B && !no_fuse_bn;   // below 128 rows the two-kernel form measured faster
     if (!fuse_bn) MMAD_CUDA_OK(cudaMemsetAsync(ws + p.st_all, 0, p.st_bytes, s));
+    else if (vib) MMAD_CUDA_OK(cudaMemsetAsync(ws + p.kl, 0, 8, s));        // the KL accumulator shares that region
     MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
 
     // an activation / gradient matrix: fp32 and (tensor-core modes) fp16 hi/lo twins, same leading dimension
@@ -775,6 +847,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         }
     }
     const int loss_tile_n = tc ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
+    int loss_slots = 0;               // > 0: the loss follow-up kernel wrote whole-row sums
     for (int m = 0; m < 2; ++m) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
@@ -816,10 +889,27 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             if (tc) {
                 const LayerView lv = handle_layer(h, m, i);
                 e.acc_scale = 1.f / lv.wscale;
-                if (bn && !(B >= 2048 && tc2_available())) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
-                    e.pre = nullptr; e.Y = pre; e.ldy = Np; e.y_cols = N; e.plain = 1; e.split_k_ok = 1; e.pre_zeroed = 1;
+                const bool small = !(B >= 2048 && tc2_available());
+                if (small) {   // trivial epilogue (bias + store): plain mode, split-K when the tile count is small
+                    Epilogue pe;
+                    pe.bias = L.b; pe.slope = slope; pe.acc_scale = e.acc_scale;
+                    pe.Y = pre; pe.ldy = Np; pe.y_cols = N; pe.plain = 1; pe.split_k_ok = 1; pe.pre_zeroed = 1;
+                    rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, pe, s);
+                    if (!rc && !bn && !last) {       // twins of the bare Linear output for the next layer
+                        twin_split_kernel<<<ew_grid((size_t)B * Np / 4), 256, 0, s>>>(pre, Np, B, N, Np, 1.f, oh, ol, Np);
+                        MMAD_LAUNCHED();
+                    }
+                    if (!rc && last) {               // d = xhat - x, its twins (x 2 GS), row sums of d^2
+                        const int li = d.n_enc + d.n_dec - 1;
+                        loss_diff_kernel<<<(B + 1) / 2, 256, 0, s>>>(pre, Np, xref, ldxref, B, N, Np, (float*)(ws + p.g[0]), p.maxNp,
+                                                                     (__half*)(ws + p.gth[li]), (__half*)(ws + p.gtl[li]), p.maxNp, 2.f * GS,
+                                                                     (float*)(ws + p.rowpart));
+                        MMAD_LAUNCHED();
+                        loss_slots = 1;
+                    }
+                } else {
+                    rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e, s);
                 }
-                rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, e, s);
             } else {
                 GemmShape g;
                 g.M = B; g.N = N; g.K = K; g.A = cur.f; g.lda = cur.ld; g.B = L.W; g.ldb = K;
@@ -856,7 +946,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         }
     }
     {   // loss = sum d^2 (+ beta KL)
-        const int slots = (D + loss_tile_n - 1) / loss_tile_n;
+        const int slots = loss_slots ? loss_slots : (D + loss_tile_n - 1) / loss_tile_n;
         int rc = reduce_sum_all((const float*)(ws + p.rowpart), B, B, 0, slots, d_loss, s);
         if (rc) return rc;
         if (vib) {
@@ -989,12 +1079,19 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 const LayerView lv = handle_layer(h, r.m, r.i);
                 e.y_cols = np_of(r.K);
                 e.acc_scale = 1.f / (GS * lv.wscale);
-                if (!prev.bn) {   // the consumer is a bare Linear: it needs the twins of g_pre = g_in directly
+                const bool small = !(B >= 2048 && tc2_available());
+                if (!prev.bn && !small) {   // the consumer is a bare Linear: it needs the twins of g_pre = g_in directly
                     e.Yh = (__half*)(ws + p.gth[idx - 1]); e.Yl = (__half*)(ws + p.gtl[idx - 1]); e.ldh = p.maxNp; e.y_split_scale = GS;
                 } else {
                     e.plain = 1; e.split_k_ok = 1; e.y_cols = r.K;
                 }
                 rc = tc_gemm(gpre.h, gpre.l, gpre.ld, false, lv.Wh, lv.Wl, lv.Kp, true, B, r.K, r.N, e, s);
+                if (!rc && !prev.bn && small) {   // small batch: plain split-K GEMM, twins by a follow-up kernel
+                    const int Kq = np_of(r.K);
+                    twin_split_kernel<<<ew_grid((size_t)B * Kq / 4), 256, 0, s>>>(gout, p.maxNp, B, r.K, Kq, GS, (__half*)(ws + p.gth[idx - 1]),
+                                                                               (__half*)(ws + p.gtl[idx - 1]), p.maxNp);
+                    MMAD_LAUNCHED();
+                }
             } else {
                 GemmShape g;
                 g.M = B; g.N = r.K; g.K = r.N;

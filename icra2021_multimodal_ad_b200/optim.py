@@ -46,6 +46,15 @@ class Adam(torch.optim.Optimizer):
             self._tables[gi] = st
         return st
 
+    def zero_grad(self, set_to_none: bool = True):
+        """torch.optim.Optimizer.zero_grad without the profiler scope and foreach bookkeeping (30 us of host time in front
+        of every step's launch for 36 parameters)."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        for group in self.param_groups:
+            for p in group["params"]:
+                p.grad = None
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
