@@ -146,6 +146,8 @@ struct SplitMulti {
 // 16-byte aligned (K odd), so the loads are scalar -- consecutive lanes still read consecutive 16-byte groups.
 // (One element per thread with a 64-bit div/mod each cost 34 us for the 5.1 M weights of the benchmark model: 6 % of a step.)
 __global__ void __launch_bounds__(256) split_weights_multi_kernel(const __grid_constant__ SplitMulti a) {
+    pdl_trigger();
+    pdl_wait();
     int t = 0;
     while (t + 1 < a.n && (int)blockIdx.x >= a.block_start[t + 1]) ++t;
     const int Kp = a.Kp[t], K = a.K[t], q4 = Kp >> 2;
@@ -236,6 +238,8 @@ __global__ void finalize_scores_warp_kernel(const float* __restrict__ part, int 
 __global__ void reduce_sum_all_kernel(const float* __restrict__ part, int stride, int n, int s_lo, int s_hi,
                                       float* __restrict__ acc) {
     // double accumulation inside the block, one atomic per block
+    pdl_trigger();
+    pdl_wait();
     double a = 0.0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
         for (int s = s_lo; s < s_hi; ++s) a += (double)part[(size_t)s * stride + r];
@@ -442,7 +446,7 @@ int split_weights_multi(int n, const float* const* W, const int* N, const int* K
         blocks += (int)(((size_t)N[t] * Kp[t] + 4095) / 4096);
     }
     a.block_start[n] = blocks;
-    split_weights_multi_kernel<<<blocks, 256, 0, s>>>(a);
+    MMAD_CUDA_OK(launch_k(split_weights_multi_kernel, dim3(blocks), dim3(256), 0, s, a));
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;
@@ -486,7 +490,7 @@ int reduce_sum_all(const float* rowpart, int stride, int n, int slot_lo, int slo
     if (n <= 0) return MMAD_OK;
     int g = (n + 255) / 256;
     if (g > 64) g = 64;
-    reduce_sum_all_kernel<<<g, 256, 0, s>>>(rowpart, stride, n, slot_lo, slot_hi, acc);
+    MMAD_CUDA_OK(launch_k(reduce_sum_all_kernel, dim3(g), dim3(256), 0, s, rowpart, stride, n, slot_lo, slot_hi, acc));
     MMAD_LAUNCHED();
     MMAD_CUDA_OK(cudaGetLastError());
     return MMAD_OK;

@@ -69,6 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    pdl_trigger();
     if (threadIdx.x == 0) tc_stamp(p, 0);
     const int num_kb = (p.K + BK - 1) / BK;
     const int num_tiles = p.tiles_m * p.tiles_n * p.splits;     // work items: tile-major, split fastest
@@ -94,6 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above ran under the previous kernel's tail (PDL launches); global memory from here on
     if (threadIdx.x == 0) tc_stamp(p, 1);
 
     if (warp == 0) {
@@ -368,8 +370,8 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (A.mn && !B.mn) { set_error("gemm_tc: MN-major A with K-major B is not instantiated"); return MMAD_E_UNSUPPORTED; }
 #define MMAD_TC_LAUNCH2(P, AM, BMN, BNV)                                                                              \
-    gemm_tc_kernel<P, AM, BMN, BNV><<<grid, NTHREADS, Cfg<P, BNV>::kSmemBytes, s>>>(A.hi, P >= 2 ? A.lo : A.hi, B.hi, \
-                                                                                   P >= 3 ? B.lo : B.hi, p, e)
+    MMAD_CUDA_OK(launch_k(gemm_tc_kernel<P, AM, BMN, BNV>, dim3(grid), dim3(NTHREADS), Cfg<P, BNV>::kSmemBytes, s, A.hi, P >= 2 ? A.lo : A.hi, B.hi, \
+                          P >= 3 ? B.lo : B.hi, p, e))
 #define MMAD_TC_LAUNCH(P, AM, BMN)                  \
     do {                                            \
         if (bn == 256) MMAD_TC_LAUNCH2(P, AM, BMN, 256); \

@@ -14,6 +14,7 @@ namespace mmad {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+thread_local bool g_pdl = false;
 
 void set_error(const char* fmt, ...) {
     va_list ap;

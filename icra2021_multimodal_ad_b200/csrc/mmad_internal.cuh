@@ -37,6 +37,37 @@ struct NvtxScope {
     NvtxScope& operator=(const NvtxScope&) = delete;
 };
 
+// Programmatic dependent launch (PDL).  A train step at B = 256 is ~55 dependent kernels of 3-6 us: the launch latency
+// between two of them and the next kernel's prologue (barrier init, TMEM allocation, tensor-map fetch) are a third of the
+// step.  Kernels launched through launch_k while a PdlScope is active carry the programmatic-stream-serialization
+// attribute: their CTAs may become resident while the previous kernel is still running, and they call pdl_wait() before
+// touching any global memory (it returns when the previous grid has completed and its writes are visible).  Every kernel
+// signals pdl_trigger() at its start.  Only kernels that contain pdl_wait() may be launched through launch_k.
+extern thread_local bool g_pdl;
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
+    ~PdlScope() { g_pdl = prev; }
+    PdlScope(const PdlScope&) = delete;
+    PdlScope& operator=(const PdlScope&) = delete;
+};
+template <typename... KA, typename... A>
+inline cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    if (g_pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 

@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
                                                            float* __restrict__ out, int ldo, __half* __restrict__ oh,
                                                            __half* __restrict__ ol) {
     __shared__ double sm[(kCT / 32) * 2 * kFB];
+    pdl_trigger();
+    pdl_wait();
     const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
     const int c0 = blockIdx.x * kFB + cq * 4;
     const bool col_ok = c0 < N;
@@ -359,6 +361,8 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
                                                            __half* __restrict__ gl, float twin_scale, float* __restrict__ gb,
                                                            float* __restrict__ ggamma, float* __restrict__ gbeta) {
     __shared__ double sm[(kCT / 32) * 2 * kFB];
+    pdl_trigger();
+    pdl_wait();
     const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
     const int c0 = blockIdx.x * kFB + cq * 4;
     const bool col_ok = c0 < N;
@@ -433,6 +437,8 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
 // fp16 hi / lo twins of scale * src[:, :cols] (zero padded to ldh columns... up to cols_p)
 __global__ void __launch_bounds__(256) twin_split_kernel(const float* __restrict__ src, int lds, int B, int cols, int cols_p, float scale,
                                                          __half* __restrict__ h, __half* __restrict__ l, int ldh) {
+    pdl_trigger();
+    pdl_wait();
     const int q4 = cols_p >> 2;
     const size_t total = (size_t)B * q4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -456,6 +462,8 @@ __global__ void __launch_bounds__(256) loss_diff_kernel(const float* __restrict_
                                                         __half* __restrict__ dh, __half* __restrict__ dl, int lddh, float twin_scale,
                                                         float* __restrict__ rowsum) {
     __shared__ float s_part[8];
+    pdl_trigger();
+    pdl_wait();
     const int half = threadIdx.x >> 7, t = threadIdx.x & 127;
     const int r = blockIdx.x * 2 + half;
     float sq = 0.f;
@@ -485,6 +493,8 @@ __global__ void __launch_bounds__(256) loss_diff_kernel(const float* __restrict_
 __global__ void __launch_bounds__(kCT) col_sum_scaled_kernel(const float* __restrict__ g, int ldg, int B, int N, float scale,
                                                              float* __restrict__ gb, int RS) {
     __shared__ double sm[(kCT / 32) * 1 * kCB];
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = blockIdx.x * kCB + lane * 4;
     const int r_lo = blockIdx.y * RS, r_hi = min(B, r_lo + RS);
@@ -650,6 +660,8 @@ struct TrainPlan {
     size_t st_all = 0, st_bytes = 0;
     size_t pre_all = 0, pre_bytes = 0;
     size_t g[2] = {0, 0};                      // gradient ping-pong [B, maxNp]
+    size_t gz[2 * MMAD_MAX_LAYERS] = {0};      // B <= 512 (tensor-core path): one input-gradient buffer per layer inside the zeroed region,
+    bool has_gz = false;                       // so the split-K dX GEMMs need no memset node between the kernels of the step
     size_t z = 0, genc = 0, eps = 0;           // VIB: sampled code, gradient wrt the encoder output, staged noise
     size_t rowpart = 0;
     size_t kl = 0;
@@ -686,6 +698,10 @@ TrainPlan make_train_plan(const mmad_desc_t& d, int B, bool tc) {
         const int n = m == 0 ? d.n_enc : d.n_dec;
         const int* w = m == 0 ? d.enc_widths : d.dec_widths;
         for (int i = 0; i < n; ++i) p.pre[m][i] = take((size_t)B * np_of(w[i + 1]) * 4);
+    }
+    if (tc && B <= 512) {
+        for (int i = 0; i < d.n_enc + d.n_dec; ++i) p.gz[i] = take((size_t)B * maxNp * 4);
+        p.has_gz = true;
     }
     p.pre_bytes = off - p.pre_all;
     for (int m = 0; m < 2; ++m) {
@@ -836,16 +852,20 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 if (i < n - 1) { span(Ls[i].ggamma, lv.N); span(Ls[i].gbeta, lv.N); }
             }
         }
-        int rc = split_weights_multi(nt, Wp, Ns, Ks, Kps, wscale, Whp, Wlp, s);
-        if (rc) return rc;
         // split-K outputs start from zero: the pre-activation buffers (contiguous) and, when ALL gradient tensors
-        // tile one flat buffer exactly (they do in the Python layer), that buffer -- two memsets instead of one per GEMM
+        // tile one flat buffer exactly (they do in the Python layer), that buffer -- two memsets instead of one per GEMM.
+        // All memsets come first: from here on the step is an unbroken chain of kernels (programmatic dependent launches).
         MMAD_CUDA_OK(cudaMemsetAsync(ws + p.pre_all, 0, p.pre_bytes, s));
         if (g_hi - g_lo <= g_sum + 12 * (size_t)g_cnt) {      // the gradient tensors tile one buffer (gaps < 16 B are alignment padding)
             MMAD_CUDA_OK(cudaMemsetAsync(reinterpret_cast<void*>(g_lo), 0, g_hi - g_lo, s));
             gw_zeroed = true;
         }
+        int rc = split_weights_multi(nt, Wp, Ns, Ks, Kps, wscale, Whp, Wlp, s);
+        if (rc) return rc;
     }
+    // programmatic dependent launches for the kernels of the main stream from here on (mmad_internal.cuh)
+    static const bool no_pdl = getenv("MMAD_NO_PDL") != nullptr;
+    PdlScope pdl_scope(tc && !no_pdl);
     const int loss_tile_n = tc ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
     int loss_slots = 0;               // > 0: the loss follow-up kernel wrote whole-row sums
     for (int m = 0; m < 2; ++m) {
@@ -896,14 +916,14 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                     pe.Y = pre; pe.ldy = Np; pe.y_cols = N; pe.plain = 1; pe.split_k_ok = 1; pe.pre_zeroed = 1;
                     rc = tc_gemm(cur.h, cur.l, cur.ld, false, lv.Wh, lv.Wl, lv.Kp, false, B, N, K, pe, s);
                     if (!rc && !bn && !last) {       // twins of the bare Linear output for the next layer
-                        twin_split_kernel<<<ew_grid((size_t)B * Np / 4), 256, 0, s>>>(pre, Np, B, N, Np, 1.f, oh, ol, Np);
+                        MMAD_CUDA_OK(launch_k(twin_split_kernel, dim3(ew_grid((size_t)B * Np / 4)), dim3(256), 0, s, pre, Np, B, N, Np, 1.f, oh, ol, Np));
                         MMAD_LAUNCHED();
                     }
                     if (!rc && last) {               // d = xhat - x, its twins (x 2 GS), row sums of d^2
                         const int li = d.n_enc + d.n_dec - 1;
-                        loss_diff_kernel<<<(B + 1) / 2, 256, 0, s>>>(pre, Np, xref, ldxref, B, N, Np, (float*)(ws + p.g[0]), p.maxNp,
-                                                                     (__half*)(ws + p.gth[li]), (__half*)(ws + p.gtl[li]), p.maxNp, 2.f * GS,
-                                                                     (float*)(ws + p.rowpart));
+                        MMAD_CUDA_OK(launch_k(loss_diff_kernel, dim3((B + 1) / 2), dim3(256), 0, s, pre, Np, xref, ldxref, B, N, Np, (float*)(ws + p.g[0]),
+                                              p.maxNp, (__half*)(ws + p.gth[li]), (__half*)(ws + p.gtl[li]), p.maxNp, 2.f * GS,
+                                              (float*)(ws + p.rowpart)));
                         MMAD_LAUNCHED();
                         loss_slots = 1;
                     }
@@ -922,8 +942,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
                 if (fuse_bn) {
-#define MMAD_BN_FWD(R) bn_fwd_fused_kernel<R><<<(N + kFB - 1) / kFB, kCT, 0, s>>>(pre, Np, B, N, slope, d.bn_eps, bn_momentum, L.gamma, L.beta, \
-                           L.run_mean, L.run_var, L.num_batches_tracked, mean, inv, tc ? nullptr : out, Np, oh, ol)
+#define MMAD_BN_FWD(R) MMAD_CUDA_OK(launch_k(bn_fwd_fused_kernel<R>, dim3((N + kFB - 1) / kFB), dim3(kCT), 0, s, pre, Np, B, N, slope, d.bn_eps, bn_momentum, \
+                           L.gamma, L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv, tc ? nullptr : out, Np, oh, ol))
                     if (B <= 64) MMAD_BN_FWD(1); else if (B <= 128) MMAD_BN_FWD(2); else if (B <= 256) MMAD_BN_FWD(4); else MMAD_BN_FWD(8);
 #undef MMAD_BN_FWD
                     MMAD_LAUNCHED();
@@ -989,12 +1009,13 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     // ------------------------------- backward -------------------------------
     // g (ping) holds d = xhat - x in fp32 (and 2 d GS as twins); dL/dxhat = 2 d enters through gscale
     int gi = 0;
+    const float* gcur = (const float*)(ws + p.g[0]);     // fp32 gradient entering the current layer
     float gscale = 2.f;
     for (int idx = (int)order.size() - 1; idx >= 0; --idx) {
         const Ref& r = order[idx];
         const mmad_train_layer_t& L = *r.L;
         double* st = (double*)(ws + p.st[r.m][r.i]);
-        Mat gin{(const float*)(ws + p.g[gi]), tc ? (const __half*)(ws + p.gth[idx]) : nullptr,
+        Mat gin{gcur, tc ? (const __half*)(ws + p.gth[idx]) : nullptr,
                 tc ? (const __half*)(ws + p.gtl[idx]) : nullptr, p.maxNp};
         if (vib && r.m == 0 && r.i == d.n_enc - 1)
             gin = Mat{(const float*)(ws + p.genc), tc ? (const __half*)(ws + p.gench) : nullptr,
@@ -1010,8 +1031,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
             if (fuse_bn) {
-#define MMAD_BN_BWD(R) bn_bwd_fused_kernel<R><<<(r.N + kFB - 1) / kFB, kCT, 0, s>>>(gin.f, gin.ld, pre, r.Np, B, r.N, slope, gscale, mean, inv, L.gamma, \
-                           tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta)
+#define MMAD_BN_BWD(R) MMAD_CUDA_OK(launch_k(bn_bwd_fused_kernel<R>, dim3((r.N + kFB - 1) / kFB), dim3(kCT), 0, s, gin.f, gin.ld, pre, r.Np, B, r.N, slope, \
+                           gscale, mean, inv, L.gamma, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta))
                 if (B <= 64) MMAD_BN_BWD(1); else if (B <= 128) MMAD_BN_BWD(2); else if (B <= 256) MMAD_BN_BWD(4); else MMAD_BN_BWD(8);
 #undef MMAD_BN_BWD
                 MMAD_LAUNCHED();
@@ -1034,8 +1055,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             gi ^= 1;
             gemm_scale = 1.f;
         } else {
-            MMAD_CUDA_OK(cudaMemsetAsync(L.gb, 0, (size_t)r.N * 4, s));
-            col_sum_scaled_kernel<<<col_grid(r.N, B), kCT, 0, s>>>(gin.f, gin.ld, B, r.N, gscale, L.gb, row_slab(B));
+            if (!gw_zeroed) MMAD_CUDA_OK(cudaMemsetAsync(L.gb, 0, (size_t)r.N * 4, s));      // (else: inside the flat buffer zeroed at step start)
+            MMAD_CUDA_OK(launch_k(col_sum_scaled_kernel, col_grid(r.N, B), dim3(kCT), 0, s, gin.f, gin.ld, B, r.N, gscale, L.gb, row_slab(B)));
             MMAD_LAUNCHED();
         }
         {   // gW[N,K] = g_pre^T in
@@ -1053,7 +1074,10 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                     sw = s2;
                     forked = true;
                 }
-                rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e, sw);
+                {
+                    PdlScope side(sw == s ? g_pdl : false);      // second stream: ordinary (event) dependencies
+                    rc = tc_gemm(gpre.h, gpre.l, gpre.ld, true, r.in.h, r.in.l, r.in.ld, true, r.N, r.K, B, e, sw);
+                }
                 // the module's last weight gradient is queued: its bucket follows on the same stream (the fork event above is
                 // behind every bias / BatchNorm gradient of the module, which are computed on the main stream)
                 if (!rc && grad_ar && r.i == 0) rc = module_grad_allreduce(r.m, sw);
@@ -1071,9 +1095,11 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
         if (idx > 0) {   // g_in[B,K] = g_pre W
             const bool into_vib = vib && r.m == 1 && r.i == 0;
             const Ref& prev = order[idx - 1];
-            float* gout = (float*)(ws + p.g[gi ^ 1]);
+            const bool use_gz = tc && p.has_gz;
+            float* gout = use_gz ? (float*)(ws + p.gz[idx]) : (float*)(ws + p.g[gi ^ 1]);
             Epilogue e;
             e.Y = gout; e.ldy = p.maxNp;
+            if (use_gz) e.pre_zeroed = 1;
             int rc;
             if (tc) {
                 const LayerView lv = handle_layer(h, r.m, r.i);
@@ -1088,8 +1114,8 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 rc = tc_gemm(gpre.h, gpre.l, gpre.ld, false, lv.Wh, lv.Wl, lv.Kp, true, B, r.K, r.N, e, s);
                 if (!rc && !prev.bn && small) {   // small batch: plain split-K GEMM, twins by a follow-up kernel
                     const int Kq = np_of(r.K);
-                    twin_split_kernel<<<ew_grid((size_t)B * Kq / 4), 256, 0, s>>>(gout, p.maxNp, B, r.K, Kq, GS, (__half*)(ws + p.gth[idx - 1]),
-                                                                               (__half*)(ws + p.gtl[idx - 1]), p.maxNp);
+                    MMAD_CUDA_OK(launch_k(twin_split_kernel, dim3(ew_grid((size_t)B * Kq / 4)), dim3(256), 0, s, (const float*)gout, p.maxNp, B, r.K, Kq, GS,
+                                          (__half*)(ws + p.gth[idx - 1]), (__half*)(ws + p.gtl[idx - 1]), p.maxNp));
                     MMAD_LAUNCHED();
                 }
             } else {
@@ -1103,6 +1129,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             }
             if (rc) return rc;
             gi ^= 1;
+            gcur = gout;
             if (into_vib) {
                 vib_train_bwd_kernel<<<ew_grid((size_t)B * dec_in), 256, 0, s>>>(gout, p.maxNp, (const float*)(ws + p.pre[0][prev.i]), prev.Np,
                                                                                  B, dec_in, d_eps, beta_kl, (float*)(ws + p.genc), np_of(enc_out),

@@ -80,8 +80,9 @@ def test_against_oracle_ragged_and_edges(precision):
     wide = torch.rand(100, D + 7, device="cuda")      # > 64 rows: both calls take the same kernel family
     o1 = eng.score(wide[:, :D], 0, nl + 1)["sap"]
     o2 = eng.score(wide[:, :D].contiguous(), 0, nl + 1)["sap"]
-    if precision == "fp32":      # aligned rows of a model this narrow take the fused whole-chain kernel, the strided view the per-layer ones
-        assert torch.allclose(o1, o2, rtol=1e-5, atol=0)
+    if precision in ("fp32", "f16x3"):      # aligned rows of a model this narrow take the fused whole-chain kernels, the strided view the per-layer ones
+        rel = float(((o1 - o2).abs() / o2.abs()).max())
+        assert rel < (5e-5 if precision == "f16x3" else 1e-5), rel
     else:
         assert torch.equal(o1, o2)
     # determinism
