@@ -89,6 +89,8 @@ SIGNATURES = {
     "mmad_peer_open": (_i, [_vp, _vp, _i, _i]),
     "mmad_peer_close": (_i, [_vp]),
     "mmad_peer_allreduce_f64": (_i, [_vp, _vp, _ll, _vp]),
+    "mmad_peer_grad_alloc": (_i, [_vp, _ll, _vp, _vp]),
+    "mmad_peer_grad_open": (_i, [_vp, _vp]),
     "mmad_multisensory_width": (_i, [_i, _i, _i, _i]),
     "mmad_multisensory_forward": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(FeatureWeights), C.POINTER(C.c_float), _vp, _i, _vp]),
     "mmad_profile_begin": (_i, [_vp]),

@@ -77,6 +77,8 @@ int comm_allreduce(mmad_t h, void* d_buf, long long count, bool f64, cudaStream_
     if (world <= 1 || count <= 0) return MMAD_OK;
     // small fp64 vectors (BatchNorm statistics, NAP column sums): one-kernel exchange over NVLink peer memory when it is open
     if (f64 && count <= peer_max_doubles() && peer_ready(h)) return peer_allreduce_f64(h, static_cast<double*>(d_buf), count, s);
+    // the flat gradient buffer, when it is the library-owned peer-mapped one: in-place sum over NVLink peer memory
+    if (!f64 && peer_grads_match(h, d_buf, count)) return peer_allreduce_grads(h, s);
     if (!comm) { set_error("no communicator (mmad_comm_init)"); return MMAD_E_STATE; }
     return nccl_ok(g_nccl.all_reduce(d_buf, d_buf, (size_t)count, f64 ? kNcclFloat64 : kNcclFloat32, kNcclSum, comm, s), "ncclAllReduce");
 }

@@ -214,6 +214,80 @@ void peer_state_free(void* state);
 bool peer_ready(mmad_t h);
 int peer_max_doubles();
 int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s);
+bool peer_grads_match(mmad_t h, const void* d_buf, long long count);
+int peer_allreduce_grads(mmad_t h, cudaStream_t s);
+
+// Every rank's exchange buffer as mapped by this rank (cudaIpc), [2 sets][world slots][2 * kPeerMaxDoubles] (data, tag) pairs
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerMaxDoubles = 4096;                 // 2 x the widest BatchNorm layer (padded) fits with room to spare
+struct PeerPtrs {
+    uint2* buf[kPeerMaxWorld];
+    int world, rank;
+};
+// kernel arguments of an exchange fused into another kernel (peer_exchange_cta): false when the peer buffers are not open
+bool peer_kernel_args(mmad_t h, PeerPtrs* ptrs, unsigned long long** seq_ctr, unsigned int** done_ctr);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint2 peer_ld(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_st(uint2* p, uint32_t data, uint32_t seq) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
+}
+
+// All-reduce (sum over ranks, rank order, fp64) of NV <= 64 doubles held in shared memory by ONE CTA, as part of a grid-wide
+// exchange in which every CTA of the grid does the same for its own elements: CTA-local element e is element elem_of(e) of the
+// exchange vector.  Protocol of peer.cu: each value travels as two 8-byte (32 data bits, tag) pairs into the sender's slot of
+// EVERY rank's buffer, the receiver polls its own buffer; the tag is the exchange's sequence number + 1, the buffer set its
+// parity.  The CTA that finishes last advances the sequence number (all CTAs have read it by then).  Call with all threads of
+// the CTA (>= 2 * NV threads); `vals` holds the local sums on entry and the global sums on return.
+template <int NV, typename ElemOf>
+__device__ __forceinline__ void peer_exchange_cta(const PeerPtrs& P, unsigned long long* seq_ctr, unsigned int* done_ctr, double* vals,
+                                                  ElemOf elem_of) {
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_ctr);
+    const uint32_t tag = (uint32_t)seq + 1u;
+    const size_t set = (size_t)(seq & 1) * P.world * (2 * kPeerMaxDoubles);
+    const int t = threadIdx.x;
+    if (t < 2 * NV) {
+        const int e = t >> 1, part = t & 1;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[e]);
+        const uint32_t w = part ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+        const size_t off = set + (size_t)P.rank * (2 * kPeerMaxDoubles) + 2 * (size_t)elem_of(e) + part;
+        for (int r = 0; r < P.world; ++r) peer_st(P.buf[r] + off, w, tag);
+    }
+    __syncthreads();            // every thread has read vals[]
+    if (t < NV) {
+        const uint2* mine = P.buf[P.rank] + set + 2 * (size_t)elem_of(t);
+        const long long t0 = clock64();
+        double sum = 0.0;
+        for (int r = 0; r < P.world; ++r) {
+            const uint2* q = mine + (size_t)r * (2 * kPeerMaxDoubles);
+            uint2 a = peer_ld(q), b = peer_ld(q + 1);
+            while (a.y != tag || b.y != tag) {
+                if (clock64() - t0 > 4000000000LL) {
+                    printf("mmad fused exchange: rank %d never received element %d of rank %d (exchange %llu)\n", P.rank, elem_of(t), r, seq);
+                    __trap();
+                }
+                if (a.y != tag) a = peer_ld(q);
+                if (b.y != tag) b = peer_ld(q + 1);
+            }
+            sum += __longlong_as_double((long long)(((unsigned long long)b.x << 32) | a.x));
+        }
+        vals[t] = sum;
+    }
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(done_ctr, 1u) + 1u == gridDim.x) {
+            *done_ctr = 0;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long*>(seq_ctr) = seq + 1;
+        }
+    }
+}
+#endif
 
 // NCCL communicator of a handle (comm.cu)
 void handle_comm(mmad_t h, void** comm, int* world);

@@ -20,14 +20,7 @@ namespace mmad {
 
 namespace {
 
-constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerMaxDoubles = 4096;                 // 2 x the widest BatchNorm layer (padded) fits with room to spare
 constexpr int kPeerThreads = 1024;
-
-struct PeerPtrs {
-    uint2* buf[kPeerMaxWorld];                        // every rank's buffer, [2 sets][world slots][2 * kPeerMaxDoubles] pairs
-    int world, rank;
-};
 
 struct PeerState {
     PeerPtrs p;
@@ -36,16 +29,79 @@ struct PeerState {
     double* d_out = nullptr;                 // sums before they are copied back in place
     bool open = false;
     void* mapped[kPeerMaxWorld] = {nullptr};
+    // gradient all-reduce: this rank's flat gradient buffer (library-owned so that it can be mapped by the peers)
+    float* gbuf = nullptr;
+    long long gcount = 0;
+    bool gopen = false;
+    void* gmapped[kPeerMaxWorld] = {nullptr};
+    float* gptr[kPeerMaxWorld] = {nullptr};
+    unsigned long long* g_seq = nullptr;     // [0]: sequence number of the gradient all-reduce, [1]: CTA completion counter
 };
 
-__device__ __forceinline__ uint2 peer_ld(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+struct GradPtrs {
+    float* buf[kPeerMaxWorld];               // every rank's gradient buffer as mapped here
+    uint2* flags[kPeerMaxWorld];             // every rank's flag area: [2 phases][world] (unused, tag) pairs
+    int world, rank;
+};
+constexpr size_t kPeerExchangeBytes = (size_t)2 * kPeerMaxWorld * (2 * kPeerMaxDoubles) * sizeof(uint2);     // 2 MB, flags follow
+constexpr int kGradThreads = 512;
+
+// Sum of the flat fp32 gradient buffers of all ranks, in place on every rank, over NVLink peer memory:
+//   entry barrier  every rank flags "my backward pass is done" into every peer's flag area and waits for all flags;
+//   slice          rank r owns chunk r of the vector: it LOADS that chunk from every rank's buffer (16-byte P2P loads, L1
+//                  bypassed), adds in rank order and STORES the sum into chunk r of every rank's buffer -- nobody else reads
+//                  or writes chunk r, so the two phases of a textbook reduce-scatter + all-gather need no barrier between them;
+//   exit barrier   system-scope fence, the last CTA flags "my chunk is everywhere" to all peers and waits for theirs.
+// Each rank moves (world-1)/world of the vector in each direction once: 17.5 MB at 8 GPUs for the 20 MB of the benchmark
+// model -- ~25 us of NVLink time against ~100 us for ncclAllReduce at this size.  Every rank adds the same numbers in the
+// same order: the replicas stay bit-identical.  All polls are bounded (trap, not hang).
+__global__ void __launch_bounds__(kGradThreads)
+peer_allreduce_f32_kernel(const GradPtrs G, long long n4, unsigned long long* __restrict__ seq_ctr, unsigned int* __restrict__ done_ctr) {
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_ctr);
+    const uint32_t tag = (uint32_t)seq + 1u;
+    const int world = G.world, rank = G.rank, tid = threadIdx.x;
+    auto poll = [&](const uint2* flag, int what) {
+        const long long t0 = clock64();
+        while (peer_ld(flag).y != tag) {
+            if (clock64() - t0 > 4000000000LL) {
+                printf("mmad gradient all-reduce: rank %d: %s flag of rank %d never arrived (exchange %llu)\n", rank, what ? "exit" : "entry", tid, seq);
+                __trap();
+            }
+        }
+    };
+    if (blockIdx.x == 0 && tid < world) peer_st(G.flags[tid] + rank, 0u, tag);
+    if (tid < world) poll(G.flags[rank] + tid, 0);
+    __syncthreads();
+    const long long chunk = (n4 + world - 1) / world;
+    const long long lo = (long long)rank * chunk, hi = lo + chunk < n4 ? lo + chunk : n4;
+    for (long long i = lo + (long long)blockIdx.x * kGradThreads + tid; i < hi; i += (long long)gridDim.x * kGradThreads) {
+        float4 v[kPeerMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < world) v[r] = __ldcg(reinterpret_cast<const float4*>(G.buf[r]) + i);
+        float4 a = v[0];
+#pragma unroll
+        for (int r = 1; r < kPeerMaxWorld; ++r)
+            if (r < world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < world) __stcg(reinterpret_cast<float4*>(G.buf[r]) + i, a);
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (tid == 0) s_last = atomicAdd(done_ctr, 1u) + 1u == gridDim.x;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (tid < world) {
+        peer_st(G.flags[tid] + world + rank, 0u, tag);
+        poll(G.flags[rank] + world + tid, 1);
+    }
+    __syncthreads();
+    if (tid == 0) { *done_ctr = 0; __threadfence(); *reinterpret_cast<volatile unsigned long long*>(seq_ctr) = seq + 1; }
 }
-__device__ __forceinline__ void peer_st(uint2* p, uint32_t data, uint32_t seq) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(seq) : "memory");
-}
+
 
 // grid = world CTAs: CTA r pushes this rank's vector to rank r; the CTAs then share the polling / summation of the elements.
 // One CTA for everything was push-bound at 8 ranks (45 000 remote 8-byte stores through one SM).
@@ -106,7 +162,8 @@ void peer_state_free(void* p) {
     PeerState* S = static_cast<PeerState*>(p);
     if (!S) return;
     for (int r = 0; r < kPeerMaxWorld; ++r) if (S->mapped[r]) cudaIpcCloseMemHandle(S->mapped[r]);
-    cudaFree(S->local); cudaFree(S->d_seq); cudaFree(S->d_out);
+    for (int r = 0; r < kPeerMaxWorld; ++r) if (S->gmapped[r]) cudaIpcCloseMemHandle(S->gmapped[r]);
+    cudaFree(S->local); cudaFree(S->d_seq); cudaFree(S->d_out); cudaFree(S->gbuf); cudaFree(S->g_seq);
     delete S;
 }
 
@@ -116,6 +173,41 @@ bool peer_ready(mmad_t h) {
 }
 
 int peer_max_doubles() { return kPeerMaxDoubles; }
+
+// the library-owned gradient buffer, when d_buf / count are exactly it and every peer has mapped it
+bool peer_grads_match(mmad_t h, const void* d_buf, long long count) {
+    PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
+    return S && S->open && S->gopen && d_buf == S->gbuf && count == S->gcount;
+}
+
+int peer_allreduce_grads(mmad_t h, cudaStream_t s) {
+    PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
+    if (!S || !S->gopen) { set_error("peer gradient buffers are not open"); return MMAD_E_STATE; }
+    GradPtrs G;
+    memset(&G, 0, sizeof G);
+    G.world = S->p.world; G.rank = S->p.rank;
+    for (int r = 0; r < G.world; ++r) {
+        G.buf[r] = S->gptr[r];
+        G.flags[r] = reinterpret_cast<uint2*>(reinterpret_cast<char*>(S->p.buf[r]) + kPeerExchangeBytes);
+    }
+    const long long n4 = S->gcount / 4;
+    const long long per_rank = (n4 + G.world - 1) / G.world;
+    int grid = (int)std::min<long long>(128, (per_rank + kGradThreads - 1) / kGradThreads);
+    if (grid < 1) grid = 1;
+    peer_allreduce_f32_kernel<<<grid, kGradThreads, 0, s>>>(G, n4, S->g_seq, reinterpret_cast<unsigned int*>(S->g_seq + 1));
+    MMAD_LAUNCHED();
+    MMAD_CUDA_OK(cudaGetLastError());
+    return MMAD_OK;
+}
+
+bool peer_kernel_args(mmad_t h, PeerPtrs* ptrs, unsigned long long** seq_ctr, unsigned int** done_ctr) {
+    PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
+    if (!S || !S->open) return false;
+    *ptrs = S->p;
+    *seq_ctr = S->d_seq;
+    *done_ctr = reinterpret_cast<unsigned int*>(S->d_seq + 1);
+    return true;
+}
 
 int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s) {
     PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
@@ -141,9 +233,11 @@ int mmad_peer_create(mmad_t h, unsigned char* h_handle) {
     mmad_peer_close(h);
     PeerState* S = new PeerState();
     handle_peer_set(h, S);
-    const size_t bytes = (size_t)2 * kPeerMaxWorld * (2 * kPeerMaxDoubles) * sizeof(uint2);       // 2 MB
+    const size_t bytes = kPeerExchangeBytes + 4096;       // 2 MB of exchange slots + the flags of the gradient all-reduce
     MMAD_CUDA_OK(cudaMalloc(&S->local, bytes));
     MMAD_CUDA_OK(cudaMemset(S->local, 0, bytes));
+    MMAD_CUDA_OK(cudaMalloc(&S->g_seq, 16));
+    MMAD_CUDA_OK(cudaMemset(S->g_seq, 0, 16));
     MMAD_CUDA_OK(cudaMalloc(&S->d_seq, 16));
     MMAD_CUDA_OK(cudaMemset(S->d_seq, 0, 16));
     MMAD_CUDA_OK(cudaMalloc(&S->d_out, (size_t)kPeerMaxDoubles * 8));
@@ -182,6 +276,40 @@ int mmad_peer_close(mmad_t h) {
         peer_state_free(p);
         handle_peer_set(h, nullptr);
     }
+    return MMAD_OK;
+}
+
+int mmad_peer_grad_alloc(mmad_t h, long long n_floats, float** d_ptr, unsigned char* h_handle) {
+    if (!h || !d_ptr || !h_handle || n_floats <= 0) { set_error("bad argument"); return MMAD_E_ARG; }
+    PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
+    if (!S || !S->local) { set_error("mmad_peer_create first"); return MMAD_E_STATE; }
+    if (S->gbuf) { set_error("the gradient buffer of this handle is already allocated"); return MMAD_E_STATE; }
+    const long long padded = (n_floats + 3) / 4 * 4;
+    MMAD_CUDA_OK(cudaMalloc(&S->gbuf, (size_t)padded * 4));
+    MMAD_CUDA_OK(cudaMemset(S->gbuf, 0, (size_t)padded * 4));
+    MMAD_CUDA_OK(cudaDeviceSynchronize());
+    S->gcount = padded;
+    cudaIpcMemHandle_t hd;
+    MMAD_CUDA_OK(cudaIpcGetMemHandle(&hd, S->gbuf));
+    memcpy(h_handle, &hd, sizeof hd);
+    *d_ptr = S->gbuf;
+    return MMAD_OK;
+}
+
+int mmad_peer_grad_open(mmad_t h, const unsigned char* h_handles) {
+    if (!h || !h_handles) { set_error("bad argument"); return MMAD_E_ARG; }
+    PeerState* S = static_cast<PeerState*>(handle_peer_get(h));
+    if (!S || !S->open || !S->gbuf) { set_error("mmad_peer_open and mmad_peer_grad_alloc first"); return MMAD_E_STATE; }
+    for (int r = 0; r < S->p.world; ++r) {
+        if (r == S->p.rank) { S->gptr[r] = S->gbuf; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, h_handles + (size_t)r * sizeof hd, sizeof hd);
+        void* q = nullptr;
+        MMAD_CUDA_OK(cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess));
+        S->gmapped[r] = q;
+        S->gptr[r] = static_cast<float*>(q);
+    }
+    S->gopen = true;
     return MMAD_OK;
 }
 

@@ -286,15 +286,20 @@ __device__ __forceinline__ void fused_col_reduce(double (&s)[NS][4], double* sm 
         }
 }
 
-template <int RPT>
+// DP: the column sums are combined across the ranks INSIDE the kernel (peer_exchange_cta: NVLink peer memory, no separate
+// all-reduce launch, no second pass over the layer) -- the data-parallel step keeps the single-GPU kernel count.
+struct PeerArgs { PeerPtrs P; unsigned long long* seq; unsigned int* done; int stride; double Bg; };
+
+template <int RPT, bool DP>
 __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restrict__ pre, int ld, int B, int N, float slope, float eps,
                                                            float momentum, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ run_mean,
                                                            float* __restrict__ run_var, long long* __restrict__ nbt,
                                                            float* __restrict__ mean_out, float* __restrict__ inv_out,
                                                            float* __restrict__ out, int ldo, __half* __restrict__ oh,
-                                                           __half* __restrict__ ol) {
+                                                           __half* __restrict__ ol, const PeerArgs pa) {
     __shared__ double sm[(kCT / 32) * 2 * kFB];
+    __shared__ double s_tot[2 * kFB];
     pdl_trigger();
     pdl_wait();
     const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
@@ -315,8 +320,24 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
         for (int j = 0; j < 4; ++j) { s[0][j] += (double)a[i][j]; s[1][j] = fma((double)a[i][j], (double)a[i][j], s[1][j]); }
     double tot[2][4];
     fused_col_reduce<2>(s, sm, tot);
+    if (DP) {
+        if (rl == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_tot[k * kFB + cq * 4 + j] = tot[k][j];
+        }
+        __syncthreads();
+        const int col_base = blockIdx.x * kFB, stride = pa.stride;
+        peer_exchange_cta<2 * kFB>(pa.P, pa.seq, pa.done, s_tot, [=](int e) { return (e / kFB) * stride + col_base + (e % kFB); });
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tot[k][j] = s_tot[k * kFB + cq * 4 + j];
+    }
     if (!col_ok) return;
-    const double Bg = (double)B;
+    const double Bg = DP ? pa.Bg : (double)B;
     float m[4], iv[4], g[4], b[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -353,14 +374,15 @@ __global__ void __launch_bounds__(kCT) bn_fwd_fused_kernel(const float* __restri
 
 // backward twin: s1 = sum g, s2 = sum g xhat, g_pre = gamma inv (g - s1/B - xhat s2/B) lrelu'(pre), gb = sum g_pre,
 // ggamma = s2, gbeta = s1 -- everything bn_bwd_reduce_kernel + bn_bwd_apply_kernel produce, from one read of g and pre
-template <int RPT>
+template <int RPT, bool DP>
 __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre, int ld,
                                                            int B, int N, float slope, float gscale, const float* __restrict__ mean,
                                                            const float* __restrict__ inv, const float* __restrict__ gamma,
                                                            float* __restrict__ gpre, int ldo, __half* __restrict__ gh,
                                                            __half* __restrict__ gl, float twin_scale, float* __restrict__ gb,
-                                                           float* __restrict__ ggamma, float* __restrict__ gbeta) {
+                                                           float* __restrict__ ggamma, float* __restrict__ gbeta, const PeerArgs pa) {
     __shared__ double sm[(kCT / 32) * 2 * kFB];
+    __shared__ double s_tot[2 * kFB];
     pdl_trigger();
     pdl_wait();
     const int cq = threadIdx.x & 3, rl = threadIdx.x >> 2;
@@ -399,13 +421,30 @@ __global__ void __launch_bounds__(kCT) bn_bwd_fused_kernel(const float* __restri
     }
     double tot[2][4];
     fused_col_reduce<2>(s, sm, tot);
-    const double Bg = (double)B;
+    // BatchNorm parameter gradients from the LOCAL sums (the flat gradient buffer is all-reduced as a whole afterwards)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (col_ok && c0 + j < N && rl == 0) { gbeta[c0 + j] = (float)tot[0][j]; ggamma[c0 + j] = (float)tot[1][j]; }
+    if (DP) {
+        if (rl == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_tot[k * kFB + cq * 4 + j] = tot[k][j];
+        }
+        __syncthreads();
+        const int col_base = blockIdx.x * kFB, stride = pa.stride;
+        peer_exchange_cta<2 * kFB>(pa.P, pa.seq, pa.done, s_tot, [=](int e) { return (e / kFB) * stride + col_base + (e % kFB); });
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tot[k][j] = s_tot[k * kFB + cq * 4 + j];
+    }
+    const double Bg = DP ? pa.Bg : (double)B;
     float a1[4], a2[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        a1[j] = (float)(tot[0][j] / Bg); a2[j] = (float)(tot[1][j] / Bg);
-        if (col_ok && c0 + j < N && rl == 0) { gbeta[c0 + j] = (float)tot[0][j]; ggamma[c0 + j] = (float)tot[1][j]; }
-    }
+    for (int j = 0; j < 4; ++j) { a1[j] = (float)(tot[0][j] / Bg); a2[j] = (float)(tot[1][j] / Bg); }
     double acc[1][4] = {{0.0, 0.0, 0.0, 0.0}};
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
@@ -786,7 +825,17 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
     constexpr float GS = 16.f;       // gradients are scaled by 2^4 before the fp16 hi/lo split
     // one-kernel BatchNorm (statistics + apply) when one rank holds the whole batch and it fits the register tile
     static const bool no_fuse_bn = getenv("MMAD_NO_FUSED_BN") != nullptr;
-    const bool fuse_bn = !dist && B >= 128 && B <= 512 && global_batch == (long long)B && !no_fuse_bn;   // below 128 rows the two-kernel form measured faster
+    // Data parallel over the handle's peer buffers: the same kernels with the cross-rank combination of the column sums inside
+    // (no hook, every rank holds B rows, the statistic vectors fit the exchange buffer).
+    PeerArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.Bg = Bg;
+    int max_np = 0;
+    for (int i = 1; i <= d.n_enc; ++i) max_np = std::max(max_np, np_of(d.enc_widths[i]));
+    for (int i = 1; i <= d.n_dec; ++i) max_np = std::max(max_np, np_of(d.dec_widths[i]));
+    const bool fuse_dp = dist && !allreduce && !no_fuse_bn && B <= 512 && global_batch == (long long)B * comm_world &&
+                         2 * max_np <= kPeerMaxDoubles && peer_kernel_args(h, &pa.P, &pa.seq, &pa.done);
+    const bool fuse_bn = fuse_dp || (!dist && B >= 128 && B <= 512 && global_batch == (long long)B && !no_fuse_bn);   // below 128 rows the two-kernel form measured faster
     if (!fuse_bn) MMAD_CUDA_OK(cudaMemsetAsync(ws + p.st_all, 0, p.st_bytes, s));
     else if (vib) MMAD_CUDA_OK(cudaMemsetAsync(ws + p.kl, 0, 8, s));        // the KL accumulator shares that region
     MMAD_CUDA_OK(cudaMemsetAsync(d_loss, 0, 4, s));
@@ -942,9 +991,12 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
                 float* inv = (float*)(ws + p.inv[m][i]);
                 float* out = (float*)(ws + p.out[m][i]);
                 if (fuse_bn) {
-#define MMAD_BN_FWD(R) MMAD_CUDA_OK(launch_k(bn_fwd_fused_kernel<R>, dim3((N + kFB - 1) / kFB), dim3(kCT), 0, s, pre, Np, B, N, slope, d.bn_eps, bn_momentum, \
-                           L.gamma, L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv, tc ? nullptr : out, Np, oh, ol))
+#define MMAD_BN_FWD2(R, DPV) MMAD_CUDA_OK(launch_k(bn_fwd_fused_kernel<R, DPV>, dim3((N + kFB - 1) / kFB), dim3(kCT), 0, s, pre, Np, B, N, slope, d.bn_eps, bn_momentum, \
+                           L.gamma, L.beta, L.run_mean, L.run_var, L.num_batches_tracked, mean, inv, tc ? nullptr : out, Np, oh, ol, pa))
+#define MMAD_BN_FWD(R) do { if (fuse_dp) MMAD_BN_FWD2(R, true); else MMAD_BN_FWD2(R, false); } while (0)
+                    pa.stride = Np;
                     if (B <= 64) MMAD_BN_FWD(1); else if (B <= 128) MMAD_BN_FWD(2); else if (B <= 256) MMAD_BN_FWD(4); else MMAD_BN_FWD(8);
+#undef MMAD_BN_FWD2
 #undef MMAD_BN_FWD
                     MMAD_LAUNCHED();
                 } else {
@@ -1031,9 +1083,12 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             __half* gol = tc ? (__half*)(ws + p.gtl[idx]) : nullptr;
             double* stb = st + 2 * r.Np;       // backward statistics (zeroed with the forward ones at step start)
             if (fuse_bn) {
-#define MMAD_BN_BWD(R) MMAD_CUDA_OK(launch_k(bn_bwd_fused_kernel<R>, dim3((r.N + kFB - 1) / kFB), dim3(kCT), 0, s, gin.f, gin.ld, pre, r.Np, B, r.N, slope, \
-                           gscale, mean, inv, L.gamma, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta))
+#define MMAD_BN_BWD2(R, DPV) MMAD_CUDA_OK(launch_k(bn_bwd_fused_kernel<R, DPV>, dim3((r.N + kFB - 1) / kFB), dim3(kCT), 0, s, gin.f, gin.ld, pre, r.Np, B, r.N, slope, \
+                           gscale, mean, inv, L.gamma, tc ? nullptr : go, p.maxNp, goh, gol, GS, L.gb, L.ggamma, L.gbeta, pa))
+#define MMAD_BN_BWD(R) do { if (fuse_dp) MMAD_BN_BWD2(R, true); else MMAD_BN_BWD2(R, false); } while (0)
+                pa.stride = r.Np;
                 if (B <= 64) MMAD_BN_BWD(1); else if (B <= 128) MMAD_BN_BWD(2); else if (B <= 256) MMAD_BN_BWD(4); else MMAD_BN_BWD(8);
+#undef MMAD_BN_BWD2
 #undef MMAD_BN_BWD
                 MMAD_LAUNCHED();
             } else {

@@ -185,11 +185,61 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
                 else:
                     check(lib().mmad_peer_close(eng._h))
                 dist.barrier(group)
+                if st.peer and os.environ.get("MMAD_NO_PEER_GRADS", "0") != "1":
+                    _peer_gradient_buffer(st, eng, group, dev)
         st.native = True
         st.native_handle = eng._h.value      # the communicator lives in THIS library handle
         st.grads_in_step = bool(overlap_grads)
     st.batch_checked = None
     return st
+
+
+class _DevicePtr:
+    """A library-owned device buffer as seen by ``torch.as_tensor`` (zero copy; torch keeps this object alive)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _peer_gradient_buffer(st, eng, group, dev):
+    """Move the flat gradient buffer into memory the library allocated and every peer mapped (``mmad_peer_grad_alloc`` /
+    ``mmad_peer_grad_open``): ``allreduce_gradients`` then runs as ONE kernel per rank over NVLink peer memory instead of
+    ncclAllReduce (include/mmad.h).  All ranks or none."""
+    import torch.distributed as dist
+    n = st.flat_grad.numel()
+    hb = (C.c_ubyte * 64)()
+    ptr = C.c_void_p()
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    try:
+        check(lib().mmad_peer_grad_alloc(eng._h, n, C.byref(ptr), hb))
+    except _lib.MmadError:
+        ok.zero_()
+    mine = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(st.world)]
+    dist.all_gather(allh, mine, group=group)
+    if int(ok.item()):
+        try:
+            raw = (C.c_ubyte * (64 * st.world))(*torch.cat(allh).cpu().tolist())
+            check(lib().mmad_peer_grad_open(eng._h, raw))
+        except _lib.MmadError:
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    dist.barrier(group)
+    st.peer_grads = bool(int(ok.item()))
+    if not st.peer_grads:
+        return
+    n4 = (n + 3) // 4 * 4
+    flat = torch.as_tensor(_DevicePtr(ptr.value, n4), device=dev)
+    assert flat.data_ptr() == ptr.value
+    st.flat_grad = flat
+    st.views, off = [], 0
+    pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
+    for p in st.params:
+        st.views.append(flat[off:off + p.numel()].view_as(p))
+        off += pad4(p.numel())
+        p.grad = None
+    st.view_of = {id(p): v for p, v in zip(st.params, st.views)}
+    st._tables = None
 
 
 def _check_native_comm(st, eng):

@@ -293,6 +293,15 @@ int mmad_peer_create(mmad_t h, unsigned char* h_handle);
 int mmad_peer_open(mmad_t h, const unsigned char* h_handles, int rank, int world);
 int mmad_peer_close(mmad_t h);
 int mmad_peer_allreduce_f64(mmad_t h, double* d_buf, long long count, void* stream);
+/* Gradient all-reduce over peer memory.  The flat fp32 gradient buffer must be mapped by the peers, so the library owns it:
+ * mmad_peer_grad_alloc (after mmad_peer_open) allocates n_floats (rounded up to 4) zeroed floats on this rank, returns the
+ * device pointer and its cudaIpc handle; the host layer gathers the handles (rank order) and every rank calls
+ * mmad_peer_grad_open, then a barrier.  From then on mmad_comm_allreduce_f32 on EXACTLY that buffer (pointer and rounded
+ * count) runs as one kernel per rank: entry barrier over flags in peer memory, rank r sums chunk r of all ranks' buffers
+ * (P2P loads, rank order) and stores it into every buffer, exit barrier.  Replaces torch.distributed.all_reduce of
+ * novelty_detection.py's gradient step (the reference is single-GPU).  Freed by mmad_peer_close. */
+int mmad_peer_grad_alloc(mmad_t h, long long n_floats, float** d_ptr, unsigned char* h_handle);
+int mmad_peer_grad_open(mmad_t h, const unsigned char* h_handles);
 
 /* ---- multimodal feature extractor in front of the autoencoder ----
  * utils/data_loaders.py:152-229 (HSR_Net.forward) / 601-674 (Multisensory_module.forward): per sample

@@ -54,7 +54,10 @@ def run(bn, grads, steps=40):
         print(f"world {world} B {B}: BN {bn:5s} grads {grads:6s}: {float(t):.3f} ms/step", flush=True)
 
 
-for bn, grads in (("none", "none"), ("none", "flat"), ("nccl", "none"), ("peer", "none"), ("nccl", "flat"), ("peer", "flat"), ("nccl", "bucket"), ("peer", "bucket")):
+cases = (("none", "none"), ("none", "flat"), ("nccl", "none"), ("peer", "none"), ("nccl", "flat"), ("peer", "flat"), ("nccl", "bucket"), ("peer", "bucket"))
+if os.environ.get("CASES"):      # e.g. CASES=peer:flat,nccl:flat
+    cases = tuple(tuple(c.split(":")) for c in os.environ["CASES"].split(","))
+for bn, grads in cases:
     if grads == "bucket" and bn == "none":
         continue
     run(bn, grads)
