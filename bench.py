@@ -365,7 +365,8 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
     def step(x):
         if world == 1:
             return AutoEncoder.step(eng, (x, None))
-        model.train()
+        if not model.training:
+            model.train()
         opt.zero_grad()
         loss = model.get_loss_value(x.cuda(local), None)
         loss.backward()
@@ -403,10 +404,13 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
             "e2e": {"value": world * batch / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": batch * D * 4,
                     "d2h_bytes_per_step": 4}, "optimizer": "mmad multi-tensor Adam", "gemm": {"fp32": "fp32 CUDA-core", "f16x3": "tcgen05 f16x3 split", "f16": "tcgen05 f16", "f16f8": "tcgen05 f16x3 split"}[precision],
             "graph": True, "collectives": None if world == 1 else {
-                "bn_statistics": "one-kernel NVLink peer-memory exchange per BatchNorm layer and direction (csrc/peer.cu)" if getattr(st, "peer", False)
+                "bn_statistics": "exchanged over NVLink peer memory INSIDE the one-kernel BatchNorm forward / backward (csrc/train.cu bn_*_fused_kernel<.., DP>, "
+                                 "csrc/mmad_internal.cuh peer_exchange_cta)" if getattr(st, "peer", False)
                 else "ncclAllReduce per BatchNorm layer and direction",
                 "gradients": "two NCCL all-reduces inside the captured step (decoder bucket overlaps the encoder backward)"
-                if getattr(st, "grads_in_step", False) else "one flat NCCL all-reduce after the step"}}
+                if getattr(st, "grads_in_step", False) else
+                ("one peer-memory kernel per rank after the step: chunk r of all ranks' buffers summed by rank r over NVLink (csrc/peer.cu)"
+                 if getattr(st, "peer_grads", False) else "one flat NCCL all-reduce after the step")}}
 
 
 def bench_stream(eng, batches=(1, 8, 10, 64), calls=400, warm=60):

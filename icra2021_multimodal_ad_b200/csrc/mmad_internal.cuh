@@ -255,7 +255,11 @@ __device__ __forceinline__ void peer_exchange_cta(const PeerPtrs& P, unsigned lo
         const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[e]);
         const uint32_t w = part ? (uint32_t)(bits >> 32) : (uint32_t)bits;
         const size_t off = set + (size_t)P.rank * (2 * kPeerMaxDoubles) + 2 * (size_t)elem_of(e) + part;
-        for (int r = 0; r < P.world; ++r) peer_st(P.buf[r] + off, w, tag);
+        for (int k = 0; k < P.world; ++k) {       // own rank last: the ranks start with different peers
+            int r = P.rank + 1 + k;
+            if (r >= P.world) r -= P.world;
+            peer_st(P.buf[r] + off, w, tag);
+        }
     }
     __syncthreads();            // every thread has read vals[]
     if (t < NV) {

@@ -39,7 +39,10 @@ struct PeerState {
 };
 
 struct GradPtrs {
-    float* buf[kPeerMaxWorld];               // every rank's gradient buffer as mapped here
+    float* buf[kPeerMaxWorld];               // every rank's gradient buffer as mapped here, ROTATED: entry k is rank (rank + 1 + k) % world
+                                             // (own buffer last) -- at any moment the 8 ranks talk to 8 different peers instead of all
+                                             // starting with rank 0's memory.  Chunk r is summed by rank r alone and broadcast, so the
+                                             // order of ITS additions need not match any other rank's: the replicas stay identical.
     uint2* flags[kPeerMaxWorld];             // every rank's flag area: [2 phases][world] (unused, tag) pairs
     int world, rank;
 };
@@ -49,12 +52,13 @@ constexpr int kGradThreads = 512;
 // Sum of the flat fp32 gradient buffers of all ranks, in place on every rank, over NVLink peer memory:
 //   entry barrier  every rank flags "my backward pass is done" into every peer's flag area and waits for all flags;
 //   slice          rank r owns chunk r of the vector: it LOADS that chunk from every rank's buffer (16-byte P2P loads, L1
-//                  bypassed), adds in rank order and STORES the sum into chunk r of every rank's buffer -- nobody else reads
+//                  bypassed), adds them in a fixed order (peers r+1, r+2, ..., itself) and STORES the sum into chunk r of every rank's buffer -- nobody else reads
 //                  or writes chunk r, so the two phases of a textbook reduce-scatter + all-gather need no barrier between them;
 //   exit barrier   system-scope fence, the last CTA flags "my chunk is everywhere" to all peers and waits for theirs.
 // Each rank moves (world-1)/world of the vector in each direction once: 17.5 MB at 8 GPUs for the 20 MB of the benchmark
-// model -- ~25 us of NVLink time against ~100 us for ncclAllReduce at this size.  Every rank adds the same numbers in the
-// same order: the replicas stay bit-identical.  All polls are bounded (trap, not hang).
+// model.  Measured in the data-parallel step at B = 256 per GPU: +14 us at 2 GPUs (ncclAllReduce +32 us), +139 us at 8
+// (ncclAllReduce +251 us) before the peer order was rotated.  Every rank receives the same sums: the replicas stay
+// bit-identical.  All polls are bounded (trap, not hang).
 __global__ void __launch_bounds__(kGradThreads)
 peer_allreduce_f32_kernel(const GradPtrs G, long long n4, unsigned long long* __restrict__ seq_ctr, unsigned int* __restrict__ done_ctr) {
     const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_ctr);
@@ -187,7 +191,7 @@ int peer_allreduce_grads(mmad_t h, cudaStream_t s) {
     memset(&G, 0, sizeof G);
     G.world = S->p.world; G.rank = S->p.rank;
     for (int r = 0; r < G.world; ++r) {
-        G.buf[r] = S->gptr[r];
+        G.buf[r] = S->gptr[(G.rank + 1 + r) % G.world];
         G.flags[r] = reinterpret_cast<uint2*>(reinterpret_cast<char*>(S->p.buf[r]) + kPeerExchangeBytes);
     }
     const long long n4 = S->gcount / 4;
