@@ -385,7 +385,7 @@ __device__ __forceinline__ void epi_block(const Epilogue& e, const EpiPtrs& q, i
                         uint2 hv, lv;
                         hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
                         *reinterpret_cast<uint2*>(q.Dh + (size_t)rr * e.lddh + c0) = hv;
-                        if (e.lo_f8) {
+                        if (e.d_lo_f8) {
                             lv.x = pack_e4m3x4((s0 - f01.x) * kF8LoScale, (s1 - f01.y) * kF8LoScale, (s2 - f23.x) * kF8LoScale, (s3 - f23.y) * kF8LoScale);
                             lv.y = pack_e4m3x4(s0, s1, s2, s3);
                         } else {

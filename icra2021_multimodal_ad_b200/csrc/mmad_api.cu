@@ -202,13 +202,20 @@ struct PlanOpts {
 
 static int nap_passes() {
     static int v = 0;
-    if (!v) { const char* e = getenv("MMAD_NAP_PASSES"); v = (e && e[0] == '2') ? 2 : 3; }
+    if (!v) { const char* e = getenv("MMAD_NAP_PASSES"); v = (e && e[0] == '2') ? 2 : (e && e[0] == '4') ? 4 : 3; }
     return v;
 }
 
 static bool use_tc(mmad_t h) { return h->desc.precision != MMAD_PREC_FP32 && !h->skinny; }
 static bool f8_mode(mmad_t h) { return h->desc.precision == MMAD_PREC_F16F8 && !h->skinny; }
-static float diff_scale(mmad_t h) { return f8_mode(h) ? kDiffScaleF8 : kDiffScale; }
+// NAP rotation with fp8 cross terms (one fp16 hi*hi MMA + one double-length fp8 MMA carrying both cross terms, like the F16F8
+// layer GEMMs): always in the F16F8 mode; in the F16X3 mode when selected (mmad_set_option "nap_passes" 4).  The diffs then
+// leave the chain as (fp16 hi, fp8 twin) pairs.
+static int nap_passes_eff(mmad_t h) { return h->nap_passes ? h->nap_passes : nap_passes(); }
+static bool nap_f8(mmad_t h) {
+    return !h->skinny && (h->desc.precision == MMAD_PREC_F16F8 || (h->desc.precision == MMAD_PREC_F16X3 && nap_passes_eff(h) == 4));
+}
+static float diff_scale(mmad_t h) { return nap_f8(h) ? kDiffScaleF8 : kDiffScale; }
 static int tc_passes(mmad_t h) {
     return h->desc.precision == MMAD_PREC_F16X3 ? 3 : h->desc.precision == MMAD_PREC_F16F8 ? 4 : 1;
 }
@@ -355,6 +362,7 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     A.rows = rows; A.k = Lr.K;
     e.acc_scale = 1.f / (f8 ? Lr.wscale8 : Lr.wscale);
     e.lo_f8 = f8 ? 1 : 0;
+    e.d_lo_f8 = nap_f8(h) ? 1 : 0;
     const int passes = tc_passes(h);
     e.acc_comp = (float)(h->acc_comp * instr_per_kb(passes));
     if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, f8 ? Lr.tcB2_f8 : Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
@@ -656,7 +664,8 @@ int mmad_set_option(mmad_t h, const char* name, double value) {
         if (!(value >= 0.0 && value < 1e-6)) { set_error("acc_comp out of range [0, 1e-6)"); return MMAD_E_ARG; }
         h->acc_comp = value;
     } else if (!strcmp(name, "nap_passes")) {
-        if (value != 0 && value != 2 && value != 3) { set_error("nap_passes must be 0 (default), 2 or 3"); return MMAD_E_ARG; }
+        if (value != 0 && value != 2 && value != 3 && value != 4) { set_error("nap_passes must be 0 (default), 2, 3 or 4"); return MMAD_E_ARG; }
+        if (h->nap_passes != (int)value) h->nap.ready = false;      // the fit's variances carry the old arithmetic's rounding noise
         h->nap_passes = (int)value;
     } else if (!strcmp(name, "require_pinned")) {
         h->require_pinned = value != 0;
@@ -821,7 +830,7 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         rc = h->skinny ? gemm_skinny(g, e, s) : gemm_simt(g, e, s);
     } else {
         TcOperand A;
-        const bool f8 = f8_mode(h);
+        const bool f8 = nap_f8(h);
         rc = operand_map(h, &A.hi, ws + p.dh, rows, f.Dp, p.Dselp, 0);
         if (!rc && f8) rc = operand_map(h, &A.lo, ws + p.dl, rows, f.Dp, p.Dselp * 2, 1);
         else if (!rc) rc = operand_map(h, &A.lo, ws + p.dl, rows, f.Dp, p.Dselp, 0);
@@ -833,7 +842,7 @@ static int nap_gemm(mmad_t h, const Plan& p, char* ws, int rows, float* d_nap, c
         // fp16 (two MMAs per product, +17 % scoring throughput): fine for well-conditioned layer selections (score
         // error ~1e-4), NOT for the rank-deficient all-layers default, whose near-null directions it perturbs beyond
         // the reference's own error (tests/test_gpu_metrics.py::test_nap_all_layers_protocol fails with it)
-        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? (h->nap_passes ? h->nap_passes : nap_passes()) : tc_passes(h);
+        const int passes = h->desc.precision == MMAD_PREC_F16X3 ? nap_passes_eff(h) : tc_passes(h);
         e.acc_comp = (float)(h->acc_comp * instr_per_kb(passes));
         if (rows >= kPairMinRows && tc2_available()) rc = gemm_tc2(A, f8 ? f.tcB2_f8 : f.tcB2, rows, f.K, f.Dp, passes, e, s);
         else rc = gemm_tc(A, f8 ? f.tcB_f8 : f.tcB, rows, f.K, f.Dp, passes, e, s);
@@ -856,6 +865,7 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     // F16F8 NAP: the fit's variances carry this mode's rounding noise in the near-null directions, so scoring keeps the
     // same arithmetic at every batch size
     if (h->desc.precision == MMAD_PREC_F16F8 && d_nap) h->skinny = false;
+    if (h->desc.precision == MMAD_PREC_F16X3 && d_nap && nap_passes_eff(h) != 3) h->skinny = false;      // same for the optional rotations
     // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29) in the fp32 mode: base / SAP
     // scores from ONE fused exact-fp32 kernel (smallnet.cu): 65 / 48 M windows/s at D = 64 / 128 against 29 / 27 M for the
     // per-layer fp32 kernels.  The tensor-core modes keep their per-layer kernels (93 / 92 M windows/s in f16x3).

@@ -114,6 +114,7 @@ struct Epilogue {
     // 4 x e4m3((v - hi) * 2^11) then 4 x e4m3(v)  (v = value * split scale).  Same bytes per row as the fp16 lo; a
     // 64-column k-block of the fp16 operand corresponds to one 128-byte block of the twin.
     int lo_f8 = 0;
+    int d_lo_f8 = 0;             // the DIFF twins (Dh / Dl) in the fp8 twin layout (lo_f8 describes the activation twins Yh / Yl)
 };
 
 constexpr float kF8LoScale = 2048.f;   // the residual v - fp16(v) is at most 2^-11 |v|: scaled to |lo8| <= |v|

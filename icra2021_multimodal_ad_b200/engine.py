@@ -86,8 +86,12 @@ class Engine:
         self._ws_rows = 0
 
     def set_option(self, name: str, value: float):
-        """``mmad_set_option``: 'acc_comp', 'nap_passes', 'require_pinned' (include/mmad.h)."""
+        """``mmad_set_option``: 'acc_comp', 'nap_passes', 'require_pinned', 'smallnet' (include/mmad.h).  Changing
+        'nap_passes' drops the installed NAP fit (its variances belong to the old arithmetic): refit afterwards."""
         check(lib().mmad_set_option(self._h, name.encode(), float(value)))
+        if name == "nap_passes":
+            self.nap_range = None
+            self.nap_fit_state = None
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         """Pack a reference-format state dict (keys ``encoder.net.{i}.layer.weight`` ...).  An installed NAP fit

@@ -79,7 +79,9 @@ int mmad_set_precision(mmad_t h, int precision);   /* invalidates an installed N
  * same reference arithmetic):
  *   "acc_comp"        relative shrink of a tensor-core accumulator per MMA instruction that the epilogue compensates
  *                     (first-order correction of the truncating fp32 accumulation); 0 = off
- *   "nap_passes"      F16X3 NAP rotation: 3 = full split (default), 2 = whitening rows rounded to fp16, 0 = default
+ *   "nap_passes"      F16X3 NAP rotation: 3 = full split (default), 4 = fp16 hi*hi + fp8 cross terms (the F16F8 arithmetic for
+ *                     this one GEMM; <= 2.2e-5 on well-conditioned selections), 2 = whitening rows
+ *                     rounded to fp16, 0 = default.  Changing it invalidates the installed NAP fit
  *   "require_pinned"  1: mmad_score_host returns MMAD_E_ARG for pageable bulk input instead of accepting it
  *   "smallnet"        0: FP32-mode models whose widths are all <= 128 use the per-layer kernels instead of the fused
  *                     whole-chain kernel (default 1)

@@ -11,7 +11,7 @@ from icra2021_multimodal_ad_b200.utils import metric as M
 g, sd, xtr, xte, y, truth = T._nap_full_case()
 D, btl, nl = g["D"], g["btl"], g["n_layers"]
 ref = g["nap"]["score"].numpy().astype(np.float64)
-for passes in (3, 2):
+for passes in (3, 2, 4):
     eng = T._model(D, btl, nl, sd, "f16x3").engine()
     eng.set_option("nap_passes", passes)
     eng.nap_fit(xtr.cuda(), 0, nl + 1, distributed=False)
@@ -24,7 +24,7 @@ for passes in (3, 2):
 for name, sel in (("score_D1728.pt", (0, 1)), ("score_D1728.pt", (5, 6)), ("score_D64.pt", (0, 1))):
     g, sd, xtr, xte, y, truth = T._nap_case(name, sel)
     D, btl, nl = g["D"], g["btl"], g["n_layers"]
-    for passes in (3, 2):
+    for passes in (3, 2, 4):
         eng = T._model(D, btl, nl, sd, "f16x3").engine()
         eng.set_option("nap_passes", passes)
         eng.nap_fit(xtr.cuda(), sel[0], sel[1], distributed=False)
