@@ -224,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             float sq[8];
-            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
+            epi_tile<BN>(e, p.M, p.N, p.splits, sp, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -243,6 +243,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
     if (threadIdx.x == 0) tc_stamp(p, 7);
+}
+
+// ---- the fused epilogue as a stand-alone kernel (small batches) ------------------------------------------------
+// A scoring call of 17..256 rows is one or two row tiles: 11-28 CTAs per layer, each walking all k-blocks alone (27 at
+// K = 1728: 12 us) and then the fused epilogue with nothing to hide it behind (9-13 us) -- 25 us per layer, 15 layers.  The same
+// layer as a PLAIN split-K GEMM over all SMs (5 us) plus this kernel (bias is already in the accumulator; LeakyReLU, BatchNorm
+// affine, fp32 stash, fp16 hi/lo twins, diff against the reference, diff twins, row sums of squares per 128-column block) is a
+// third of that.  The GEMM's splits do NOT add atomically: split sp stores its partial tile into slab sp and this kernel adds
+// the slabs in order, so the scores stay bit-reproducible from call to call and nothing has to be zeroed.
+// One warp per (row, 128-column block), lane <-> 4 columns.
+__global__ void __launch_bounds__(256) epi_follow_kernel(const Epilogue e, const float* __restrict__ acc, int ldacc, int rows, int N, int cols_p,
+                                                         int splits, long long slab_stride) {
+    pdl_trigger();
+    pdl_wait();
+    const int nblk = (cols_p + 127) / 128;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= rows * nblk) return;
+    const int r = w / nblk, blk = w - r * nblk;
+    const int c = blk * 128 + lane * 4;
+    float sq = 0.f;
+    if (c < cols_p) {
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < N) {
+            float4 a = *reinterpret_cast<const float4*>(acc + (size_t)r * ldacc + c);
+            for (int sp = 1; sp < splits; ++sp) {          // the split-K partial tiles, added in a fixed order: deterministic
+                const float4 b = *reinterpret_cast<const float4*>(acc + (size_t)sp * (size_t)slab_stride + (size_t)r * ldacc + c);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w;
+            if (e.bn_scale) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j < N) {
+                        const float v = y[j] > 0.f ? y[j] : y[j] * e.slope;
+                        y[j] = fmaf(v, __ldg(e.bn_scale + c + j), __ldg(e.bn_shift + c + j));
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (c + j >= N) y[j] = 0.f;
+        }
+        if (e.Y && c < e.y_cols) *reinterpret_cast<float4*>(e.Y + (size_t)r * e.ldy + c) = make_float4(y[0], y[1], y[2], y[3]);
+        if (e.Yh && c < e.y_cols) {
+            const float ys = e.y_split_scale;
+            const __half2 h01 = __floats2half2_rn(y[0] * ys, y[1] * ys), h23 = __floats2half2_rn(y[2] * ys, y[3] * ys);
+            uint2 hv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+            *reinterpret_cast<uint2*>(e.Yh + (size_t)r * e.ldh + c) = hv;
+            if (e.Yl) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(y[0] * ys - f01.x, y[1] * ys - f01.y);
+                const __half2 l23 = __floats2half2_rn(y[2] * ys - f23.x, y[3] * ys - f23.y);
+                uint2 lv;
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(e.Yl + (size_t)r * e.ldh + c) = lv;
+            }
+        }
+        if (e.ref) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c + 3 < N) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(e.ref + (size_t)r * e.ldref + c));
+                d[0] = y[0] - f.x; d[1] = y[1] - f.y; d[2] = y[2] - f.z; d[3] = y[3] - f.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c + j < N) d[j] = y[j] - e.ref[(size_t)r * e.ldref + c + j];
+            }
+            sq = fmaf(d[0], d[0], fmaf(d[1], d[1], fmaf(d[2], d[2], d[3] * d[3])));
+            if (e.dout && c < e.d_cols) *reinterpret_cast<float4*>(e.dout + (size_t)r * e.lddout + c) = make_float4(d[0], d[1], d[2], d[3]);
+            if (e.Dh && c < e.d_cols) {
+                const float s0 = d[0] * e.d_scale, s1 = d[1] * e.d_scale, s2 = d[2] * e.d_scale, s3 = d[3] * e.d_scale;
+                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(e.Dh + (size_t)r * e.lddh + c) = hv;
+                *reinterpret_cast<uint2*>(e.Dl + (size_t)r * e.lddh + c) = lv;
+            }
+        }
+    }
+    if (e.rowpart && e.ref) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) e.rowpart[(size_t)blk * e.rowpart_stride + r] = sq;
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -332,7 +417,9 @@ int tc_make_operand_map_f8(CUtensorMap* map, const void* base, int rows, int k, 
     return MMAD_OK;
 }
 
-int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s, int bn) {
+int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, cudaStream_t s, int bn,
+            int* splits_out, int max_splits) {
+    if (splits_out) *splits_out = 1;
     if (!init_tc()) { set_error("tcgen05 path unavailable on this device"); return MMAD_E_UNSUPPORTED; }
     if (M <= 0 || N <= 0) return MMAD_OK;
     auto al = [](const void* q, int ld, int ldm) { return q == nullptr || (((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ld % ldm == 0); };
@@ -358,13 +445,14 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
         // split-K when it fills the machine better: cost ~ waves x k-blocks per item; ties go to fewer splits
         // (every split adds one atomic pass over the output)
         long best = (long)((tiles + g_num_sms - 1) / g_num_sms) * num_kb;
-        for (int sp = 2; sp <= 16 && sp <= num_kb; ++sp) {
+        for (int sp = 2; sp <= max_splits && sp <= num_kb; ++sp) {
             const long waves = ((long)tiles * sp + g_num_sms - 1) / g_num_sms;
             const long cost = waves * ((num_kb + sp - 1) / sp) + waves;       // + per-item fill/epilogue overhead
             if (cost * 10 < best * 9) { best = cost; p.splits = sp; }          // require >= 10 % gain
         }
     }
-    if (p.splits > 1 && !e.pre_zeroed)    // partial sums are accumulated atomically: the output starts at zero
+    if (splits_out) *splits_out = p.splits;
+    if (p.splits > 1 && !e.pre_zeroed && !e.slab_stride)    // partial sums are accumulated atomically: the output starts at zero
         MMAD_CUDA_OK(cudaMemset2DAsync(e.Y, (size_t)e.ldy * 4, 0, (size_t)N * 4, M, s));
     const int items = tiles * p.splits;
     const int grid = items < g_num_sms ? items : g_num_sms;
@@ -406,6 +494,28 @@ int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int pas
                 t[10] - t[5], t[11] - t[5], t[12] - t[5], t[13] - t[5], t[14] - t[5], t[15] - t[5]);
         last_end = t[7];
     }
+    return MMAD_OK;
+}
+
+// small-batch layer: plain split-K GEMM into slabs (one per split, `slab_stride` elements apart) + the follow-up kernel above
+int gemm_tc_small(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, float* slabs, int ldacc,
+                  long long slab_stride, int max_slabs, cudaStream_t s) {
+    if (e.plain || e.pre || e.sq_self || e.lo_f8 || e.d_lo_f8 || e.col_scale || e.b_upper_tri || (e.rowpart && !e.ref) || ROWPART_COLS != 128) {
+        set_error("gemm_tc_small: epilogue not covered by the follow-up kernel");
+        return MMAD_E_UNSUPPORTED;
+    }
+    Epilogue pe;
+    pe.bias = e.bias; pe.acc_scale = e.acc_scale; pe.acc_comp = e.acc_comp;
+    pe.Y = slabs; pe.ldy = ldacc; pe.y_cols = N; pe.plain = 1; pe.split_k_ok = 1; pe.slab_stride = slab_stride;
+    int splits = 1;
+    int rc = gemm_tc(A, B, M, N, K, passes, pe, s, 128, &splits, std::max(1, std::min(16, max_slabs)));
+    if (rc) return rc;
+    int cols_p = std::max(std::max(e.Y ? e.y_cols : 0, e.Yh ? e.y_cols : 0), e.ref ? std::max(e.d_cols, N) : 0);
+    if (cols_p <= 0) return MMAD_OK;
+    cols_p = (cols_p + 3) & ~3;
+    const int nblk = (cols_p + 127) / 128;
+    MMAD_CUDA_OK(launch_k(epi_follow_kernel, dim3((M * nblk + 7) / 8), dim3(256), 0, s, e, (const float*)slabs, ldacc, M, N, cols_p, splits, slab_stride));
+    MMAD_LAUNCHED();
     return MMAD_OK;
 }
 

@@ -303,7 +303,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             const int row_base = m0 + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             float sq[8];
-            epi_tile<BN>(e, p.M, p.N, p.splits, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
+            epi_tile<BN>(e, p.M, p.N, p.splits, sp, row_base, n0, taddr, stg, s_mul, s_bias, s_sc, s_sh, lane, col_lo, col_hi, sq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even(smem_u32(&acc_empty[acc]));

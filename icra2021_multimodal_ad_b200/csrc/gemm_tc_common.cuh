@@ -212,14 +212,15 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 }
 
 template <int BN>
-__device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
+__device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, int splits, int sp, int row_base, int n0, uint32_t taddr,
                                                float4* stg, const float* s_mul, const float* s_bias, int lane, int col_lo,
                                                int col_hi) {
     int n_cols = N - n0; if (n_cols > BN) n_cols = BN;
     int c_end = (n_cols + 31) & ~31;
     if (c_end > col_hi) c_end = col_hi;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(e.Y) & 15) == 0) && (e.ldy % 4 == 0);
-    const bool atomic = splits > 1;
+    float* const Yb = e.Y + (e.slab_stride ? (size_t)sp * (size_t)e.slab_stride : 0);      // slab of this split, or the one output
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(Yb) & 15) == 0) && (e.ldy % 4 == 0);
+    const bool atomic = splits > 1 && !e.slab_stride;
     const uint32_t stg_s = smem_u32(stg), mul_s = smem_u32(s_mul), bias_s = smem_u32(s_bias);
     for (int c0 = col_lo; c0 < c_end; c0 += 32) {
         uint32_t v[32];
@@ -245,7 +246,7 @@ __device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, 
                     if (r >= M || gc >= N) continue;
                     const float x0 = fmaf(a[it].x, mul.x, bia.x), x1 = fmaf(a[it].y, mul.y, bia.y);
                     const float x2 = fmaf(a[it].z, mul.z, bia.z), x3 = fmaf(a[it].w, mul.w, bia.w);
-                    float* dst = e.Y + (size_t)r * e.ldy + gc;
+                    float* dst = Yb + (size_t)r * e.ldy + gc;
                     if (gc + 3 < N) {
                         if (atomic) red_add_v4(dst, x0, x1, x2, x3);
                         else *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
@@ -278,8 +279,8 @@ __device__ __forceinline__ void epi_tile_plain(const Epilogue& e, int M, int N, 
                     const int r = row_base + ph * 16 + rl;
                     if (r >= M || gc >= N) continue;
                     const float val = fmaf(a[rl], mulc, biac);
-                    if (atomic) atomicAdd(e.Y + (size_t)r * e.ldy + gc, val);
-                    else e.Y[(size_t)r * e.ldy + gc] = val;
+                    if (atomic) atomicAdd(Yb + (size_t)r * e.ldy + gc, val);
+                    else Yb[(size_t)r * e.ldy + gc] = val;
                 }
                 __syncwarp();
             }
@@ -406,13 +407,13 @@ __device__ __forceinline__ void epi_block(const Epilogue& e, const EpiPtrs& q, i
 }
 
 template <int BN>
-__device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int row_base, int n0, uint32_t taddr,
+__device__ __forceinline__ void epi_tile(const Epilogue& e, int M, int N, int splits, int sp, int row_base, int n0, uint32_t taddr,
                                          float4* stg, const float* s_mul, const float* s_bias, const float* s_sc,
                                          const float* s_sh, int lane, int col_lo, int col_hi, float (&sq)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) sq[i] = 0.f;
     if (e.plain) {
-        epi_tile_plain<BN>(e, M, N, splits, row_base, n0, taddr, stg, s_mul, s_bias, lane, col_lo, col_hi);
+        epi_tile_plain<BN>(e, M, N, splits, sp, row_base, n0, taddr, stg, s_mul, s_bias, lane, col_lo, col_hi);
         return;
     }
     const int rsub = lane >> 3;             // 0..3  row inside a group of 4

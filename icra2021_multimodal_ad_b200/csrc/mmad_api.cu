@@ -177,6 +177,7 @@ struct Plan {
     size_t G[MMAD_MAX_LAYERS + 1] = {0};   // decoder outputs, index 1..Ld
     size_t E[MMAD_MAX_LAYERS + 1] = {0};   // enc(xhat) outputs, index 1..L
     size_t rowpart = 0;
+    size_t slab = 0; long long slab_stride = 0; int n_slabs = 0;    // small batches: split-K partial tiles of ONE layer (gemm_tc_small)
     size_t diffs = 0;
     size_t gram32 = 0;
     size_t rot = 0;         // [R, Kp] rotated rows (Standardizer refit pass)
@@ -243,6 +244,13 @@ static int tile_n_for(mmad_t h) {
     return use_tc(h) ? gemm_tc_rowpart_cols() : gemm_simt_tile_n();
 }
 
+constexpr int kSmallTcRowsMax = 1024;
+static int small_tc_rows() {           // <= this many rows: plain split-K GEMM + stand-alone epilogue kernel (gemm_tc_small)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMAD_SMALL_TC_ROWS"); v = e ? std::min(kSmallTcRowsMax, std::max(0, atoi(e))) : 1024; }
+    return v;
+}
+
 static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
     Plan p;
     p.R = R;
@@ -283,6 +291,14 @@ static Plan make_plan(mmad_t h, int R, const PlanOpts& o) {
         for (int l = 1; l <= Ld; ++l) { p.Gh[l] = take(RR * h->dec[l - 1].Np * 2); p.Gl[l] = take(RR * h->dec[l - 1].Np * 2); }
         for (int l = 1; l <= L; ++l) { p.Eh[l] = take(RR * h->enc[l - 1].Np * 2); p.El[l] = take(RR * h->enc[l - 1].Np * 2); }
         if (o.diffs_ws) { p.dh = take(RR * p.Dselp * 2); p.dl = take(RR * p.Dselp * 2); }
+        if (R <= small_tc_rows()) {
+            int max_np = Dp;
+            for (int l = 1; l <= L; ++l) max_np = std::max(max_np, h->enc[l - 1].Np);
+            for (int l = 1; l <= Ld; ++l) max_np = std::max(max_np, h->dec[l - 1].Np);
+            p.n_slabs = R <= 256 ? 16 : (R <= 512 ? 8 : 4);
+            p.slab_stride = (long long)RR * max_np;
+            p.slab = take((size_t)p.n_slabs * p.slab_stride * 4);
+        }
     }
     p.total = off;
     return p;
@@ -337,7 +353,13 @@ static int operand_map(mmad_t h, CUtensorMap* out, const void* base, int rows, i
 // MMA instructions per 64-wide k-block and accumulator in each tensor-core mode (the unit of acc_comp)
 static float instr_per_kb(int passes) { return passes == 3 ? 12.f : passes == 1 ? 4.f : 8.f; }
 
-static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogue e, cudaStream_t s) {
+static bool small_tc(mmad_t h, int rows) {
+    static const bool off = getenv("MMAD_NO_SMALL_TC") != nullptr;
+    return !off && use_tc(h) && h->desc.precision == MMAD_PREC_F16X3 && !nap_f8(h) && rows > 0 && rows <= small_tc_rows();
+}
+
+static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogue e, cudaStream_t s, float* slabs = nullptr,
+                     long long slab_stride = 0, int n_slabs = 0) {
     ProfScope prof(h, s, 2.0 * rows * (double)Lr.N * (double)Lr.K);
     e.bias = Lr.bias;
     if (Lr.has_bn) { e.bn_scale = Lr.scale; e.bn_shift = Lr.shift; }
@@ -365,6 +387,8 @@ static int run_layer(mmad_t h, const Layer& Lr, const Act& in, int rows, Epilogu
     e.d_lo_f8 = nap_f8(h) ? 1 : 0;
     const int passes = tc_passes(h);
     e.acc_comp = (float)(h->acc_comp * instr_per_kb(passes));
+    if (slabs && small_tc(h, rows))      // 128-row weight boxes (tile width 128)
+        return gemm_tc_small(A, Lr.tcB2, rows, Lr.N, Lr.K, passes, e, slabs, Lr.Np, slab_stride, n_slabs, s);
     if (rows >= kPairMinRows && tc2_available()) return gemm_tc2(A, f8 ? Lr.tcB2_f8 : Lr.tcB2, rows, Lr.N, Lr.K, passes, e, s);
     return gemm_tc(A, f8 ? Lr.tcB_f8 : Lr.tcB, rows, Lr.N, Lr.K, passes, e, s);
 }
@@ -399,6 +423,11 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         if (x_aligned) { a0.f = x; a0.ld = ldx; }   // d_0 reads the caller's x directly
     }
     const bool want_enc2 = co.hi > 1 && co.hi > co.lo;   // any d_l with l>=1 requested
+    // small batches: every layer stores its split-K partial tiles into the slab scratch, a follow-up kernel adds them in order
+    const bool small = small_tc(h, rows) && p.n_slabs > 0;
+    float* const slabs = small ? (float*)(ws + p.slab) : nullptr;
+    static const bool no_pdl = getenv("MMAD_NO_PDL") != nullptr;
+    PdlScope pdl_scope(small && !no_pdl);      // a chain of ~30 small dependent kernels: programmatic dependent launches
     // ---- encoder on x ----
     Act cur = a0;
     for (int l = 1; l <= L; ++l) {
@@ -406,7 +435,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
         Epilogue e;
         e.Y = (float*)(ws + p.H[l]); e.ldy = Lr.Np; e.y_cols = Lr.Np;
         if (tc) { e.Yh = (__half*)(ws + p.Hh[l]); e.Yl = (__half*)(ws + p.Hl[l]); e.ldh = Lr.Np; }
-        int rc = run_layer(h, Lr, cur, rows, e, s);
+        int rc = run_layer(h, Lr, cur, rows, e, s, slabs, p.slab_stride, p.n_slabs);
         if (rc) return rc;
         cur = Act{e.Y, Lr.Np, e.Yh, e.Yl, Lr.Np};
     }
@@ -434,7 +463,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
                 if (co.dh) { e.Dh = co.dh; e.Dl = co.dl; e.lddh = co.lddh; e.d_scale = diff_scale(h); }
             }
         }
-        int rc = run_layer(h, Lr, cur, rows, e, s);
+        int rc = run_layer(h, Lr, cur, rows, e, s, slabs, p.slab_stride, p.n_slabs);
         if (rc) return rc;
         cur = Act{e.Y, Lr.Np, e.Yh, e.Yl, Lr.Np};
     }
@@ -460,7 +489,7 @@ static int run_chain(mmad_t h, const float* x, int ldx, int rows, char* ws, cons
             if (co.dh) { e.Dh = co.dh + col_off; e.Dl = co.dl + col_off; e.lddh = co.lddh; e.d_scale = diff_scale(h); }
             col_off += Lr.Np;
         }
-        int rc = run_layer(h, Lr, cur, rows, e, s);
+        int rc = run_layer(h, Lr, cur, rows, e, s, slabs, p.slab_stride, p.n_slabs);
         if (rc) return rc;
         cur = Act{(const float*)(ws + p.E[l]), Lr.Np, (const __half*)(ws + p.Eh[l]), (const __half*)(ws + p.El[l]), Lr.Np};
     }
@@ -866,6 +895,10 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     // same arithmetic at every batch size
     if (h->desc.precision == MMAD_PREC_F16F8 && d_nap) h->skinny = false;
     if (h->desc.precision == MMAD_PREC_F16X3 && d_nap && nap_passes_eff(h) != 3) h->skinny = false;      // same for the optional rotations
+    // F16X3, 17..64 rows, base / SAP only: the split-K tensor-core layers + stand-alone epilogue (gemm_tc_small) take ~9 us per
+    // layer against ~28 us for the weight-streaming kernels (<= 16 rows keep them: exact fp32, and host calls of that size
+    // take the one-launch kernel anyway)
+    if (h->skinny && h->desc.precision == MMAD_PREC_F16X3 && !d_nap && n > 16 && !getenv("MMAD_NO_SMALL_TC")) h->skinny = false;
     // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29) in the fp32 mode: base / SAP
     // scores from ONE fused exact-fp32 kernel (smallnet.cu): 65 / 48 M windows/s at D = 64 / 128 against 29 / 27 M for the
     // per-layer fp32 kernels.  The tensor-core modes keep their per-layer kernels (93 / 92 M windows/s in f16x3).

@@ -109,6 +109,8 @@ struct Epilogue {
     int b_upper_tri = 0;                                // number of leading rows n of B with B[n, k] == 0 for k < n (tensor-core kernels skip those k-blocks)
     int pre_zeroed = 0;                                 // split-K: the caller already zeroed Y (no memset inside gemm_tc)
     int split_k_ok = 0;                                 // plain mode: split-K with atomic accumulation allowed
+    long long slab_stride = 0;                          // plain split-K WITHOUT atomics: split sp stores its partial tile at Y + sp * slab_stride
+                                                        // (elements); the consumer adds the slabs in order -- deterministic, no zeroing
     float y_split_scale = 1.f;                          // Yh/Yl hold the split of (value * y_split_scale)
     // MMAD_PREC_F16F8: Yl / Dl hold the fp8 twin instead of the fp16 lo part -- per 4 columns 8 bytes:
     // 4 x e4m3((v - hi) * 2^11) then 4 x e4m3(v)  (v = value * split scale).  Same bytes per row as the fp16 lo; a
@@ -140,6 +142,11 @@ __host__ __device__ inline int seg_pad_col(const SegMap& m, int c) {
     return m.pad_off[i] + (c - m.tight_off[i]);
 }
 
+// small batches on the tensor cores: plain split-K GEMM into `acc` (zeroed by the caller) + the epilogue as its own kernel (gemm_tc.cu)
+struct TcOperand;
+int gemm_tc_small(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes, const Epilogue& e, float* slabs, int ldacc,
+                  long long slab_stride, int max_slabs, cudaStream_t s);
+
 // CUDA-core fp32 GEMM with the fused epilogue (gemm_simt.cu)
 int gemm_simt(const GemmShape& g, const Epilogue& e, cudaStream_t s);
 int gemm_simt_tile_n();   // columns covered by one rowpart slot
@@ -161,7 +168,8 @@ int tc_make_operand_map(CUtensorMap* map, const __half* base, int rows, int kp, 
 // fp8 twin ([rows, 2 * round_up(k, 64)] bytes, row stride ld_bytes): box = [128 bytes x box_rows]
 int tc_make_operand_map_f8(CUtensorMap* map, const void* base, int rows, int k, int ld_bytes, int box_rows);
 int gemm_tc(const TcOperand& A, const TcOperand& B, int M, int N, int K, int passes,
-            const Epilogue& e, cudaStream_t s, int bn = 256);   // bn: CTA tile width; K-major B maps need box_rows == bn
+            const Epilogue& e, cudaStream_t s, int bn = 256,    // bn: CTA tile width; K-major B maps need box_rows == bn
+            int* splits_out = nullptr, int max_splits = 16);    // split-K factor chosen (plain epilogue), its upper bound
 int gemm_tc_tile_n();                    // the default (256)
 int gemm_tc_rowpart_cols();              // columns per row-partial slot written by the tensor-core epilogues (128)
 int gemm_tc_pick_bn(int M, int N);

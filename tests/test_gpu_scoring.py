@@ -207,8 +207,8 @@ def test_cta_pair_kernel_matches_fp32_on_tall_chunks(D, btl, nl, n):
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("n", [1, 8, 10, 33, 64])
 def test_streaming_batches_take_the_fp32_weight_streaming_path(n, precision):
-    """realtime_tester-style calls (test_file/realtime_tester.py:291-309): up to 32 windows run on the exact-fp32
-    weight-streaming kernels whatever the handle's precision (33 and 64 rows: tensor-core kernels, graph replay);
+    """realtime_tester-style calls (test_file/realtime_tester.py:291-309): up to 16 windows run on exact-fp32 kernels
+    whatever the handle's precision (f16x3, 17+ rows: split-K tensor-core layers + stand-alone epilogue, deterministic);
     device and host entry points, base/SAP/NAP and diffs against the oracle."""
     from oracle import rapp_oracle as RO
     D, btl, nl, seed = 1728, 100, 5, 31
