@@ -13,8 +13,10 @@
  *    mmad_last_error() returns a thread-local message.  No C++ exception crosses.
  *  - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  The caller owns
  *    every buffer; the library allocates device memory only in mmad_create /
- *    mmad_set_layer / mmad_nap_set_fit (packed weights), and lazily in the two host-buffer
- *    entry points that take no workspace (mmad_score_host, mmad_stream_*) -- never in mmad_score.
+ *    mmad_set_layer / mmad_nap_set_fit (packed weights), mmad_peer_create / mmad_peer_grad_alloc (exchange
+ *    buffers), and lazily on first use: in the two host-buffer entry points that take no workspace
+ *    (mmad_score_host, mmad_stream_*) and, for a per-modality model in the fp32 mode, the transposed
+ *    weight copy of the fused whole-chain kernel at its first mmad_score.  Otherwise never in mmad_score.
  *  - scratch comes from a caller-provided workspace sized by the *_workspace_bytes
  *    queries; work is enqueued on the caller's cudaStream_t (passed as void*),
  *    asynchronously, with no implicit synchronisation unless stated.
