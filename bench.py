@@ -372,7 +372,7 @@ def bench_train(dev, local, world, batch, steps, warmup, precision, vib=False):
         loss.backward()
         T.allreduce_gradients(model)
         opt.step()
-        return (float(loss.detach()), )
+        return (T.step_loss(model, loss), )
 
     def timed(x, n):
         for _ in range(warmup):

@@ -97,6 +97,7 @@ SIGNATURES = {
     "mmad_profile_end": (_i, [_vp, C.POINTER(C.c_double)]),
     "mmad_launch_count": (C.c_ulonglong, []),
     "mmad_train_workspace_bytes": (_sz, [_vp, _i]),
+    "mmad_train_loss": (_i, [_vp, _vp]),
     "mmad_train_fwd_bwd": (_i, [_vp, _vp, _i, _i, _ll, C.POINTER(TrainLayer), C.POINTER(TrainLayer), _vp, _f, _f,
                                 _vp, _vp, _sz, ALLREDUCE_FN, _vp, _vp]),
     "mmad_adam_step": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),

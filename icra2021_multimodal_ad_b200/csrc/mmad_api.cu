@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "mmad_internal.cuh"
 
@@ -105,6 +106,11 @@ struct mmad_handle {
     // (mmad_set_option "acc_comp")
     double acc_comp = kAccCompDefault;
     int nap_passes = 0;            // 0 = env MMAD_NAP_PASSES / default 3 (mmad_set_option "nap_passes")
+    // train step: the loss is published to mapped pinned memory as a (value, sequence) pair as soon as the forward pass has
+    // produced it (train.cu loss_publish_kernel), so the host can read it while backward + Adam are still running
+    uint2* h_loss_pair = nullptr; uint2* d_loss_pair = nullptr;
+    unsigned long long* d_loss_seq = nullptr;
+    unsigned long long loss_published = 0;      // publishes enqueued so far
     bool require_pinned = false;   // mmad_score_host rejects pageable bulk input (mmad_set_option "require_pinned")
     // TMA descriptors of workspace operands, keyed by (base, rows, k, ld, kind): encoded once, not per layer per call
     struct MapRec { const void* base; int rows, k, ld, kind; CUtensorMap map; };
@@ -536,6 +542,42 @@ int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev
     return 0;
 }
 
+int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq) {
+    if (!h->h_loss_pair) {
+        if (cudaHostAlloc(&h->h_loss_pair, sizeof(uint2), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&h->d_loss_pair, h->h_loss_pair, 0) != cudaSuccess ||
+            cudaMalloc(&h->d_loss_seq, 8) != cudaSuccess || cudaMemset(h->d_loss_seq, 0, 8) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        h->h_loss_pair->x = 0; h->h_loss_pair->y = 0;
+        cudaDeviceSynchronize();
+    }
+    *d_pair = h->d_loss_pair; *d_seq = h->d_loss_seq;
+    return 0;
+}
+void handle_loss_published(mmad_t h) { ++h->loss_published; }
+int handle_loss_read(mmad_t h, float* out) {
+    if (!h->h_loss_pair || h->loss_published == 0) { set_error("no train step has published a loss on this handle"); return MMAD_E_STATE; }
+    const uint32_t want = (uint32_t)h->loss_published;
+    volatile uint2* p = h->h_loss_pair;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (p->y != want) {
+        __builtin_ia32_pause();
+        if ((++spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+            cudaError_t e = cudaDeviceSynchronize();
+            if (p->y == want) break;
+            set_error("train loss never arrived (%s)", cudaGetErrorString(e));
+            return MMAD_E_CUDA;
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const uint32_t bits = p->x;
+    memcpy(out, &bits, 4);
+    return MMAD_OK;
+}
+
 void handle_graph_clear(mmad_t h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     h->graphs.clear();
@@ -656,6 +698,8 @@ int mmad_destroy(mmad_t h) {
     cudaFree(h->nap.B); cudaFree(h->nap.colscale); cudaFree(h->nap.bias); cudaFree(h->nap.bias_rot);
     cudaFree(h->nap.Bh); cudaFree(h->nap.Bl);
     cudaFree(h->nap.Bh8); cudaFree(h->nap.B8); cudaFree(h->nap.d_wscale8);
+    if (h->h_loss_pair) cudaFreeHost(h->h_loss_pair);
+    cudaFree(h->d_loss_seq);
     cudaFree(h->host_ws);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->host_x[i]); cudaFree(h->host_out[i]);

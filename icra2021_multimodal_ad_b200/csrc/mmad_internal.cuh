@@ -224,6 +224,10 @@ bool peer_ready(mmad_t h);
 int peer_max_doubles();
 int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s);
 bool peer_grads_match(mmad_t h, const void* d_buf, long long count);
+// train step: early publication of the loss to mapped pinned memory (mmad_api.cu)
+int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq);
+void handle_loss_published(mmad_t h);
+int handle_loss_read(mmad_t h, float* out);
 int peer_allreduce_grads(mmad_t h, cudaStream_t s);
 
 // Every rank's exchange buffer as mapped by this rank (cudaIpc), [2 sets][world slots][2 * kPeerMaxDoubles] (data, tag) pairs

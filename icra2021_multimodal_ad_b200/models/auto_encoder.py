@@ -101,7 +101,8 @@ class AutoEncoder(AbstractModel):
         loss = engine.model.get_loss_value(x, x)
         loss.backward(retain_graph=True)
         engine.optimizer.step()
-        return (float(loss.detach()), )
+        from ..train import step_loss
+        return (step_loss(engine.model, loss), )     # float(loss) without waiting for backward + Adam (train.step_loss)
 
     @staticmethod
     def validate(engine, mini_batch):

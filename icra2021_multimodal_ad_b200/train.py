@@ -337,4 +337,20 @@ def fused_train_loss(model, x: torch.Tensor, eps: Optional[torch.Tensor] = None,
             # own storage so autograd's accumulation (zero_grad(set_to_none=False) callers) stays correct
             if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
                 p.grad = p.grad.clone()
-    return _FusedStep.apply(model, x, eps, beta_kl, st.anchor)
+    out = _FusedStep.apply(model, x, eps, beta_kl, st.anchor)
+    st.last_loss = out          # step_loss() recognises the tensor the step produced
+    return out
+
+
+def step_loss(model, loss: torch.Tensor) -> float:
+    """``float(loss)`` for the loss tensor ``fused_train_loss`` just returned, WITHOUT waiting for the backward pass, the
+    optimizer and whatever else is queued on the stream: the step publishes the value to mapped pinned memory as soon as
+    its forward pass has it (``mmad_train_loss``).  ``AutoEncoder.step`` returns the loss every step
+    (models/auto_encoder.py:77); read through the stream, the host would only get back to launching the next step after the
+    GPU has gone idle.  Any other tensor (a scaled loss, a validation loss) takes the ordinary ``float()``."""
+    st = getattr(model, "_train_state", None)
+    if st is None or getattr(st, "last_loss", None) is not loss:
+        return float(loss.detach())
+    out = C.c_float()
+    check(lib().mmad_train_loss(model.handle_engine()._h, C.byref(out)))
+    return float(out.value)

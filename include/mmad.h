@@ -262,6 +262,11 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
                        const float* d_eps, float beta_kl, float bn_momentum,
                        float* d_loss, void* d_ws, size_t ws_bytes,
                        mmad_allreduce_fn allreduce, void* allreduce_ctx, void* stream);
+/* The loss of the LAST mmad_train_fwd_bwd enqueued on this handle, read from a (value, sequence) pair in mapped pinned memory
+ * that the step publishes as soon as its forward pass has produced the loss -- i.e. without waiting for the backward pass
+ * and whatever else is queued behind it (AutoEncoder.step returns float(loss) every step, models/auto_encoder.py:77; through
+ * the stream that read is a wait for the whole step).  Blocks (polling) until the value has arrived. */
+int mmad_train_loss(mmad_t h, float* h_loss);
 /* torch.optim.Adam (novelty_detection.py:90) over a flat list of tensors, one launch. */
 int mmad_adam_step(int n_tensors, float* const* h_params, float* const* h_grads, float* const* h_m,
                    float* const* h_v, const long long* h_numel, int step, float lr, float beta1,
