@@ -141,6 +141,10 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
     import os
     import torch.distributed as dist
     st = train_state(model)
+    if getattr(st, "peer_grads", False):
+        # a previous call moved the flat gradient buffer into library-owned memory, which the calls below free or replace:
+        # back to a torch-owned buffer first, so that nothing ever points at freed memory
+        _own_gradient_buffer(st)
     st.group = group
     st.world = dist.get_world_size(group) if dist.is_initialized() else 1
     st.native = False
@@ -194,6 +198,23 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
     return st
 
 
+def _rebind_gradient_views(st, flat):
+    st.flat_grad = flat
+    st.views, off = [], 0
+    pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
+    for p in st.params:
+        st.views.append(flat[off:off + p.numel()].view_as(p))
+        off += pad4(p.numel())
+        p.grad = None
+    st.view_of = {id(p): v for p, v in zip(st.params, st.views)}
+    st._tables = None
+
+
+def _own_gradient_buffer(st):
+    _rebind_gradient_views(st, torch.zeros(st.flat_grad.numel(), dtype=torch.float32, device=st.params[0].device))
+    st.peer_grads = False
+
+
 class _DevicePtr:
     """A library-owned device buffer as seen by ``torch.as_tensor`` (zero copy; torch keeps this object alive)."""
 
@@ -231,15 +252,7 @@ def _peer_gradient_buffer(st, eng, group, dev):
     n4 = (n + 3) // 4 * 4
     flat = torch.as_tensor(_DevicePtr(ptr.value, n4), device=dev)
     assert flat.data_ptr() == ptr.value
-    st.flat_grad = flat
-    st.views, off = [], 0
-    pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
-    for p in st.params:
-        st.views.append(flat[off:off + p.numel()].view_as(p))
-        off += pad4(p.numel())
-        p.grad = None
-    st.view_of = {id(p): v for p, v in zip(st.params, st.views)}
-    st._tables = None
+    _rebind_gradient_views(st, flat)
 
 
 def _check_native_comm(st, eng):
