@@ -55,9 +55,10 @@ constexpr int kGradThreads = 512;
 //                  bypassed), adds them in a fixed order (peers r+1, r+2, ..., itself) and STORES the sum into chunk r of every rank's buffer -- nobody else reads
 //                  or writes chunk r, so the two phases of a textbook reduce-scatter + all-gather need no barrier between them;
 //   exit barrier   system-scope fence, the last CTA flags "my chunk is everywhere" to all peers and waits for theirs.
-// Each rank moves (world-1)/world of the vector in each direction once: 17.5 MB at 8 GPUs for the 20 MB of the benchmark
+// Each rank moves (world-1)/world of the vector in each direction once: 35.8 MB at 8 GPUs for the 40.9 MB of the benchmark
 // model.  Measured in the data-parallel step at B = 256 per GPU: +14 us at 2 GPUs (ncclAllReduce +32 us), +139 us at 8
-// (ncclAllReduce +251 us) before the peer order was rotated.  Every rank receives the same sums: the replicas stay
+// (ncclAllReduce +251 us) before the peer order was rotated, +44 us after (0.81 TB/s per direction: the NVLink 5 rate).
+// Every rank receives the same sums: the replicas stay
 // bit-identical.  All polls are bounded (trap, not hang).
 __global__ void __launch_bounds__(kGradThreads)
 peer_allreduce_f32_kernel(const GradPtrs G, long long n4, unsigned long long* __restrict__ seq_ctr, unsigned int* __restrict__ done_ctr) {
