@@ -945,7 +945,7 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
     if (h->skinny && h->desc.precision == MMAD_PREC_F16X3 && !d_nap && n > 16 && !getenv("MMAD_NO_SMALL_TC")) h->skinny = false;
     // per-modality models (every width <= 128: force_torque, mic; utils/data_loaders.py:16-29) in the fp32 mode: base / SAP
     // scores from ONE fused exact-fp32 kernel (smallnet.cu): 65 / 48 M windows/s at D = 64 / 128 against 29 / 27 M for the
-    // per-layer fp32 kernels.  The tensor-core modes keep their per-layer kernels (93 / 92 M windows/s in f16x3).
+    // per-layer fp32 kernels.
     if (n > 0 && !d_nap && !d_diffs && h->smallnet && h->desc.precision == MMAD_PREC_FP32 && !h->prof && smallnet_enabled() &&
         smallnet_fits(h) && d_x && (ldx % 4 == 0) &&
         ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) && !check_range(h, lo, hi)) {
@@ -953,7 +953,8 @@ int mmad_score(mmad_t h, const float* d_x, int ldx, int n, int lo, int hi, float
         if (rc != MMAD_E_UNSUPPORTED) { h->skinny = false; return rc; }      // (plan not built while the stream is capturing)
     }
     // ... and in the F16X3 mode from ONE fused tensor-core kernel (smallnet_tc.cu): weights and activations in shared memory,
-    // accumulators in TMEM, nothing but x and the scores in HBM.  Calls of <= 64 rows keep the exact-fp32 small-batch kernels.
+    // accumulators in TMEM, nothing but x and the scores in HBM: 391 / 369 M windows/s at D = 64 / 128 against 93 / 92 M for the
+    // per-layer tensor-core kernels.  Calls of <= 64 rows keep the small-batch kernels.
     if (n > 64 && !d_nap && !d_diffs && h->smallnet && h->desc.precision == MMAD_PREC_F16X3 && !h->prof && smallnet_enabled() &&
         smallnet_fits(h) && tc_available() && d_x && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ldx >= D_of(h) &&
         !check_range(h, lo, hi)) {
