@@ -130,14 +130,17 @@ def set_data_parallel(model, group=None, native: Optional[bool] = None, overlap_
     itself, so the data-parallel step is one CUDA-graph replay.  Otherwise ``torch.distributed.all_reduce`` is
     called back from inside the step (works with any backend).
 
-    peer (default: env MMAD_NO_PEER != 1): the 32 BatchNorm-statistics exchanges of a step (<= 2 x 1408 doubles each,
-    strictly serialised with the layer chain) run as one-kernel exchanges over NVLink peer memory (``mmad_peer_*``: every
-    rank maps every other rank's buffer through cudaIpc) instead of ncclAllReduce.  Falls back to NCCL if the GPUs cannot
-    map each other.
+    peer (default: env MMAD_NO_PEER != 1): both collectives of the step run over NVLink peer memory (``mmad_peer_*``: every
+    rank maps every other rank's buffers through cudaIpc) instead of NCCL -- the 16 BatchNorm-statistics exchanges
+    (<= 2 x 1408 doubles each, strictly serialised with the layer chain) INSIDE the one-kernel BatchNorm forward / backward
+    (batches <= 512 rows; separate one-kernel exchanges above that), and the flat gradient all-reduce as one kernel per rank
+    (the gradient buffer then lives in library-owned, peer-mapped memory; env MMAD_NO_PEER_GRADS=1 keeps it in torch memory
+    and on NCCL).  Falls back to NCCL if the GPUs cannot map each other.
     overlap_grads (default off): the gradients are all-reduced inside the captured step in two buckets on the second
     stream, the decoder's while the encoder's backward pass still runs; ``allreduce_gradients`` is then a no-op.  Measured
-    at B = 256 per GPU (scripts/dp_ablation.py): no better than ONE flat all-reduce after the step at 2 GPUs (0.987 vs
-    0.998 ms) and worse at 8 (1.232 vs 1.168 ms) -- the overlapped collective takes SMs from a chain of 15-us GEMMs."""
+    at B = 256 per GPU at the start of round 2 (scripts/dp_ablation.py): no better than ONE flat all-reduce after the step at
+    2 GPUs (0.987 vs 0.998 ms) and worse at 8 (1.232 vs 1.168 ms) -- the overlapped collective takes SMs from a chain of
+    small GEMMs.  (The shipped default now runs the step in 0.55 / 0.63 ms at 2 / 8 GPUs)"""
     import os
     import torch.distributed as dist
     st = train_state(model)
