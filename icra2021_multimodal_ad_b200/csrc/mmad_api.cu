@@ -542,7 +542,8 @@ int handle_aux(mmad_t h, cudaStream_t* s2, cudaEvent_t* ev_fork, cudaEvent_t* ev
     return 0;
 }
 
-int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq) {
+int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq, bool allocate) {
+    if (!h->h_loss_pair && !allocate) return 1;
     if (!h->h_loss_pair) {
         if (cudaHostAlloc(&h->h_loss_pair, sizeof(uint2), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&h->d_loss_pair, h->h_loss_pair, 0) != cudaSuccess ||

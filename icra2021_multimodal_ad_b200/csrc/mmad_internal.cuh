@@ -225,7 +225,7 @@ int peer_max_doubles();
 int peer_allreduce_f64(mmad_t h, double* d_buf, long long count, cudaStream_t s);
 bool peer_grads_match(mmad_t h, const void* d_buf, long long count);
 // train step: early publication of the loss to mapped pinned memory (mmad_api.cu)
-int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq);
+int handle_loss_doorbell(mmad_t h, uint2** d_pair, unsigned long long** d_seq, bool allocate);   // 0: available
 void handle_loss_published(mmad_t h);
 int handle_loss_read(mmad_t h, float* out);
 int peer_allreduce_grads(mmad_t h, cudaStream_t s);

@@ -817,7 +817,7 @@ size_t mmad_train_workspace_bytes(mmad_t h, int batch) {
 static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool tc, bool vib, int batch, long long global_batch,
                       const mmad_train_layer_t* enc, const mmad_train_layer_t* dec, float beta_kl, float bn_momentum,
                       float* d_loss, char* ws, mmad_allreduce_fn allreduce, void* allreduce_ctx, cudaStream_t s,
-                      cudaStream_t s2, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                      cudaStream_t s2, cudaEvent_t ev_fork, cudaEvent_t ev_join, bool publish) {
     bool forked = false;
     // cross-rank combination of the BatchNorm statistics: caller's hook, or the handle's own NCCL communicator
     void* comm_p = nullptr; int comm_world = 1;
@@ -1042,7 +1042,7 @@ static int train_body(mmad_t h, const mmad_desc_t& d, const TrainPlan& p, bool t
             MMAD_LAUNCHED();
         }
         uint2* d_pair = nullptr; unsigned long long* d_seq = nullptr;
-        if (!handle_loss_doorbell(h, &d_pair, &d_seq)) {          // (allocated by mmad_train_fwd_bwd before any capture)
+        if (publish && !handle_loss_doorbell(h, &d_pair, &d_seq, false)) {      // (allocated by mmad_train_fwd_bwd, outside any capture)
             MMAD_CUDA_OK(launch_k(loss_publish_kernel, dim3(1), dim3(1), 0, s, (const float*)d_loss, d_pair, d_seq));
             MMAD_LAUNCHED();
         }
@@ -1269,12 +1269,12 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
     const bool use_graph = !allreduce && graphs_enabled() && cap == cudaStreamCaptureStatusNone;
     // the loss doorbell (mapped pinned pair + device sequence counter) is allocated here, outside any capture
     uint2* bell_pair = nullptr; unsigned long long* bell_seq = nullptr;
-    const bool bell = cap == cudaStreamCaptureStatusNone && !handle_loss_doorbell(h, &bell_pair, &bell_seq);
+    const bool bell = cap == cudaStreamCaptureStatusNone && !handle_loss_doorbell(h, &bell_pair, &bell_seq, true);
     {
         cudaStream_t s2 = nullptr; cudaEvent_t ef = nullptr, ej = nullptr;
         if (tc && handle_aux(h, &s2, &ef, &ej)) s2 = nullptr;
         if (!use_graph) {
-            rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, allreduce, allreduce_ctx, s, s2, ef, ej);
+            rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, allreduce, allreduce_ctx, s, s2, ef, ej, bell);
             if (!rc && bell) handle_loss_published(h);
             return rc;
         }
@@ -1296,7 +1296,7 @@ int mmad_train_fwd_bwd(mmad_t h, const float* d_x, int ldx, int batch, long long
         MMAD_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
         cudaStream_t s2 = nullptr; cudaEvent_t ef = nullptr, ej = nullptr;
         if (tc && handle_aux(h, &s2, &ef, &ej)) s2 = nullptr;
-        rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, nullptr, nullptr, cs, s2, ef, ej);
+        rc = train_body(h, d, p, tc, vib, batch, global_batch, enc, dec, beta_kl, bn_momentum, d_loss, ws, nullptr, nullptr, cs, s2, ef, ej, bell);
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         n_launch = g_launches - l0;

@@ -368,5 +368,6 @@ def step_loss(model, loss: torch.Tensor) -> float:
     if st is None or getattr(st, "last_loss", None) is not loss:
         return float(loss.detach())
     out = C.c_float()
-    check(lib().mmad_train_loss(model.handle_engine()._h, C.byref(out)))
+    if lib().mmad_train_loss(model.handle_engine()._h, C.byref(out)) != 0:
+        return float(loss.detach())      # nothing was published (the step ran inside a caller's own stream capture)
     return float(out.value)
