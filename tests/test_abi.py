@@ -118,3 +118,35 @@ def test_precision_modes_match_the_header():
     d.precision = max(enum.values()) + 1
     assert L.mmad_create(ctypes.byref(d), ctypes.byref(h)) == -1
     assert b"precision" in L.mmad_last_error()
+
+
+def test_round2_entry_points_reject_bad_arguments_without_gpu():
+    """Argument checking of the entry points added in round 2 happens before any device call."""
+    L = _lib.lib()
+    out = ctypes.c_float()
+    assert L.mmad_train_loss(None, ctypes.byref(out)) == -1
+    hb = (ctypes.c_ubyte * 64)()
+    ptr = ctypes.c_void_p()
+    assert L.mmad_peer_grad_alloc(None, 16, ctypes.byref(ptr), hb) == -1
+    assert L.mmad_peer_grad_open(None, hb) == -1
+    assert L.mmad_peer_close(None) == 0
+    assert L.mmad_set_option(None, b"nap_passes", 4.0) == -1
+
+
+def test_step_loss_falls_back_to_float_for_foreign_tensors():
+    """train.step_loss reads the doorbell only for the tensor the fused step itself returned; any other tensor (a scaled
+    loss, a validation loss, a CPU tensor) is read the ordinary way."""
+    import types
+    import torch
+    from icra2021_multimodal_ad_b200 import train as T
+    model = types.SimpleNamespace()                       # no _train_state at all
+    assert T.step_loss(model, torch.tensor(2.5)) == 2.5
+    model._train_state = types.SimpleNamespace(last_loss=torch.tensor(1.0))
+    assert T.step_loss(model, torch.tensor(3.5)) == 3.5   # not the tensor of the last step
+
+
+def test_device_pointer_wrapper_describes_a_flat_fp32_buffer():
+    """The library-owned, peer-mapped gradient buffer reaches torch through __cuda_array_interface__ (zero copy)."""
+    from icra2021_multimodal_ad_b200.train import _DevicePtr
+    cai = _DevicePtr(0x7f0000000000, 1024).__cuda_array_interface__
+    assert cai["shape"] == (1024,) and cai["typestr"] == "<f4" and cai["data"] == (0x7f0000000000, False) and cai["version"] == 2
